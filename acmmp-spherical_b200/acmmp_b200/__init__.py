@@ -1,0 +1,338 @@
+"""ctypes binding of libacmmp_b200.so (the C ABI declared in include/acmmp_b200.h).
+
+Used by tests/, bench.py and __graft_entry__.py.  The product's host side is the C++ `ACMMP`
+class in ../host (same surface as the reference's ACMMP.h:57-111); this module is the thin
+Python view of the same C ABI.  There is no CPU fallback: if the shared object is missing,
+importing `lib()` raises, and without an sm_100 device `Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent.parent
+LIB_PATH = PKG_DIR / "lib" / "libacmmp_b200.so"
+
+MODEL_PINHOLE = 0
+MODEL_SPHERE = 11
+
+
+class Camera(C.Structure):
+    """Mirror of the reference `struct Camera` (main.h:40-54), 120 bytes."""
+    _fields_ = [
+        ("model", C.c_int32),
+        ("params", C.c_float * 4),
+        ("R", C.c_float * 9),
+        ("t", C.c_float * 3),
+        ("K", C.c_float * 9),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("depth_min", C.c_float),
+        ("depth_max", C.c_float),
+    ]
+
+
+class Params(C.Structure):
+    """Mirror of the reference `struct PatchMatchParams` (ACMMP.h:32-55), 68 bytes."""
+    _fields_ = [
+        ("max_iterations", C.c_int32), ("patch_size", C.c_int32), ("num_images", C.c_int32),
+        ("max_image_size", C.c_int32), ("radius_increment", C.c_int32),
+        ("sigma_spatial", C.c_float), ("sigma_color", C.c_float), ("top_k", C.c_int32),
+        ("baseline", C.c_float), ("depth_min", C.c_float), ("depth_max", C.c_float),
+        ("disparity_min", C.c_float), ("disparity_max", C.c_float),
+        ("scaled_cols", C.c_float), ("scaled_rows", C.c_float),
+        ("geom_consistency", C.c_uint8), ("planar_prior", C.c_uint8), ("multi_geometry", C.c_uint8),
+        ("hierarchy", C.c_uint8), ("upsample", C.c_uint8), ("pad_", C.c_uint8 * 3),
+    ]
+
+
+assert C.sizeof(Camera) == 120 and C.sizeof(Params) == 68
+
+
+def make_camera(model, R, t, K=None, sphere=None, width=0, height=0, depth_min=0.0, depth_max=0.0) -> Camera:
+    cam = Camera()
+    cam.model = model
+    R = np.asarray(R, dtype=np.float32).reshape(9)
+    t = np.asarray(t, dtype=np.float32).reshape(3)
+    for i in range(9):
+        cam.R[i] = float(R[i])
+    for i in range(3):
+        cam.t[i] = float(t[i])
+    if K is not None:
+        K = np.asarray(K, dtype=np.float32).reshape(9)
+        for i in range(9):
+            cam.K[i] = float(K[i])
+    if sphere is not None:
+        for i, v in enumerate(sphere):
+            cam.params[i] = float(v)
+    cam.width, cam.height = int(width), int(height)
+    cam.depth_min, cam.depth_max = float(depth_min), float(depth_max)
+    return cam
+
+
+_EXPORTS = [
+    "acmmp_default_params", "acmmp_version", "acmmp_abi_sizeof_camera", "acmmp_abi_sizeof_params",
+    "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
+    "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
+    "acmmp_get_params", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
+    "acmmp_set_hierarchy_inputs", "acmmp_set_planar_prior_inputs", "acmmp_set_seed",
+    "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_random_init", "acmmp_checkerboard_pass",
+    "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
+    "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_download_state", "acmmp_upload_state",
+    "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_geom", "acmmp_probe_warp",
+    "acmmp_probe_initcost", "acmmp_last_timings", "acmmp_launch_count",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libacmmp_b200.so; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    l = C.CDLL(str(LIB_PATH))
+    for name in _EXPORTS:
+        getattr(l, name)          # AttributeError when the library does not export a declared symbol
+    l.acmmp_version.restype = C.c_char_p
+    l.acmmp_last_error.restype = C.c_char_p
+    l.acmmp_last_error.argtypes = [C.c_void_p]
+    l.acmmp_launch_count.restype = C.c_int64
+    l.acmmp_launch_count.argtypes = [C.c_void_p]
+    l.acmmp_set_seed.argtypes = [C.c_void_p, C.c_uint64]
+    for name in _EXPORTS:
+        fn = getattr(l, name)
+        if fn.argtypes is None and name not in ("acmmp_version", "acmmp_abi_sizeof_camera", "acmmp_abi_sizeof_params"):
+            fn.argtypes = None    # variadic-style: rely on explicit ctypes values at call sites
+    _lib = l
+    return l
+
+
+def exported_symbols():
+    return list(_EXPORTS)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class AcmmpError(RuntimeError):
+    pass
+
+
+class Context:
+    """One reference view being processed (== one reference `ACMMP` object)."""
+
+    def __init__(self, device: int = 0):
+        self._l = lib()
+        self._h = C.c_void_p()
+        rc = self._l.acmmp_create(C.byref(self._h), C.c_int(device))
+        if rc != 0:
+            raise AcmmpError(f"acmmp_create failed with {rc}: no usable sm_100 CUDA device (no CPU fallback exists)")
+        self._keep = []
+        self.W = self.H = 0
+        self.n = 0
+
+    def close(self):
+        if self._h:
+            self._l.acmmp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self._l.acmmp_last_error(self._h)
+            raise AcmmpError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ---- inputs -------------------------------------------------------------------------
+    def set_views(self, images, cams):
+        n = len(images)
+        imgs = [_f32(im) for im in images]
+        ptrs = (C.POINTER(C.c_float) * n)(*[_fp(im) for im in imgs])
+        ws = (C.c_int32 * n)(*[im.shape[1] for im in imgs])
+        hs = (C.c_int32 * n)(*[im.shape[0] for im in imgs])
+        carr = (Camera * n)(*cams)
+        self._ck(self._l.acmmp_set_views(self._h, C.c_int(n), ptrs, ws, hs, carr), "acmmp_set_views")
+        self.H, self.W = imgs[0].shape
+        self.n = n
+
+    def set_views_device(self, dev_ptrs, widths, heights, cams):
+        n = len(dev_ptrs)
+        ptrs = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in dev_ptrs])
+        ws = (C.c_int32 * n)(*widths)
+        hs = (C.c_int32 * n)(*heights)
+        carr = (Camera * n)(*cams)
+        self._ck(self._l.acmmp_set_views_device(self._h, C.c_int(n), ptrs, ws, hs, carr), "acmmp_set_views_device")
+        self.H, self.W = int(heights[0]), int(widths[0])
+        self.n = n
+
+    def set_geom_consistency(self, multi_geometry=False):
+        self._ck(self._l.acmmp_set_geom_consistency(self._h, C.c_int(1 if multi_geometry else 0)), "set_geom")
+
+    def set_hierarchy(self):
+        self._ck(self._l.acmmp_set_hierarchy(self._h), "set_hierarchy")
+
+    def set_planar_prior(self):
+        self._ck(self._l.acmmp_set_planar_prior(self._h), "set_planar_prior")
+
+    def set_max_iterations(self, n):
+        self._ck(self._l.acmmp_set_max_iterations(self._h, C.c_int(n)), "set_max_iterations")
+
+    def params(self) -> Params:
+        p = Params()
+        self._ck(self._l.acmmp_get_params(self._h, C.byref(p)), "get_params")
+        return p
+
+    def set_depth_maps(self, maps):
+        n = len(maps)
+        ms = [_f32(m) for m in maps]
+        ptrs = (C.POINTER(C.c_float) * n)(*[_fp(m) for m in ms])
+        ws = (C.c_int32 * n)(*[m.shape[1] for m in ms])
+        hs = (C.c_int32 * n)(*[m.shape[0] for m in ms])
+        self._ck(self._l.acmmp_set_depth_maps(self._h, C.c_int(n), ptrs, ws, hs), "acmmp_set_depth_maps")
+
+    def set_depth_maps_device(self, dev_ptrs, widths, heights):
+        n = len(dev_ptrs)
+        ptrs = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in dev_ptrs])
+        ws = (C.c_int32 * n)(*widths)
+        hs = (C.c_int32 * n)(*heights)
+        self._ck(self._l.acmmp_set_depth_maps_device(self._h, C.c_int(n), ptrs, ws, hs), "acmmp_set_depth_maps_device")
+
+    def set_planes(self, planes4, costs):
+        p, c = _f32(planes4), _f32(costs)
+        self._ck(self._l.acmmp_set_planes(self._h, _fp(p), _fp(c)), "acmmp_set_planes")
+
+    def set_hierarchy_inputs(self, coarse_planes4, fine_depth):
+        cp, fd = _f32(coarse_planes4), _f32(fine_depth)
+        sh, sw = cp.shape[0], cp.shape[1]
+        self._ck(self._l.acmmp_set_hierarchy_inputs(self._h, _fp(cp), C.c_int(sw), C.c_int(sh), _fp(fd)),
+                 "acmmp_set_hierarchy_inputs")
+
+    def set_planar_prior_inputs(self, plane_params4, masks):
+        pp = _f32(plane_params4).reshape(-1, 4)
+        mk = _f32(masks)
+        self._ck(self._l.acmmp_set_planar_prior_inputs(self._h, _fp(pp), C.c_int(pp.shape[0]), _fp(mk)),
+                 "acmmp_set_planar_prior_inputs")
+
+    def set_seed(self, seed):
+        self._ck(self._l.acmmp_set_seed(self._h, C.c_uint64(seed)), "acmmp_set_seed")
+
+    def set_plane_now_semantics(self, as_compiled: bool):
+        self._ck(self._l.acmmp_set_plane_now_semantics(self._h, C.c_int(1 if as_compiled else 0)), "set_plane_now_semantics")
+
+    # ---- compute ------------------------------------------------------------------------
+    def run_patch_match(self):
+        self._ck(self._l.acmmp_run_patch_match(self._h), "acmmp_run_patch_match")
+
+    def random_init(self):
+        self._ck(self._l.acmmp_random_init(self._h), "acmmp_random_init")
+
+    def checkerboard_pass(self, colour, it):
+        self._ck(self._l.acmmp_checkerboard_pass(self._h, C.c_int(colour), C.c_int(it)), "acmmp_checkerboard_pass")
+
+    def finalize(self):
+        self._ck(self._l.acmmp_finalize(self._h), "acmmp_finalize")
+
+    def synchronize(self):
+        self._ck(self._l.acmmp_synchronize(self._h), "acmmp_synchronize")
+
+    def get_result(self):
+        planes = np.empty((self.H, self.W, 4), np.float32)
+        costs = np.empty((self.H, self.W), np.float32)
+        self._ck(self._l.acmmp_get_result(self._h, _fp(planes), _fp(costs)), "acmmp_get_result")
+        return planes, costs
+
+    def device_buffers(self):
+        p, c = C.c_void_p(), C.c_void_p()
+        self._ck(self._l.acmmp_device_buffers(self._h, C.byref(p), C.byref(c)), "acmmp_device_buffers")
+        return p.value, c.value
+
+    def export_depth_device(self, dev_ptr):
+        self._ck(self._l.acmmp_export_depth_device(self._h, C.c_void_p(int(dev_ptr))), "acmmp_export_depth_device")
+
+    def download_state(self, rand=True, pre_costs=True):
+        planes = np.empty((self.H, self.W, 4), np.float32)
+        costs = np.empty((self.H, self.W), np.float32)
+        views = np.empty((self.H, self.W), np.uint32)
+        rand6 = np.empty((self.H, self.W, 6), np.uint32) if rand else None
+        pre = np.empty((self.H, self.W), np.float32) if pre_costs else None
+        self._ck(self._l.acmmp_download_state(
+            self._h, _fp(planes), _fp(costs), views.ctypes.data_as(C.POINTER(C.c_uint32)),
+            rand6.ctypes.data_as(C.POINTER(C.c_uint32)) if rand else None,
+            _fp(pre) if pre_costs else None), "acmmp_download_state")
+        return dict(planes=planes, costs=costs, views=views, rand=rand6, pre_costs=pre)
+
+    def upload_state(self, planes=None, costs=None, views=None, rand=None, pre_costs=None):
+        keep = []
+
+        def fp(a, dt, ct):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(ct))
+        self._ck(self._l.acmmp_upload_state(self._h, fp(planes, np.float32, C.c_float), fp(costs, np.float32, C.c_float),
+                                            fp(views, np.uint32, C.c_uint32), fp(rand, np.uint32, C.c_uint32),
+                                            fp(pre_costs, np.float32, C.c_float)), "acmmp_upload_state")
+
+    # ---- probes -------------------------------------------------------------------------
+    def probe_ncc(self, planes4, view):
+        p = _f32(planes4)
+        out = np.empty((self.H, self.W), np.float32)
+        self._ck(self._l.acmmp_probe_ncc(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_ncc")
+        return out
+
+    def probe_geom(self, planes4, view):
+        p = _f32(planes4)
+        out = np.empty((self.H, self.W), np.float32)
+        self._ck(self._l.acmmp_probe_geom(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_geom")
+        return out
+
+    def probe_warp(self, planes4, view):
+        p = _f32(planes4)
+        out = np.empty((self.H, self.W, 4), np.float32)
+        self._ck(self._l.acmmp_probe_warp(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_warp")
+        return out
+
+    def probe_initcost(self, planes4):
+        p = _f32(planes4)
+        out = np.empty((self.H, self.W), np.float32)
+        views = np.empty((self.H, self.W), np.uint32)
+        self._ck(self._l.acmmp_probe_initcost(self._h, _fp(p), _fp(out), views.ctypes.data_as(C.POINTER(C.c_uint32))),
+                 "acmmp_probe_initcost")
+        return out, views
+
+    def timings(self):
+        t = (C.c_float * 8)()
+        self._ck(self._l.acmmp_last_timings(self._h, t), "acmmp_last_timings")
+        return dict(init_ms=t[0], pass_sum_ms=t[1], finalize_ms=t[2], n_pass=int(t[3]), last_pass_ms=t[4])
+
+    def launch_count(self):
+        return int(self._l.acmmp_launch_count(self._h))
+
+
+def jbu(image, coarse_depth, device=0):
+    """Joint-bilateral upsampling of a coarse depth map (replaces RunJBU, ACMMP.cpp:1071-1122)."""
+    l = lib()
+    img, dep = _f32(image), _f32(coarse_depth)
+    out = np.empty_like(img)
+    rc = l.acmmp_jbu(C.c_int(device), _fp(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _fp(dep),
+                     C.c_int(dep.shape[1]), C.c_int(dep.shape[0]), _fp(out))
+    if rc != 0:
+        raise AcmmpError(f"acmmp_jbu failed ({rc})")
+    return out

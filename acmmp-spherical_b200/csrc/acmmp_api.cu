@@ -1,0 +1,1071 @@
+// acmmp_api.cu -- host side of libacmmp_b200.so: context, uploads, launch logic, C ABI.
+//
+// Replaces the device-facing half of the reference host class: ACMMP::CudaSpaceInitialization
+// (ACMMP.cpp:681-845), ACMMP::CudaPlanarPriorInitialization (:847-867), ACMMP::RunPatchMatch
+// (ACMMP.cu:1506-1556), RunJBU / JBU::CudaRun (ACMMP.cpp:1071-1122, ACMMP.cu:1617-1649).
+// No CPU fallback exists: without a usable CUDA device every compute entry point fails.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/acmmp_b200.h"
+#include "acmmp_kernels.cuh"
+
+using namespace acmmp;
+
+static_assert(sizeof(acmmp_camera) == 120, "acmmp_camera must mirror the reference Camera (main.h:40-54)");
+static_assert(sizeof(acmmp_params) == 68, "acmmp_params must mirror PatchMatchParams (ACMMP.h:32-55)");
+
+// ---------------------------------------------------------------------------------------------
+// XORWOW sequence skipping on the host: state(y) = T^y state(0), T = (one step)^(2^67) over GF(2)
+// (what curand_init's _skipahead_sequence does with precalc_xorwow_matrix, curand_kernel.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Bits160 {
+    uint32_t w[5];
+};
+
+struct XorwowSkip {
+    Bits160 rows[160];     // rows[r] = image of basis vector r
+};
+
+inline Bits160 xorwow_step(const Bits160 &s)
+{
+    const uint32_t t = s.w[0] ^ (s.w[0] >> 2);
+    Bits160 o;
+    o.w[0] = s.w[1]; o.w[1] = s.w[2]; o.w[2] = s.w[3]; o.w[3] = s.w[4];
+    o.w[4] = (s.w[4] ^ (s.w[4] << 4)) ^ (t ^ (t << 1));
+    return o;
+}
+
+inline Bits160 mat_apply(const XorwowSkip &m, const Bits160 &v)
+{
+    Bits160 r = {{0, 0, 0, 0, 0}};
+    for (int i = 0; i < 5; ++i) {
+        uint32_t bits = v.w[i];
+        while (bits) {
+            const int j = __builtin_ctz(bits);
+            bits &= bits - 1;
+            const Bits160 &row = m.rows[i * 32 + j];
+            for (int k = 0; k < 5; ++k) r.w[k] ^= row.w[k];
+        }
+    }
+    return r;
+}
+
+const XorwowSkip &xorwow_sequence_matrix()
+{
+    static XorwowSkip T;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        XorwowSkip m;
+        for (int r = 0; r < 160; ++r) {
+            Bits160 e = {{0, 0, 0, 0, 0}};
+            e.w[r / 32] = 1u << (r % 32);
+            m.rows[r] = xorwow_step(e);
+        }
+        for (int s = 0; s < 67; ++s) {       // square 67 times: one step -> 2^67 steps
+            XorwowSkip sq;
+            for (int r = 0; r < 160; ++r) sq.rows[r] = mat_apply(m, m.rows[r]);
+            m = sq;
+        }
+        T = m;
+    });
+    return T;
+}
+
+// {d, v0..v4} of curand_init(seed, subsequence = y, offset = 0) for y = 0..H-1
+void xorwow_row_states(uint64_t seed, int H, std::vector<uint32_t> &out)
+{
+    const uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u;
+    const uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    const uint32_t t0 = 1099087573u * s0;
+    const uint32_t t1 = 2591861531u * s1;
+    const uint32_t d = 6615241u + t1 + t0;
+    Bits160 v;
+    v.w[0] = 123456789u + t0;
+    v.w[1] = 362436069u ^ t0;
+    v.w[2] = 521288629u + t1;
+    v.w[3] = 88675123u ^ t1;
+    v.w[4] = 5783321u + t0;
+    const XorwowSkip &T = xorwow_sequence_matrix();
+    out.resize((size_t)6 * H);
+    for (int y = 0; y < H; ++y) {
+        out[6 * y + 0] = d;       // the sequence skip leaves d untouched (multiple of 2^32 steps)
+        for (int k = 0; k < 5; ++k) out[6 * y + 1 + k] = v.w[k];
+        v = mat_apply(T, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 helpers, double precision
+// ---------------------------------------------------------------------------------------------
+struct M3 {
+    double m[9];
+};
+inline M3 mul(const M3 &a, const M3 &b)
+{
+    M3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+    return r;
+}
+inline M3 transpose(const M3 &a)
+{
+    M3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[3 * i + j] = a.m[3 * j + i];
+    return r;
+}
+inline void mulv(const M3 &a, const double v[3], double o[3])
+{
+    for (int i = 0; i < 3; ++i) o[i] = a.m[3 * i] * v[0] + a.m[3 * i + 1] * v[1] + a.m[3 * i + 2] * v[2];
+}
+inline M3 from_f(const float f[9])
+{
+    M3 r;
+    for (int i = 0; i < 9; ++i) r.m[i] = f[i];
+    return r;
+}
+// projection matrix the reference applies in ProjectonCamera_cu (ACMMP.cu:634-642): rows
+// (K0 K1 K2), (K3 K4 K5), (0 0 1) -- the third row of K is never read.
+inline M3 kproj(const float K[9])
+{
+    M3 r;
+    r.m[0] = K[0]; r.m[1] = K[1]; r.m[2] = K[2];
+    r.m[3] = K[3]; r.m[4] = K[4]; r.m[5] = K[5];
+    r.m[6] = 0; r.m[7] = 0; r.m[8] = 1;
+    return r;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct acmmp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    acmmp_params params;
+    int as_compiled = 1;
+    uint64_t seed = 0;
+    bool have_seeded = false;
+    uint64_t seeded_seed = 0;
+    int seeded_w = 0, seeded_h = 0;
+
+    int n = 0;                      // images (1 + sources)
+    int W = 0, H = 0;
+    std::vector<acmmp_camera> cams;
+    std::vector<int> widths, heights;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> textures;
+    float *ref_dense = nullptr;     // W*H
+    float *ref_padded = nullptr;
+    int ref_pitch = 0;
+    CUtensorMap tmap_pass, tmap_tp;
+    std::vector<float *> depth_maps;        // owned copies (host-upload variant)
+    std::vector<const float *> depth_ptrs;  // what the kernels read
+    std::vector<int> depth_w, depth_h;
+    std::vector<bool> depth_owned;
+
+    ViewConst *views_dev = nullptr;
+    float4 *planes = nullptr, *planes_alt = nullptr;
+    float *costs = nullptr, *costs_alt = nullptr, *pre_costs = nullptr;
+    uint32_t *selected_views = nullptr;
+    uint2 *rng = nullptr, *rng_seeded = nullptr;
+    float4 *prior_planes = nullptr;
+    uint32_t *plane_masks = nullptr;
+    float4 *coarse_planes = nullptr;
+    int scaled_cols = 0, scaled_rows = 0;
+
+    float4 *planes_host = nullptr;  // pinned
+    float *costs_host = nullptr;    // pinned
+    bool have_result = false;
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pass_events;
+    int pass_events_used = 0;
+    float t_init = 0.f, t_pass_sum = 0.f, t_finalize = 0.f, t_last_pass = 0.f;
+    int n_pass = 0;
+    bool timed_init = false, timed_final = false;
+    int64_t launches = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+            return ACMMP_E_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+int fail(acmmp_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int make_tmap(acmmp_ctx *ctx, CUtensorMap *tm, int box_w, int box_h)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ctx, ACMMP_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)ctx->ref_pitch, (cuuint64_t)(ctx->H + 2 * kRefPad)};
+    const cuuint64_t strides[1] = {(cuuint64_t)ctx->ref_pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ctx->ref_padded, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, ACMMP_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return ACMMP_OK;
+}
+
+void free_views(acmmp_ctx *ctx)
+{
+    for (auto t : ctx->textures) cudaDestroyTextureObject(t);
+    for (auto a : ctx->arrays) cudaFreeArray(a);
+    ctx->textures.clear();
+    ctx->arrays.clear();
+    cudaFree(ctx->ref_dense); ctx->ref_dense = nullptr;
+    cudaFree(ctx->ref_padded); ctx->ref_padded = nullptr;
+    cudaFree(ctx->views_dev); ctx->views_dev = nullptr;
+    cudaFree(ctx->planes); cudaFree(ctx->planes_alt); cudaFree(ctx->costs); cudaFree(ctx->costs_alt);
+    cudaFree(ctx->pre_costs); cudaFree(ctx->selected_views); cudaFree(ctx->rng); cudaFree(ctx->rng_seeded);
+    cudaFree(ctx->prior_planes); cudaFree(ctx->plane_masks); cudaFree(ctx->coarse_planes);
+    ctx->planes = ctx->planes_alt = nullptr;
+    ctx->costs = ctx->costs_alt = ctx->pre_costs = nullptr;
+    ctx->selected_views = nullptr;
+    ctx->rng = ctx->rng_seeded = nullptr;
+    ctx->prior_planes = nullptr; ctx->plane_masks = nullptr; ctx->coarse_planes = nullptr;
+    if (ctx->planes_host) cudaFreeHost(ctx->planes_host);
+    if (ctx->costs_host) cudaFreeHost(ctx->costs_host);
+    ctx->planes_host = nullptr; ctx->costs_host = nullptr;
+    ctx->have_seeded = false;
+    ctx->have_result = false;
+}
+
+void free_depths(acmmp_ctx *ctx)
+{
+    for (size_t i = 0; i < ctx->depth_maps.size(); ++i)
+        if (ctx->depth_owned[i]) cudaFree(ctx->depth_maps[i]);
+    ctx->depth_maps.clear();
+    ctx->depth_ptrs.clear();
+    ctx->depth_w.clear();
+    ctx->depth_h.clear();
+    ctx->depth_owned.clear();
+}
+
+// Fold (reference camera, source camera) into a ViewConst (see acmmp_types.cuh).
+ViewConst fold_view(const acmmp_camera &r, const acmmp_camera &s)
+{
+    ViewConst c;
+    std::memset(&c, 0, sizeof(c));
+    const M3 Rr = from_f(r.R), Rs = from_f(s.R);
+    const M3 Rrel = mul(Rs, transpose(Rr));          // ref cam -> src cam
+    const M3 Rinv = transpose(Rrel);                 // src cam -> ref cam
+    const double tr[3] = {r.t[0], r.t[1], r.t[2]}, ts[3] = {s.t[0], s.t[1], s.t[2]};
+    double tmp[3], trel[3], tinv[3];
+    mulv(Rrel, tr, tmp);
+    for (int i = 0; i < 3; ++i) trel[i] = ts[i] - tmp[i];
+    mulv(Rinv, ts, tmp);
+    for (int i = 0; i < 3; ++i) tinv[i] = tr[i] - tmp[i];
+
+    for (int i = 0; i < 9; ++i) { c.R[i] = (float)Rrel.m[i]; c.Ri[i] = (float)Rinv.m[i]; }
+    for (int i = 0; i < 3; ++i) { c.t[i] = (float)trel[i]; c.ti[i] = (float)tinv[i]; }
+    c.Wf = (float)s.width;
+    c.Hf = (float)s.height;
+
+    if (r.model == ACMMP_MODEL_PINHOLE) {
+        const M3 M = mul(kproj(s.K), Rrel);
+        double b[3];
+        mulv(kproj(s.K), trel, b);
+        const double ifx = 1.0 / r.K[0], ify = 1.0 / r.K[4];
+        for (int i = 0; i < 3; ++i) {
+            const double mx = M.m[3 * i + 0] * ifx, my = M.m[3 * i + 1] * ify, mz = M.m[3 * i + 2];
+            c.Mx[i] = (float)mx; c.My[i] = (float)my; c.Mz[i] = (float)mz; c.b[i] = (float)b[i];
+        }
+        for (int i = 0; i < 3; ++i) {      // +0.5 texel-centre offset folded into rows 0 and 1
+            const double h = (i < 2) ? 0.5 : 0.0;
+            c.Fx[i] = (float)((M.m[3 * i + 0] + h * M.m[6]) * ifx);
+            c.Fy[i] = (float)((M.m[3 * i + 1] + h * M.m[7]) * ify);
+            c.Fz[i] = (float)(M.m[3 * i + 2] + h * M.m[8]);
+            c.fb[i] = (float)(b[i] + h * b[2]);
+        }
+        const M3 Mi = mul(kproj(r.K), Rinv);
+        double ib[3];
+        mulv(kproj(r.K), tinv, ib);
+        const double ifxs = 1.0 / s.K[0], ifys = 1.0 / s.K[4];
+        for (int i = 0; i < 3; ++i) {
+            c.Ix[i] = (float)(Mi.m[3 * i + 0] * ifxs);
+            c.Iy[i] = (float)(Mi.m[3 * i + 1] * ifys);
+            c.Iz[i] = (float)Mi.m[3 * i + 2];
+            c.ib[i] = (float)ib[i];
+        }
+        c.cx = s.K[2];
+        c.cy = s.K[5];
+    } else {
+        c.cx = s.params[1];
+        c.cy = s.params[2];
+    }
+    return c;
+}
+
+int upload_view_consts(acmmp_ctx *ctx)
+{
+    const int nsrc = ctx->n - 1;
+    std::vector<ViewConst> vc(nsrc > 0 ? nsrc : 1);
+    for (int i = 0; i < nsrc; ++i) {
+        vc[i] = fold_view(ctx->cams[0], ctx->cams[i + 1]);
+        vc[i].tex = (unsigned long long)ctx->textures[i + 1];
+        if ((int)ctx->depth_ptrs.size() > i + 1) {
+            vc[i].depth = ctx->depth_ptrs[i + 1];
+            vc[i].dW = ctx->depth_w[i + 1];
+            vc[i].dH = ctx->depth_h[i + 1];
+        }
+    }
+    if (!ctx->views_dev) CK(cudaMalloc(&ctx->views_dev, sizeof(ViewConst) * kMaxSrc));
+    CK(cudaMemcpyAsync(ctx->views_dev, vc.data(), sizeof(ViewConst) * (size_t)(nsrc > 0 ? nsrc : 1), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));       // vc is a stack-lifetime staging buffer
+    return ACMMP_OK;
+}
+
+FrameConst frame_const(const acmmp_ctx *ctx)
+{
+    FrameConst fc;
+    std::memset(&fc, 0, sizeof(fc));
+    const acmmp_camera &r = ctx->cams[0];
+    fc.W = ctx->W; fc.H = ctx->H;
+    fc.model = r.model;
+    fc.nsrc = ctx->n - 1;
+    if (r.model == ACMMP_MODEL_PINHOLE) {
+        fc.cx = r.K[2]; fc.cy = r.K[5];
+        fc.ifx = (float)(1.0 / r.K[0]); fc.ify = (float)(1.0 / r.K[4]);
+    } else {
+        fc.cx = r.params[1]; fc.cy = r.params[2];
+    }
+    fc.Wf = (float)ctx->W; fc.Hf = (float)ctx->H;
+    for (int i = 0; i < 9; ++i) fc.R[i] = r.R[i];
+    fc.depth_min = ctx->params.depth_min;
+    fc.depth_max = ctx->params.depth_max;
+    fc.geom = ctx->params.geom_consistency;
+    fc.prior = ctx->params.planar_prior;
+    fc.hierarchy = ctx->params.hierarchy;
+    fc.upsample = ctx->params.upsample;
+    fc.scaled_cols = ctx->scaled_cols;
+    fc.scaled_rows = ctx->scaled_rows;
+    fc.as_compiled = ctx->as_compiled;
+    fc.ref_pitch = ctx->ref_pitch;
+    fc.ref_padded = ctx->ref_padded;
+    fc.views = ctx->views_dev;
+    fc.planes = ctx->planes; fc.planes_alt = ctx->planes_alt;
+    fc.costs = ctx->costs; fc.costs_alt = ctx->costs_alt;
+    fc.pre_costs = ctx->pre_costs;
+    fc.selected_views = ctx->selected_views;
+    fc.rng = ctx->rng; fc.rng_seeded = ctx->rng_seeded;
+    fc.prior_planes = ctx->prior_planes;
+    fc.plane_masks = ctx->plane_masks;
+    fc.coarse_planes = ctx->coarse_planes;
+    return fc;
+}
+
+template <int MODEL> size_t smem_tp(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kTpNT>(nsrc, kTpNT, 0).total; }
+template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassPix>(nsrc, kPassNT, kPassPix).total; }
+
+int configure_kernels(acmmp_ctx *ctx)
+{
+    static std::once_flag once;
+    static cudaError_t result = cudaSuccess;
+    std::call_once(once, [] {
+        const int big = 200 * 1024;
+        cudaError_t e;
+#define SETATTR(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) result = e;
+        SETATTR(k_pass<kModelPinhole>) SETATTR(k_pass<kModelSphere>)
+        SETATTR(k_random_init<kModelPinhole>) SETATTR(k_random_init<kModelSphere>)
+        SETATTR(k_probe<kModelPinhole>) SETATTR(k_probe<kModelSphere>)
+#undef SETATTR
+    });
+    if (result != cudaSuccess) return fail(ctx, ACMMP_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(result));
+    return ACMMP_OK;
+}
+
+int ensure_seeded(acmmp_ctx *ctx)
+{
+    if (ctx->have_seeded && ctx->seeded_seed == ctx->seed && ctx->seeded_w == ctx->W && ctx->seeded_h == ctx->H) return ACMMP_OK;
+    std::vector<uint32_t> rows;
+    xorwow_row_states(ctx->seed, ctx->H, rows);
+    uint32_t *rows_dev = nullptr;
+    CK(cudaMalloc(&rows_dev, rows.size() * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(rows_dev, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_rng_fill<<<(ctx->H + 63) / 64, 64, 0, ctx->stream>>>(rows_dev, ctx->W, ctx->H, ctx->rng_seeded);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(rows_dev));
+    ctx->have_seeded = true;
+    ctx->seeded_seed = ctx->seed;
+    ctx->seeded_w = ctx->W;
+    ctx->seeded_h = ctx->H;
+    return ACMMP_OK;
+}
+
+int check_ready(acmmp_ctx *ctx)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    if (ctx->n < 2 || !ctx->planes) return fail(ctx, ACMMP_E_ARG, "acmmp_set_views has not been called (need >= 1 source view)");
+    if (ctx->params.geom_consistency && (int)ctx->depth_ptrs.size() != ctx->n)
+        return fail(ctx, ACMMP_E_ARG, "geom_consistency is set but acmmp_set_depth_maps was not called with one map per view");
+    if (ctx->params.planar_prior && !ctx->prior_planes)
+        return fail(ctx, ACMMP_E_ARG, "planar_prior is set but acmmp_set_planar_prior_inputs was not called");
+    if (ctx->params.hierarchy && !ctx->coarse_planes)
+        return fail(ctx, ACMMP_E_ARG, "hierarchy is set but acmmp_set_hierarchy_inputs was not called");
+    return ACMMP_OK;
+}
+
+int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_device, const int32_t *widths,
+                     const int32_t *heights, const acmmp_camera *cams)
+{
+    if (!ctx || n < 2 || n > kMaxSrc + 1 || !images || !widths || !heights || !cams)
+        return fail(ctx, ACMMP_E_ARG, "acmmp_set_views: need 2..33 images");
+    for (int i = 0; i < n; ++i) {
+        if (cams[i].model != cams[0].model) return fail(ctx, ACMMP_E_UNSUPPORTED, "mixed camera models in one problem are not supported");
+        if (cams[i].model != ACMMP_MODEL_PINHOLE && cams[i].model != ACMMP_MODEL_SPHERE)
+            return fail(ctx, ACMMP_E_ARG, "unknown camera model");
+        if (widths[i] <= 0 || heights[i] <= 0) return fail(ctx, ACMMP_E_ARG, "bad image size");
+    }
+    CK(cudaSetDevice(ctx->device));
+    const bool same_shape = (ctx->n == n && ctx->W == widths[0] && ctx->H == heights[0]);
+    bool same_all = same_shape;
+    if (same_shape)
+        for (int i = 0; i < n; ++i) same_all = same_all && ctx->widths[i] == widths[i] && ctx->heights[i] == heights[i];
+    if (!same_all) {
+        free_views(ctx);
+        ctx->n = n;
+        ctx->W = widths[0];
+        ctx->H = heights[0];
+        ctx->widths.assign(widths, widths + n);
+        ctx->heights.assign(heights, heights + n);
+        const size_t npx = (size_t)ctx->W * ctx->H;
+        const cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        ctx->arrays.assign(n, nullptr);
+        ctx->textures.assign(n, 0);
+        for (int i = 0; i < n; ++i) {
+            CK(cudaMallocArray(&ctx->arrays[i], &desc, widths[i], heights[i]));
+            cudaResourceDesc res;
+            std::memset(&res, 0, sizeof(res));
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = ctx->arrays[i];
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof(td));
+            // The reference asks for Wrap with un-normalised coordinates (ACMMP.cpp:700-704), which
+            // CUDA turns into Clamp; ask for what it gets.
+            td.addressMode[0] = cudaAddressModeClamp;
+            td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            CK(cudaCreateTextureObject(&ctx->textures[i], &res, &td, nullptr));
+        }
+        ctx->ref_pitch = (ctx->W + 2 * kRefPad + 3) & ~3;
+        CK(cudaMalloc(&ctx->ref_dense, sizeof(float) * npx));
+        CK(cudaMalloc(&ctx->ref_padded, sizeof(float) * (size_t)ctx->ref_pitch * (ctx->H + 2 * kRefPad)));
+        CK(cudaMalloc(&ctx->planes, sizeof(float4) * npx));
+        CK(cudaMalloc(&ctx->planes_alt, sizeof(float4) * npx));
+        CK(cudaMalloc(&ctx->costs, sizeof(float) * npx));
+        CK(cudaMalloc(&ctx->costs_alt, sizeof(float) * npx));
+        CK(cudaMalloc(&ctx->pre_costs, sizeof(float) * npx));
+        CK(cudaMalloc(&ctx->selected_views, sizeof(uint32_t) * npx));
+        CK(cudaMalloc(&ctx->rng, sizeof(uint2) * 3 * npx));
+        CK(cudaMalloc(&ctx->rng_seeded, sizeof(uint2) * 3 * npx));
+        CK(cudaMemsetAsync(ctx->planes, 0, sizeof(float4) * npx, ctx->stream));
+        CK(cudaMemsetAsync(ctx->costs, 0, sizeof(float) * npx, ctx->stream));
+        CK(cudaMemsetAsync(ctx->pre_costs, 0, sizeof(float) * npx, ctx->stream));
+        CK(cudaMemsetAsync(ctx->selected_views, 0, sizeof(uint32_t) * npx, ctx->stream));
+        CK(cudaMallocHost(&ctx->planes_host, sizeof(float4) * npx));
+        CK(cudaMallocHost(&ctx->costs_host, sizeof(float) * npx));
+        typedef TileGeom<kPassTW, kPassTH> TGp;
+        typedef TileGeom<kTpTW, kTpTH> TGt;
+        int rc = make_tmap(ctx, &ctx->tmap_pass, TGp::PW, TGp::RH);
+        if (rc) return rc;
+        rc = make_tmap(ctx, &ctx->tmap_tp, TGt::PW, TGt::RH);
+        if (rc) return rc;
+    }
+    ctx->cams.assign(cams, cams + n);
+    for (int i = 0; i < n; ++i) {
+        ctx->cams[i].width = widths[i];
+        ctx->cams[i].height = heights[i];
+    }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int i = 0; i < n; ++i) {
+        CK(cudaMemcpy2DToArrayAsync(ctx->arrays[i], 0, 0, images[i], sizeof(float) * widths[i], sizeof(float) * widths[i],
+                                    heights[i], kind, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->ref_dense, images[0], sizeof(float) * (size_t)ctx->W * ctx->H, kind, ctx->stream));
+    {
+        dim3 grid((ctx->ref_pitch + 255) / 256, ctx->H + 2 * kRefPad);
+        k_pad_reference<<<grid, 256, 0, ctx->stream>>>(ctx->ref_dense, ctx->W, ctx->H, ctx->ref_padded, ctx->ref_pitch);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // what InuputInitialization derives (ACMMP.cpp:645-651)
+    ctx->params.depth_min = ctx->cams[0].depth_min * 0.6f;
+    ctx->params.depth_max = ctx->cams[0].depth_max * 1.2f;
+    ctx->params.num_images = n;
+    ctx->params.disparity_min = ctx->cams[0].K[0] * ctx->params.baseline / ctx->params.depth_max;
+    ctx->params.disparity_max = ctx->cams[0].K[0] * ctx->params.baseline / ctx->params.depth_min;
+    int rc = upload_view_consts(ctx);
+    if (rc) return rc;
+    return configure_kernels(ctx);
+}
+
+int set_depths_common(acmmp_ctx *ctx, int n, const float *const *maps, bool on_device, const int32_t *widths,
+                      const int32_t *heights)
+{
+    if (!ctx || n != ctx->n || !maps || !widths || !heights)
+        return fail(ctx, ACMMP_E_ARG, "acmmp_set_depth_maps: one map per view (after acmmp_set_views)");
+    CK(cudaSetDevice(ctx->device));
+    free_depths(ctx);
+    for (int i = 0; i < n; ++i) {
+        ctx->depth_w.push_back(widths[i]);
+        ctx->depth_h.push_back(heights[i]);
+        if (on_device) {
+            ctx->depth_maps.push_back(nullptr);
+            ctx->depth_ptrs.push_back(maps[i]);
+            ctx->depth_owned.push_back(false);
+        } else {
+            float *d = nullptr;
+            CK(cudaMalloc(&d, sizeof(float) * (size_t)widths[i] * heights[i]));
+            CK(cudaMemcpyAsync(d, maps[i], sizeof(float) * (size_t)widths[i] * heights[i], cudaMemcpyHostToDevice, ctx->stream));
+            ctx->depth_maps.push_back(d);
+            ctx->depth_ptrs.push_back(d);
+            ctx->depth_owned.push_back(true);
+        }
+    }
+    return upload_view_consts(ctx);
+}
+
+void record_begin(acmmp_ctx *ctx, int which)
+{
+    cudaEventRecord(ctx->ev[which], ctx->stream);
+}
+
+template <int MODEL>
+int launch_init(acmmp_ctx *ctx)
+{
+    const FrameConst fc = frame_const(ctx);
+    dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
+    k_random_init<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->tmap_tp);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return ACMMP_OK;
+}
+
+template <int MODEL>
+int launch_pass(acmmp_ctx *ctx, int colour, int iter)
+{
+    const FrameConst fc = frame_const(ctx);
+    dim3 grid((ctx->W + kPassTW - 1) / kPassTW, (ctx->H + kPassTH - 1) / kPassTH);
+    k_pass<MODEL><<<grid, kPassNT, smem_pass<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->tmap_pass, colour, iter);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::swap(ctx->planes, ctx->planes_alt);
+    std::swap(ctx->costs, ctx->costs_alt);
+    return ACMMP_OK;
+}
+
+template <int MODEL>
+int launch_finalize(acmmp_ctx *ctx)
+{
+    const FrameConst fc = frame_const(ctx);
+    const int npx = ctx->W * ctx->H;
+    k_depth_normal<MODEL><<<(npx + 255) / 256, 256, 0, ctx->stream>>>(fc);
+    const int half = ((ctx->W + 1) / 2) * ctx->H;
+    k_median_filter<<<(half + 255) / 256, 256, 0, ctx->stream>>>(fc, 0);
+    k_median_filter<<<(half + 255) / 256, 256, 0, ctx->stream>>>(fc, 1);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return ACMMP_OK;
+}
+
+int do_init(acmmp_ctx *ctx)
+{
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->params.upsample) {
+        const int Imagescale = (int)std::fmax((float)ctx->W / (float)ctx->scaled_cols, (float)ctx->H / (float)ctx->scaled_rows);
+        if ((Imagescale * Imagescale + 1) / 2 > kHalo) return fail(ctx, ACMMP_E_UNSUPPORTED, "upsample factor > 3 is not supported");
+    }
+    rc = ensure_seeded(ctx);
+    if (rc) return rc;
+    record_begin(ctx, 0);
+    rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_init<kModelPinhole>(ctx) : launch_init<kModelSphere>(ctx);
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->timed_init = true;
+    ctx->pass_events_used = 0;
+    ctx->timed_final = false;
+    return rc;
+}
+
+int do_pass(acmmp_ctx *ctx, int colour, int iter)
+{
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((int)ctx->pass_events.size() <= ctx->pass_events_used) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        ctx->pass_events.push_back(std::make_pair(a, b));
+    }
+    auto &pe = ctx->pass_events[ctx->pass_events_used++];
+    cudaEventRecord(pe.first, ctx->stream);
+    rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_pass<kModelPinhole>(ctx, colour, iter)
+                                                     : launch_pass<kModelSphere>(ctx, colour, iter);
+    cudaEventRecord(pe.second, ctx->stream);
+    return rc;
+}
+
+int do_finalize(acmmp_ctx *ctx)
+{
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    record_begin(ctx, 2);
+    rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_finalize<kModelPinhole>(ctx) : launch_finalize<kModelSphere>(ctx);
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    ctx->timed_final = true;
+    return rc;
+}
+
+int collect_timings(acmmp_ctx *ctx)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->timed_init) cudaEventElapsedTime(&ctx->t_init, ctx->ev[0], ctx->ev[1]);
+    if (ctx->timed_final) cudaEventElapsedTime(&ctx->t_finalize, ctx->ev[2], ctx->ev[3]);
+    ctx->t_pass_sum = 0.f;
+    ctx->n_pass = ctx->pass_events_used;
+    for (int i = 0; i < ctx->pass_events_used; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->pass_events[i].first, ctx->pass_events[i].second);
+        ctx->t_pass_sum += ms;
+        ctx->t_last_pass = ms;
+    }
+    return ACMMP_OK;
+}
+
+template <int MODEL>
+int launch_probe(acmmp_ctx *ctx, int mode, int view, const float4 *planes_dev, float *out, float4 *out4, uint32_t *out_views)
+{
+    const FrameConst fc = frame_const(ctx);
+    dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
+    k_probe<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->tmap_tp, mode, view, planes_dev, out, out4, out_views);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return ACMMP_OK;
+}
+
+int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *out, float *out4, uint32_t *out_views)
+{
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!planes4) return fail(ctx, ACMMP_E_ARG, "probe: planes is null");
+    if (mode != 3 && (view < 1 || view >= ctx->n)) return fail(ctx, ACMMP_E_ARG, "probe: view must be 1..n-1");
+    if (mode == 1 && (int)ctx->depth_ptrs.size() != ctx->n) return fail(ctx, ACMMP_E_ARG, "probe geom: no depth maps");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    float4 *dp = nullptr, *do4 = nullptr;
+    float *dout = nullptr;
+    uint32_t *dv = nullptr;
+    CK(cudaMalloc(&dp, sizeof(float4) * npx));
+    CK(cudaMalloc(&do4, sizeof(float4) * npx));
+    CK(cudaMalloc(&dout, sizeof(float) * npx));
+    CK(cudaMalloc(&dv, sizeof(uint32_t) * npx));
+    CK(cudaMemcpyAsync(dp, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe<kModelPinhole>(ctx, mode, view, dp, dout, do4, dv)
+                                                     : launch_probe<kModelSphere>(ctx, mode, view, dp, dout, do4, dv);
+    if (rc == ACMMP_OK) {
+        if (out) CK(cudaMemcpyAsync(out, dout, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out4) CK(cudaMemcpyAsync(out4, do4, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_views) CK(cudaMemcpyAsync(out_views, dv, sizeof(uint32_t) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(dp); cudaFree(do4); cudaFree(dout); cudaFree(dv);
+    return rc;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+void acmmp_default_params(acmmp_params *p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->max_iterations = 3; p->patch_size = 11; p->num_images = 5; p->max_image_size = 3200;
+    p->radius_increment = 2; p->sigma_spatial = 5.0f; p->sigma_color = 3.0f; p->top_k = 4;
+    p->baseline = 0.54f; p->depth_min = 0.0f; p->depth_max = 1.0f; p->disparity_min = 0.0f; p->disparity_max = 1.0f;
+}
+
+const char *acmmp_version(void) { return "acmmp_b200 0.1 (sm_100a)"; }
+int acmmp_abi_sizeof_camera(void) { return (int)sizeof(acmmp_camera); }
+int acmmp_abi_sizeof_params(void) { return (int)sizeof(acmmp_params); }
+
+int acmmp_create(acmmp_ctx **out, int device)
+{
+    if (!out) return ACMMP_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ACMMP_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ACMMP_E_CUDA;
+    if (prop.major != 10) {
+        std::fprintf(stderr, "acmmp_b200: device %d is sm_%d%d; this library only carries sm_100a code\n", device, prop.major, prop.minor);
+        return ACMMP_E_UNSUPPORTED;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
+    acmmp_ctx *ctx = new acmmp_ctx();
+    ctx->device = device;
+    acmmp_default_params(&ctx->params);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return ACMMP_E_CUDA;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return ACMMP_OK;
+}
+
+int acmmp_destroy(acmmp_ctx *ctx)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_views(ctx);
+    free_depths(ctx);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (auto &pe : ctx->pass_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ACMMP_OK;
+}
+
+const char *acmmp_last_error(const acmmp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int acmmp_set_views(acmmp_ctx *ctx, int n, const float *const *images, const int32_t *widths, const int32_t *heights,
+                    const acmmp_camera *cams)
+{
+    return set_views_common(ctx, n, images, false, widths, heights, cams);
+}
+
+int acmmp_set_views_device(acmmp_ctx *ctx, int n, const float *const *images_dev, const int32_t *widths,
+                           const int32_t *heights, const acmmp_camera *cams)
+{
+    return set_views_common(ctx, n, images_dev, true, widths, heights, cams);
+}
+
+int acmmp_set_geom_consistency(acmmp_ctx *ctx, int multi_geometry)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    ctx->params.geom_consistency = 1;             // ACMMP.cpp:548-555
+    ctx->params.max_iterations = 2;
+    if (multi_geometry) ctx->params.multi_geometry = 1;
+    return ACMMP_OK;
+}
+
+int acmmp_set_hierarchy(acmmp_ctx *ctx)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    ctx->params.hierarchy = 1;                    // ACMMP.cpp:557-560
+    return ACMMP_OK;
+}
+
+int acmmp_set_planar_prior(acmmp_ctx *ctx)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    ctx->params.planar_prior = 1;                 // ACMMP.cpp:562-565
+    return ACMMP_OK;
+}
+
+int acmmp_set_max_iterations(acmmp_ctx *ctx, int n)
+{
+    if (!ctx || n < 0) return ACMMP_E_ARG;
+    ctx->params.max_iterations = n;
+    return ACMMP_OK;
+}
+
+int acmmp_get_params(const acmmp_ctx *ctx, acmmp_params *out)
+{
+    if (!ctx || !out) return ACMMP_E_ARG;
+    *out = ctx->params;
+    return ACMMP_OK;
+}
+
+int acmmp_set_depth_maps(acmmp_ctx *ctx, int n, const float *const *maps, const int32_t *widths, const int32_t *heights)
+{
+    return set_depths_common(ctx, n, maps, false, widths, heights);
+}
+
+int acmmp_set_depth_maps_device(acmmp_ctx *ctx, int n, const float *const *maps_dev, const int32_t *widths,
+                                const int32_t *heights)
+{
+    return set_depths_common(ctx, n, maps_dev, true, widths, heights);
+}
+
+int acmmp_set_planes(acmmp_ctx *ctx, const float *planes4, const float *costs)
+{
+    if (!ctx || !ctx->planes || !planes4 || !costs) return fail(ctx, ACMMP_E_ARG, "acmmp_set_planes: call acmmp_set_views first");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    CK(cudaMemcpyAsync(ctx->planes, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->costs, costs, sizeof(float) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ACMMP_OK;
+}
+
+int acmmp_set_hierarchy_inputs(acmmp_ctx *ctx, const float *coarse_planes4, int sw, int sh, const float *fine_depth)
+{
+    if (!ctx || !ctx->planes || !coarse_planes4 || !fine_depth || sw <= 0 || sh <= 0)
+        return fail(ctx, ACMMP_E_ARG, "acmmp_set_hierarchy_inputs: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    cudaFree(ctx->coarse_planes);
+    ctx->coarse_planes = nullptr;
+    CK(cudaMalloc(&ctx->coarse_planes, sizeof(float4) * (size_t)sw * sh));
+    CK(cudaMemcpyAsync(ctx->coarse_planes, coarse_planes4, sizeof(float4) * (size_t)sw * sh, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->scaled_cols = sw;
+    ctx->scaled_rows = sh;
+    // ACMMP.cpp:808-815
+    ctx->params.upsample = (sw != ctx->W || sh != ctx->H) ? 1 : 0;
+    ctx->params.scaled_cols = (float)sw;
+    ctx->params.scaled_rows = (float)sh;
+    // plane = (0, 0, 0, fine depth): ACMMP.cpp:833-840 with the unwritten normal defined as 0
+    std::vector<float> tmp(4 * npx, 0.f);
+    for (size_t i = 0; i < npx; ++i) tmp[4 * i + 3] = fine_depth[i];
+    CK(cudaMemcpyAsync(ctx->planes, tmp.data(), sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ACMMP_OK;
+}
+
+int acmmp_set_planar_prior_inputs(acmmp_ctx *ctx, const float *plane_params4, int n_planes, const float *masks)
+{
+    if (!ctx || !ctx->planes || !masks || (n_planes > 0 && !plane_params4))
+        return fail(ctx, ACMMP_E_ARG, "acmmp_set_planar_prior_inputs: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    std::vector<float> pp(4 * npx, 0.f);
+    std::vector<uint32_t> mk(npx, 0u);
+    for (size_t i = 0; i < npx; ++i) {                 // ACMMP.cpp:855-863
+        mk[i] = (uint32_t)masks[i];
+        if (masks[i] > 0) {
+            const int id = (int)(masks[i] - 1);
+            if (id < 0 || id >= n_planes) return fail(ctx, ACMMP_E_ARG, "prior mask refers to a plane that was not supplied");
+            std::memcpy(&pp[4 * i], &plane_params4[4 * (size_t)id], 4 * sizeof(float));
+        }
+    }
+    if (!ctx->prior_planes) CK(cudaMalloc(&ctx->prior_planes, sizeof(float4) * npx));
+    if (!ctx->plane_masks) CK(cudaMalloc(&ctx->plane_masks, sizeof(uint32_t) * npx));
+    CK(cudaMemcpyAsync(ctx->prior_planes, pp.data(), sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->plane_masks, mk.data(), sizeof(uint32_t) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->params.planar_prior = 1;
+    return ACMMP_OK;
+}
+
+int acmmp_set_seed(acmmp_ctx *ctx, uint64_t seed)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    ctx->seed = seed;
+    return ACMMP_OK;
+}
+
+int acmmp_set_plane_now_semantics(acmmp_ctx *ctx, int as_compiled)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    ctx->as_compiled = as_compiled ? 1 : 0;
+    return ACMMP_OK;
+}
+
+int acmmp_random_init(acmmp_ctx *ctx) { return do_init(ctx); }
+
+int acmmp_checkerboard_pass(acmmp_ctx *ctx, int colour, int iter)
+{
+    if (!ctx || (colour != 0 && colour != 1)) return ACMMP_E_ARG;
+    return do_pass(ctx, colour, iter);
+}
+
+int acmmp_finalize(acmmp_ctx *ctx) { return do_finalize(ctx); }
+
+int acmmp_synchronize(acmmp_ctx *ctx)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return collect_timings(ctx);
+}
+
+int acmmp_run_patch_match(acmmp_ctx *ctx)
+{
+    int rc = do_init(ctx);
+    if (rc) return rc;
+    for (int i = 0; i < ctx->params.max_iterations; ++i) {
+        if ((rc = do_pass(ctx, 0, i))) return rc;
+        if ((rc = do_pass(ctx, 1, i))) return rc;
+    }
+    if ((rc = do_finalize(ctx))) return rc;
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    CK(cudaMemcpyAsync(ctx->planes_host, ctx->planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->costs_host, ctx->costs, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = collect_timings(ctx);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    ctx->have_result = true;
+    return ACMMP_OK;
+}
+
+int acmmp_get_result(acmmp_ctx *ctx, float *planes4, float *costs)
+{
+    if (!ctx || !ctx->have_result) return fail(ctx, ACMMP_E_ARG, "acmmp_get_result: no completed acmmp_run_patch_match");
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    if (planes4) std::memcpy(planes4, ctx->planes_host, sizeof(float4) * npx);
+    if (costs) std::memcpy(costs, ctx->costs_host, sizeof(float) * npx);
+    return ACMMP_OK;
+}
+
+int acmmp_width(const acmmp_ctx *ctx) { return ctx ? ctx->W : 0; }
+int acmmp_height(const acmmp_ctx *ctx) { return ctx ? ctx->H : 0; }
+
+int acmmp_device_buffers(acmmp_ctx *ctx, void **planes4_dev, void **costs_dev)
+{
+    if (!ctx || !ctx->planes) return ACMMP_E_ARG;
+    if (planes4_dev) *planes4_dev = ctx->planes;
+    if (costs_dev) *costs_dev = ctx->costs;
+    return ACMMP_OK;
+}
+
+int acmmp_export_depth_device(acmmp_ctx *ctx, float *depth_dev)
+{
+    if (!ctx || !ctx->planes || !depth_dev) return ACMMP_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int npx = ctx->W * ctx->H;
+    k_export_depth<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(ctx->planes, npx, depth_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return ACMMP_OK;
+}
+
+int acmmp_download_state(acmmp_ctx *ctx, float *planes4, float *costs, uint32_t *selected_views, uint32_t *rand6,
+                         float *pre_costs)
+{
+    if (!ctx || !ctx->planes) return ACMMP_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (planes4) CK(cudaMemcpy(planes4, ctx->planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost));
+    if (costs) CK(cudaMemcpy(costs, ctx->costs, sizeof(float) * npx, cudaMemcpyDeviceToHost));
+    if (selected_views) CK(cudaMemcpy(selected_views, ctx->selected_views, sizeof(uint32_t) * npx, cudaMemcpyDeviceToHost));
+    if (rand6) CK(cudaMemcpy(rand6, ctx->rng, sizeof(uint32_t) * 6 * npx, cudaMemcpyDeviceToHost));
+    if (pre_costs) CK(cudaMemcpy(pre_costs, ctx->pre_costs, sizeof(float) * npx, cudaMemcpyDeviceToHost));
+    return ACMMP_OK;
+}
+
+int acmmp_upload_state(acmmp_ctx *ctx, const float *planes4, const float *costs, const uint32_t *selected_views,
+                       const uint32_t *rand6, const float *pre_costs)
+{
+    if (!ctx || !ctx->planes) return ACMMP_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (planes4) CK(cudaMemcpy(ctx->planes, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice));
+    if (costs) CK(cudaMemcpy(ctx->costs, costs, sizeof(float) * npx, cudaMemcpyHostToDevice));
+    if (selected_views) CK(cudaMemcpy(ctx->selected_views, selected_views, sizeof(uint32_t) * npx, cudaMemcpyHostToDevice));
+    if (rand6) CK(cudaMemcpy(ctx->rng, rand6, sizeof(uint32_t) * 6 * npx, cudaMemcpyHostToDevice));
+    if (pre_costs) CK(cudaMemcpy(ctx->pre_costs, pre_costs, sizeof(float) * npx, cudaMemcpyHostToDevice));
+    return ACMMP_OK;
+}
+
+int acmmp_jbu_device(int device, const float *image_dev, int w, int h, const float *coarse_depth_dev, int sw, int sh,
+                     float *out_depth_dev, void *cuda_stream)
+{
+    if (!image_dev || !coarse_depth_dev || !out_depth_dev || w <= 0 || h <= 0 || sw <= 0 || sh <= 0) return ACMMP_E_ARG;
+    const int Imagescale = std::max(h / sh, w / sw);      // ACMMP.cpp:1075 (integer division)
+    if (Imagescale == 1) return ACMMP_E_ARG;              // ACMMP.cpp:1077-1080: nothing is produced
+    if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
+    dim3 grid((w + 15) / 16, (h + 15) / 16);
+    k_jbu<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(image_dev, w, h, coarse_depth_dev, sw, sh, Imagescale, out_depth_dev);
+    return cudaGetLastError() == cudaSuccess ? ACMMP_OK : ACMMP_E_CUDA;
+}
+
+int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_depth, int sw, int sh, float *out_depth)
+{
+    if (!image || !coarse_depth || !out_depth || w <= 0 || h <= 0 || sw <= 0 || sh <= 0) return ACMMP_E_ARG;
+    if (std::max(h / sh, w / sw) == 1) return ACMMP_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
+    float *di = nullptr, *dd = nullptr, *dout = nullptr;
+    int rc = ACMMP_E_CUDA;
+    if (cudaMalloc(&di, sizeof(float) * (size_t)w * h) == cudaSuccess && cudaMalloc(&dd, sizeof(float) * (size_t)sw * sh) == cudaSuccess &&
+        cudaMalloc(&dout, sizeof(float) * (size_t)w * h) == cudaSuccess &&
+        cudaMemcpy(di, image, sizeof(float) * (size_t)w * h, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(dd, coarse_depth, sizeof(float) * (size_t)sw * sh, cudaMemcpyHostToDevice) == cudaSuccess) {
+        rc = acmmp_jbu_device(device, di, w, h, dd, sw, sh, dout, nullptr);
+        if (rc == ACMMP_OK && cudaMemcpy(out_depth, dout, sizeof(float) * (size_t)w * h, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = ACMMP_E_CUDA;
+    }
+    cudaFree(di); cudaFree(dd); cudaFree(dout);
+    return rc;
+}
+
+int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 0, view, planes4, out, nullptr, nullptr); }
+int acmmp_probe_geom(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 1, view, planes4, out, nullptr, nullptr); }
+int acmmp_probe_warp(acmmp_ctx *ctx, const float *planes4, int view, float *out4) { return run_probe(ctx, 2, view, planes4, nullptr, out4, nullptr); }
+int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint32_t *selected_views)
+{
+    return run_probe(ctx, 3, 1, planes4, out, nullptr, selected_views);
+}
+
+int acmmp_last_timings(acmmp_ctx *ctx, float what[8])
+{
+    if (!ctx || !what) return ACMMP_E_ARG;
+    for (int i = 0; i < 8; ++i) what[i] = 0.f;
+    what[0] = ctx->t_init;
+    what[1] = ctx->t_pass_sum;
+    what[2] = ctx->t_finalize;
+    what[3] = (float)ctx->n_pass;
+    what[4] = ctx->t_last_pass;
+    return ACMMP_OK;
+}
+
+int64_t acmmp_launch_count(const acmmp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,970 @@
+// acmmp_kernels.cuh -- the __global__ entry points of the B200 PatchMatch path.
+//
+//   k_pass            : one red/black checkerboard pass      (reference Black/RedPixelUpdate,
+//                       CheckerboardPropagation + PlaneHypothesisRefinement, ACMMP.cu:797-1349)
+//   k_random_init     : RandomInitialization, all four branches            (ACMMP.cu:673-795)
+//   k_probe           : sub-kernel probes for parity tests (same device code as the two above)
+//   k_depth_normal    : GetDepthandNormal                                  (ACMMP.cu:1351-1364)
+//   k_median_filter   : Black/RedPixelFilter                               (ACMMP.cu:1366-1504)
+//   k_jbu             : JBU_cu                                             (ACMMP.cu:1558-1616)
+//   k_pad_reference, k_rng_fill, k_export_depth : data-layout helpers
+//
+// Work decomposition of k_pass (the kernel that is >95 % of the time): a CTA owns an 8x8 pixel
+// tile = 32 pixels of the active colour; each pixel is served by a GROUP OF 8 LANES (4 pixels per
+// warp).  Lane l evaluates candidate direction l of the adaptive checkerboard (8 neighbour
+// hypotheses in parallel, argmin by warp shuffles); the five refinement hypotheses run on lanes
+// 0..4; the current plane's cost is evaluated with the 36 taps split over the 8 lanes.  The
+// reference tile (+5 px halo) arrives in shared memory by one TMA bulk-tensor copy; bilateral
+// weights and tap rays are computed once per pixel visit; source views are bilinear R32F
+// texture fetches (identical filtering to the reference's textures by construction).
+#pragma once
+#include <cuda.h>
+#include "acmmp_device.cuh"
+
+namespace acmmp {
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up helpers
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <int MODEL, int TW, int TH, int NPIX>
+struct SmemLayout {
+    typedef TileGeom<TW, TH> TG;
+    typedef typename AuxType<MODEL>::type AuxT;
+    size_t off_tile, off_aux, off_wr, off_vc, off_bar, off_cost, off_vw, off_probs, total;
+    __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows)
+    {
+        const int nvp = nsrc | 1;
+        size_t o = 0;
+        off_tile = o; o += align_up(TG::kTileBytes, 128);
+        off_aux = o; o += align_up(sizeof(AuxT) * TG::RW * TG::RH, 16);
+        off_wr = o; o += sizeof(float2) * kTaps * NPIX;
+        off_vc = o; o += sizeof(ViewConst) * (size_t)nsrc;
+        off_bar = o; o += 16;
+        off_cost = o; o += sizeof(float) * (size_t)cost_rows * nvp;
+        off_vw = o; o += sizeof(float) * (size_t)group_rows * nvp;
+        off_probs = o; o += sizeof(float) * (size_t)group_rows * nvp;
+        total = align_up(o, 16);
+    }
+};
+
+// Stage the per-view constants and the reference tile; build the per-tile-pixel ray table.
+// Must be called by every thread of the CTA.
+template <int MODEL, int TW, int TH, int NT>
+__device__ __forceinline__ void stage_tile(const FrameConst &fc, const CUtensorMap *tmap, const int x0, const int y0,
+                                           float *tile_r, typename AuxType<MODEL>::type *aux, ViewConst *s_vc,
+                                           unsigned long long *bar)
+{
+    typedef TileGeom<TW, TH> TG;
+    const int tid = threadIdx.x;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        tma_load_tile_2d(tile_r, tmap, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, bar, TG::kTileBytes);
+    }
+    {   // view constants: nsrc * 72 words
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(fc.views);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_vc);
+        const int nwords = fc.nsrc * (int)(sizeof(ViewConst) / 4);
+        for (int i = tid; i < nwords; i += NT) dst[i] = __ldg(src + i);
+    }
+    for (int idx = tid; idx < TG::RW * TG::RH; idx += NT) {
+        const int xx = x0 - kHalo + idx % TG::RW;
+        const int yy = y0 - kHalo + idx / TG::RW;
+        aux[idx] = make_aux<MODEL>(fc, xx, yy);
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+}
+
+template <int MODEL>
+__device__ __forceinline__ PixCtx make_pix(const FrameConst &fc, const int x, const int y, const int x0, const int y0)
+{
+    PixCtx px;
+    px.x = x; px.y = y;
+    px.tx = x - x0 + kHalo; px.ty = y - y0 + kHalo;
+    px.dx = static_cast<float>(x) - fc.cx;
+    px.dy = static_cast<float>(y) - fc.cy;
+    px.dir = pixel_dir<MODEL>(fc, x, y);
+    px.Sw = px.Swr = px.Swrr = 0.f;
+    return px;
+}
+
+// ComputeMultiViewInitialCostandSelectedViews, ACMMP.cu:519-556.  costrow: nsrc floats (scratch).
+template <int MODEL, int PW, int RW, int WRS>
+__device__ __forceinline__ float init_cost_and_views(const FrameConst &fc, const ViewConst *s_vc, const float *tile_r,
+                                                     const typename AuxType<MODEL>::type *aux, const float2 *wr,
+                                                     const PixCtx &px, const float4 &plane, float *costrow,
+                                                     uint32_t &selected)
+{
+    const float cost_max = 2.0f;
+    const uint32_t all = (fc.nsrc >= 32) ? 0xffffffffu : ((1u << fc.nsrc) - 1u);
+    ncc_views<MODEL, PW, RW, WRS>(fc, s_vc, tile_r, aux, wr, px, plane, all, costrow, 1);
+    int num_valid = 0;
+    for (int i = 0; i < fc.nsrc; ++i) num_valid += (costrow[i] < cost_max) ? 1 : 0;
+    selected = 0;
+    const int top_k = min(num_valid, 4);      // params.top_k, ACMMP.h:40
+    if (top_k <= 0) return cost_max;
+    // the top_k smallest costs in ascending order == the head of the reference's sorted vector
+    uint32_t taken = 0;
+    float cost = 0.0f, threshold = 0.0f;
+    for (int k = 0; k < top_k; ++k) {
+        float best = 0.f;
+        int bi = -1;
+        for (int i = 0; i < fc.nsrc; ++i) {
+            if ((taken >> i) & 1u) continue;
+            const float c = costrow[i];
+            if (bi < 0 || c < best) { best = c; bi = i; }
+        }
+        taken |= 1u << bi;
+        cost += best;
+        threshold = best;
+    }
+    for (int i = 0; i < fc.nsrc; ++i) {
+        if (costrow[i] <= threshold) selected |= 1u << i;
+    }
+    return cost / top_k;
+}
+
+// ------------------------------------------------------------------------------------------
+// probes (parity tests): mode 0 ncc(view), 1 geom(view), 2 warp(view), 3 initial cost + views
+// thread per pixel, 16x8 tile
+// ------------------------------------------------------------------------------------------
+constexpr int kTpTW = 16, kTpTH = 8, kTpNT = 128;
+
+template <int MODEL>
+__global__ void __launch_bounds__(kTpNT)
+k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMap tmap, const int mode, const int view,
+        const float4 *__restrict__ planes, float *__restrict__ out, float4 *__restrict__ out4, uint32_t *__restrict__ out_views)
+{
+    typedef TileGeom<kTpTW, kTpTH> TG;
+    typedef typename AuxType<MODEL>::type AuxT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT> L(fc.nsrc, kTpNT, 0);
+    float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
+    AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
+    float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr);
+    ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
+    float *cost = reinterpret_cast<float *>(smem + L.off_cost);
+
+    const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
+    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, &tmap, x0, y0, tile_r, aux, s_vc, bar);
+
+    const int tid = threadIdx.x;
+    const int x = x0 + (tid % kTpTW), y = y0 + (tid / kTpTW);
+    if (x >= fc.W || y >= fc.H) return;
+    const int center = y * fc.W + x;
+    PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
+    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, wr + tid, 0, 1);
+    full_sums<kTpNT>(wr + tid, px);
+    const float4 plane = planes[center];
+    const int nvp = fc.nsrc | 1;
+    float *costrow = cost + tid * nvp;
+
+    if (mode == 0) {
+        ncc_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, wr + tid, px, plane, 1u << (view - 1), costrow, 1);
+        out[center] = costrow[view - 1];
+    } else if (mode == 1) {
+        out[center] = geom_cost<MODEL>(fc, s_vc[view - 1], px, plane);
+    } else if (mode == 2) {
+        const float depth = plane_depth(plane, px.dir);
+        float sx, sy, sd;
+        forward_project<MODEL>(fc, s_vc[view - 1], px, depth, sx, sy, sd);
+        out4[center] = make_float4(sx, sy, sd, depth);
+    } else {
+        uint32_t sel;
+        out[center] = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, wr + tid, px, plane, costrow, sel);
+        out_views[center] = sel;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// RandomInitialization, ACMMP.cu:673-795
+// ------------------------------------------------------------------------------------------
+// SpatialGauss / RangeGauss, ACMMP.cu:175-185 (double precision inside, float in/out)
+__device__ __forceinline__ float spatial_gauss(float x1, float y1, float x2, float y2, float sigma)
+{
+    const double ddx = (double)(x1 - x2), ddy = (double)(y1 - y2);      // pow(., 2) of a float is exact in double
+    const float dis = (float)(ddx * ddx + ddy * ddy - (double)0.0f);
+    return (float)exp(-1.0 * (double)dis / (double)(2 * sigma * sigma));
+}
+__device__ __forceinline__ float range_gauss(float x, float sigma)
+{
+    const float x_p = x - 0.0f;
+    return (float)exp(-1.0 * (double)(x_p * x_p) / (double)(2 * sigma * sigma));
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kTpNT)
+k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMap tmap)
+{
+    typedef TileGeom<kTpTW, kTpTH> TG;
+    typedef typename AuxType<MODEL>::type AuxT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT> L(fc.nsrc, kTpNT, 0);
+    float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
+    AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
+    float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr);
+    ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
+    float *cost = reinterpret_cast<float *>(smem + L.off_cost);
+
+    const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
+    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, &tmap, x0, y0, tile_r, aux, s_vc, bar);
+
+    const int tid = threadIdx.x;
+    const int x = x0 + (tid % kTpTW), y = y0 + (tid / kTpTW);
+    if (x >= fc.W || y >= fc.H) return;
+    const int center = y * fc.W + x;
+    PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
+    const float2 *mywr = wr + tid;
+    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, wr + tid, 0, 1);
+    full_sums<kTpNT>(mywr, px);
+    float *costrow = cost + tid * (fc.nsrc | 1);
+
+    Rng rs = rng_load(fc.rng_seeded + 3 * (size_t)center);     // curand_init(seed, y, x), ACMMP.cu:684
+    uint32_t sel = 0;
+    float4 plane;
+    float c;
+
+    if (!fc.geom && !fc.hierarchy) {
+        // GenerateRandomPlaneHypothesis, ACMMP.cu:259-265
+        const float depth = rng_uniform(rs) * (fc.depth_max - fc.depth_min) + fc.depth_min;
+        plane = random_normal(rs, px.dir);
+        plane.w = plane_offset(plane, px.dir, depth);
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+    } else if (fc.prior) {
+        if (fc.plane_masks[center] > 0 && fc.costs[center] >= 0.1f) {      // ACMMP.cu:691-703
+            const float perturbation = 0.02f;
+            const float4 prior = fc.prior_planes[center];
+            float depth_perturbed = prior.w;
+            const float depth_min_perturbed = (1 - 3 * perturbation) * depth_perturbed;
+            const float depth_max_perturbed = (1 + 3 * perturbation) * depth_perturbed;
+            depth_perturbed = rng_uniform(rs) * (depth_max_perturbed - depth_min_perturbed) + depth_min_perturbed;
+            plane = perturbed_normal(rs, px.dir, prior, (float)(3 * perturbation * 3.14159265358979323846));
+            plane.w = depth_perturbed;
+        } else {                                                          // ACMMP.cu:704-710
+            plane = fc.planes[center];
+            const float depth = plane.w;
+            plane.w = plane_offset(plane, px.dir, depth);
+        }
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+    } else if (fc.upsample) {
+        // joint-bilateral NORMAL upsampling from the coarse level, ACMMP.cu:713-779
+        const float scaled_cols = (float)fc.scaled_cols, scaled_rows = (float)fc.scaled_rows;
+        const float scale = (float)(1.0 * scaled_cols / fc.W);
+        const float sigmad = 0.50f, sigmar = 25.5f;
+        const int Imagescale = (int)fmaxf(fc.W / scaled_cols, fc.H / scaled_rows);
+        const int WinWidth = Imagescale * Imagescale + 1;
+        const int num_neighbors = WinWidth / 2;           // host guarantees <= kHalo
+        const float o_y = y * scale, o_x = x * scale;
+        const float refPix = tile_r[px.ty * TG::PW + px.tx];
+        float normalizing_factor = 0.0f;
+        float4 n_total = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = -num_neighbors; j <= num_neighbors; ++j) {
+            int r_y = (int)(o_y + j);
+            r_y = (r_y > 0 ? (r_y < scaled_rows ? r_y : (int)(scaled_rows - 1)) : 0);
+            for (int i = -num_neighbors; i <= num_neighbors; ++i) {
+                int r_x = (int)(o_x + i);
+                r_x = (r_x > 0 ? (r_x < scaled_cols ? r_x : (int)(scaled_cols - 1)) : 0);
+                const int s_center = (int)(r_y * scaled_cols + r_x);
+                float4 srcNorm = fc.coarse_planes[s_center];
+                const float neighborPix = tile_r[(px.ty + j) * TG::PW + (px.tx + i)];
+                const float sgauss = spatial_gauss(o_x, o_y, (float)r_x, (float)r_y, sigmad);
+                const float rgauss = range_gauss(fabsf(refPix - neighborPix), sigmar);
+                const float totalgauss = sgauss * rgauss;
+                normalizing_factor += totalgauss;
+                srcNorm.x = srcNorm.x * totalgauss;
+                srcNorm.y = srcNorm.y * totalgauss;
+                srcNorm.z = srcNorm.z * totalgauss;
+                n_total.x = n_total.x + srcNorm.x;
+                n_total.y = n_total.y + srcNorm.y;
+                n_total.z = n_total.z + srcNorm.z;
+            }
+        }
+        n_total.x = n_total.x / normalizing_factor;
+        n_total.y = n_total.y / normalizing_factor;
+        n_total.z = n_total.z / normalizing_factor;
+        normalize3(n_total);
+        // cost of the plane exactly as uploaded (normal part defined as 0 here) -> pre_costs, :770-771
+        const float4 uploaded = fc.planes[center];
+        uint32_t sel0;
+        const float c0 = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, uploaded, costrow, sel0);
+        fc.pre_costs[center] = c0;
+        plane = normal_to_cam(fc, n_total);
+        plane.w = plane_offset(plane, px.dir, uploaded.w);
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+    } else {
+        // reload, ACMMP.cu:780-793
+        plane = fc.hierarchy ? fc.coarse_planes[center] : fc.planes[center];
+        plane = normal_to_cam(fc, plane);
+        const float depth = plane.w;
+        plane.w = plane_offset(plane, px.dir, depth);
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+    }
+    fc.planes[center] = plane;
+    fc.costs[center] = c;
+    fc.selected_views[center] = sel;
+    rng_store(fc.rng + 3 * (size_t)center, rs);
+}
+
+// ------------------------------------------------------------------------------------------
+// checkerboard pass
+// ------------------------------------------------------------------------------------------
+constexpr int kPassTW = 8, kPassTH = 8, kPassNT = 256, kPassPix = 32;
+
+// FindMinCostIndex / FindMaxCostIndex, ACMMP.cu:62-86 (ties -> last index)
+__device__ __forceinline__ int find_min_idx(const float (&c)[8])
+{
+    float m = c[0];
+    int mi = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        if (c[i] <= m) { m = c[i]; mi = i; }
+    }
+    return mi;
+}
+__device__ __forceinline__ int find_max_idx(const float (&c)[8])
+{
+    float m = c[0];
+    int mi = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        if (c[i] >= m) { m = c[i]; mi = i; }
+    }
+    return mi;
+}
+
+__device__ __forceinline__ float4 shfl_plane(const unsigned gmask, const float4 &p, const int src)
+{
+    float4 r;
+    r.x = __shfl_sync(gmask, p.x, src);
+    r.y = __shfl_sync(gmask, p.y, src);
+    r.z = __shfl_sync(gmask, p.z, src);
+    r.w = __shfl_sync(gmask, p.w, src);
+    return r;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kPassNT, 2)
+k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMap tmap, const int colour, const int iter)
+{
+    typedef TileGeom<kPassTW, kPassTH> TG;
+    typedef typename AuxType<MODEL>::type AuxT;
+    constexpr int WRS = kPassPix;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout<MODEL, kPassTW, kPassTH, kPassPix> L(fc.nsrc, kPassNT, kPassPix);
+    float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
+    AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
+    float2 *wr_all = reinterpret_cast<float2 *>(smem + L.off_wr);
+    ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
+    float *cost_all = reinterpret_cast<float *>(smem + L.off_cost);
+    float *vw_all = reinterpret_cast<float *>(smem + L.off_vw);
+    float *probs_all = reinterpret_cast<float *>(smem + L.off_probs);
+
+    const int W = fc.W, H = fc.H;
+    const int x0 = blockIdx.x * kPassTW, y0 = blockIdx.y * kPassTH;
+    const int tid = threadIdx.x;
+
+    // pixels of the other colour are carried over to the output buffers unchanged
+    if (tid < kPassPix) {
+        const int yy = y0 + (tid >> 2);
+        const int xx = x0 + 2 * (tid & 3) + ((yy + colour + 1) & 1);
+        if (xx < W && yy < H) {
+            const int cc = yy * W + xx;
+            fc.planes_alt[cc] = fc.planes[cc];
+            fc.costs_alt[cc] = fc.costs[cc];
+        }
+    }
+
+    stage_tile<MODEL, kPassTW, kPassTH, kPassNT>(fc, &tmap, x0, y0, tile_r, aux, s_vc, bar);
+
+    const int g = tid >> 3;            // pixel slot in the CTA
+    const int gl = tid & 7;            // lane in the pixel group == candidate direction
+    const int lane = tid & 31;
+    const int gbase = lane & ~7;       // first lane of the group inside the warp
+    const unsigned gmask = 0xFFu << gbase;
+    const int y = y0 + (g >> 2);
+    const int x = x0 + 2 * (g & 3) + ((y + colour) & 1);
+    if (x >= W || y >= H) return;      // whole groups leave together; no block-wide sync below
+
+    const int center = y * W + x;
+    const int nsrc = fc.nsrc;
+    const int nvp = nsrc | 1;
+    PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
+    float2 *wr = wr_all + g;
+    float *costrow = cost_all + (g * 8 + gl) * nvp;
+    float *cost_grp = cost_all + (g * 8) * nvp;
+    float *vw = vw_all + g * nvp;
+    float *probs = probs_all + g * nvp;
+    const float4 *planes_in = fc.planes;
+    const float *costs_in = fc.costs;
+
+    fill_weights<MODEL, TG::PW, WRS>(fc, tile_r, px, wr, gl, 8);
+
+    // ---- adaptive checkerboard sampling: lane l scans direction l (ACMMP.cu:965-1143) -------
+    // 0 up_near 1 up_far 2 down_near 3 down_far 4 left_near 5 left_far 6 right_near 7 right_far
+    bool flag = false;
+    int pos = center;
+    {
+        const bool vertical = gl < 4;
+        const int du = (gl & 2) ? 1 : -1;
+        const bool far_dir = (gl & 1) != 0;
+        const int a = vertical ? y : x, A = vertical ? H : W;
+        const int b = vertical ? x : y, B = vertical ? W : H;
+        const int sa = vertical ? W : 1, sb = vertical ? 1 : W;
+#define ACMMP_INB(s) (du < 0 ? (a - (s) >= 0) : (a + (s) <= A - 1))
+        if (far_dir) {
+            flag = ACMMP_INB(3);
+            if (flag) {
+                pos = center + du * 3 * sa;
+                float cmin = costs_in[pos];
+                for (int i = 1; i < 11; ++i) {
+                    if (ACMMP_INB(3 + 2 * i)) {
+                        const int pt = center + du * (3 + 2 * i) * sa;
+                        const float cv = costs_in[pt];
+                        if (cv < cmin) { cmin = cv; pos = pt; }
+                    }
+                }
+            }
+        } else {
+            flag = ACMMP_INB(1);
+            if (flag) {
+                pos = center + du * sa;
+                float cmin = costs_in[pos];
+                for (int i = 0; i < 3; ++i) {
+                    if (ACMMP_INB(2 + i)) {
+                        if (b > i) {
+                            const int pt = center + du * (2 + i) * sa - i * sb;
+                            const float cv = costs_in[pt];
+                            if (cv < cmin) { cmin = cv; pos = pt; }
+                        }
+                        if (b < B - 1 - i) {
+                            const int pt = center + du * (2 + i) * sa + i * sb;
+                            const float cv = costs_in[pt];
+                            if (cv < cmin) { cmin = cv; pos = pt; }
+                        }
+                    }
+                }
+            }
+        }
+#undef ACMMP_INB
+    }
+    float4 cand = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (flag) cand = planes_in[pos];
+    // view bitmask of the immediate neighbour in this direction (near lanes; ACMMP.cu:1149-1160)
+    uint32_t nbsel = 0;
+    if (flag && !(gl & 1)) {
+        const int nb = (gl < 4) ? center + ((gl & 2) ? W : -W) : center + ((gl & 2) ? 1 : -1);
+        nbsel = fc.selected_views[nb];
+    }
+    const unsigned flagbits = (__ballot_sync(gmask, flag) >> gbase) & 0xFFu;
+
+    __syncwarp(gmask);
+    full_sums<WRS>(wr, px);
+
+    // ---- phase A: 8 neighbour hypotheses x all views (ACMMP.cu:981-1142) ---------------------
+    const uint32_t all_views = (nsrc >= 32) ? 0xffffffffu : ((1u << nsrc) - 1u);
+    if (flag) {
+        ncc_views<MODEL, TG::PW, TG::RW, WRS>(fc, s_vc, tile_r, aux, wr, px, cand, all_views, costrow, 1);
+    } else {
+        // `float cost_array[8][32] = {2.0f}` (ACMMP.cu:957): only element [0][0] is 2, the rest 0
+        for (int v = 0; v < nsrc; ++v) costrow[v] = (gl == 0 && v == 0) ? 2.0f : 0.0f;
+    }
+    __syncwarp(gmask);
+
+    // ---- multi-hypothesis joint view selection (ACMMP.cu:1146-1208) --------------------------
+    {
+        const float cost_threshold = (float)(0.8 * (double)expf((iter) * (iter) / (-90.0f)));
+        uint32_t nsel[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) nsel[n] = __shfl_sync(gmask, nbsel, gbase + 2 * n);
+        for (int i = gl; i < nsrc; i += 8) {
+            float prior = 0.0f;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                if ((flagbits >> (2 * n)) & 1u) prior += ((nsel[n] >> i) & 1u) ? 0.9f : 0.1f;
+            }
+            float count = 0;
+            int count_false = 0;
+            float tmpw = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float cj = cost_grp[j * nvp + i];
+                if (cj < cost_threshold) {
+                    tmpw += expf(cj * cj / (-0.18f));
+                    count++;
+                }
+                if (cj > 1.2f) count_false++;
+            }
+            float prob = 0.0f;
+            if (count > 2 && count_false < 3) {
+                prob = tmpw / count;
+            } else if (count_false < 3) {
+                prob = expf(cost_threshold * cost_threshold / (-0.32f));
+            }
+            probs[i] = prob * prior;
+        }
+    }
+    __syncwarp(gmask);
+
+    Rng rs;
+    uint32_t temp_selected_views = 0;
+    float weight_norm = 0;
+    if (gl == 0) {
+        rs = rng_load(fc.rng + 3 * (size_t)center);
+        // TransformPDFToCDF, ACMMP.cu:137-151
+        float prob_sum = 0.0f;
+        for (int i = 0; i < nsrc; ++i) prob_sum += probs[i];
+        const float inv_prob_sum = 1.0f / prob_sum;
+        float cum_prob = 0.0f;
+        for (int i = 0; i < nsrc; ++i) {
+            const float prob = probs[i] * inv_prob_sum;
+            cum_prob += prob;
+            probs[i] = cum_prob;
+            vw[i] = 0.0f;
+        }
+        for (int sample = 0; sample < 15; ++sample) {
+            const float rand_prob = rng_uniform(rs) - FLT_EPSILON;
+            for (int image_id = 0; image_id < nsrc; ++image_id) {
+                if (probs[image_id] > rand_prob) {
+                    vw[image_id] += 1.0f;
+                    break;
+                }
+            }
+        }
+        for (int i = 0; i < nsrc; ++i) {
+            if (vw[i] > 0) {
+                temp_selected_views |= 1u << i;
+                weight_norm += vw[i];
+            }
+        }
+    }
+    temp_selected_views = __shfl_sync(gmask, temp_selected_views, gbase);
+    weight_norm = __shfl_sync(gmask, weight_norm, gbase);
+    __syncwarp(gmask);
+
+    // ---- weighted neighbour costs and arg-min over the 8 lanes (ACMMP.cu:1210-1230) ----------
+    float final_cost = 0.0f;
+    for (int j = 0; j < nsrc; ++j) {
+        const float wj = vw[j];
+        if (wj > 0) {
+            if (fc.geom) {
+                if (flag) {
+                    final_cost += wj * (costrow[j] + 0.2f * geom_cost<MODEL>(fc, s_vc[j], px, cand));
+                } else {
+                    final_cost += wj * (costrow[j] + 0.1f * 3.0f);
+                }
+            } else {
+                final_cost += wj * costrow[j];
+            }
+        }
+    }
+    final_cost /= weight_norm;
+    float final_costs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) final_costs[k] = __shfl_sync(gmask, final_cost, gbase + k);
+    const int min_cost_idx = find_min_idx(final_costs);
+
+    // ---- cost of the current plane, taps split over the group (ACMMP.cu:1232-1245) -----------
+    const float4 cur_plane = planes_in[center];
+    float cost_now = 0.0f;
+    for (int j = 0; j < nsrc; ++j) {
+        const float wj = vw[j];
+        if (wj > 0) {       // zero-weight views contribute exactly 0 in the reference's sum
+            const float cj = ncc_tapsplit<MODEL, TG::PW, TG::RW, WRS>(fc, s_vc[j], tile_r, aux, wr, px, cur_plane, gl, gmask);
+            if (fc.geom) {
+                cost_now += wj * (cj + 0.2f * geom_cost<MODEL>(fc, s_vc[j], px, cur_plane));
+            } else {
+                cost_now += wj * cj;
+            }
+        }
+    }
+    cost_now /= weight_norm;
+    float depth_now = plane_depth(cur_plane, px.dir);
+
+    // what memory holds for [center] unless the final write-back replaces it
+    float4 plane_center = cur_plane;
+    float cost_center = cost_now;                        // ACMMP.cu:1244
+    uint32_t sel_center = 0;
+    bool sel_dirty = false;
+    float restricted_cost = 0.0f;
+    float4 plane_now = cur_plane;
+    bool have_plane_now = false;                         // as-compiled semantics, see below
+    float4 plane_intended = cur_plane;                   // "the plane the pixel currently holds"
+
+    const uint32_t mask_c = fc.prior ? fc.plane_masks[center] : 0u;
+    float4 prior_plane = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fc.prior && mask_c > 0) prior_plane = fc.prior_planes[center];
+    const float depth_sigma = (fc.depth_max - fc.depth_min) / 64.0f;
+    const float two_depth_sigma_squared = 2 * depth_sigma * depth_sigma;
+    const float beta = 0.18f;
+    const float gamma = 0.5f;
+
+    if (fc.prior) {                                      // ACMMP.cu:1247-1299
+        if (mask_c > 0) {
+            const float angle_sigma = (float)(3.14159265358979323846 * (double)(5.0f / 180.0f));
+            const float two_angle_sigma_squared = 2 * angle_sigma * angle_sigma;
+            const float depth_prior = plane_depth(prior_plane, px.dir);
+            float restricted = 0.0f;
+            if (flag) {
+                const float depth_c = plane_depth(cand, px.dir);
+                const float depth_diff = depth_c - depth_prior;
+                const float angle_cos = dot3(prior_plane, cand);
+                const float angle_diff = acosf(angle_cos);
+                const float prior = gamma + expf(-depth_diff * depth_diff / two_depth_sigma_squared) *
+                                                expf(-angle_diff * angle_diff / two_angle_sigma_squared);
+                restricted = expf(-final_cost * final_cost / beta) * prior;
+            }
+            float restricted_final_costs[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) restricted_final_costs[k] = __shfl_sync(gmask, restricted, gbase + k);
+            const int max_cost_idx = find_max_idx(restricted_final_costs);
+
+            float restricted_cost_now;
+            {
+                const float depth_diff = depth_now - depth_prior;
+                const float angle_cos = dot3(prior_plane, cur_plane);
+                const float angle_diff = acosf(angle_cos);
+                const float prior = gamma + expf(-depth_diff * depth_diff / two_depth_sigma_squared) *
+                                                expf(-angle_diff * angle_diff / two_angle_sigma_squared);
+                restricted_cost_now = expf(-cost_now * cost_now / beta) * prior;
+            }
+            const float4 nb = shfl_plane(gmask, cand, gbase + max_cost_idx);
+            if ((flagbits >> max_cost_idx) & 1u) {
+                plane_now = nb;
+                have_plane_now = true;
+                const float depth_before = plane_depth(nb, px.dir);
+                if (depth_before >= fc.depth_min && depth_before <= fc.depth_max &&
+                    restricted_final_costs[max_cost_idx] > restricted_cost_now) {
+                    // note: the reference updates a SHADOWING depth_now here (ACMMP.cu:1271, :1282)
+                    plane_center = nb;
+                    plane_intended = nb;
+                    cost_center = final_costs[max_cost_idx];
+                    restricted_cost = restricted_final_costs[max_cost_idx];
+                    sel_center = temp_selected_views;
+                    sel_dirty = true;
+                }
+            }
+        } else {
+            const float4 nb = shfl_plane(gmask, cand, gbase + min_cost_idx);
+            if ((flagbits >> min_cost_idx) & 1u) {
+                plane_now = nb;
+                have_plane_now = true;
+                const float depth_before = plane_depth(nb, px.dir);
+                if (depth_before >= fc.depth_min && depth_before <= fc.depth_max && final_costs[min_cost_idx] < cost_now) {
+                    depth_now = depth_before;
+                    plane_center = nb;
+                    plane_intended = nb;
+                    cost_center = final_costs[min_cost_idx];
+                }
+            }
+        }
+    } else {                                             // ACMMP.cu:1301-1311
+        const float4 nb = shfl_plane(gmask, cand, gbase + min_cost_idx);
+        if ((flagbits >> min_cost_idx) & 1u) {
+            const float depth_before = plane_depth(nb, px.dir);
+            const bool accept = depth_before >= fc.depth_min && depth_before <= fc.depth_max && final_costs[min_cost_idx] < cost_now;
+            plane_now = nb;
+            have_plane_now = true;
+            if (accept) {
+                depth_now = depth_before;
+                cost_now = final_costs[min_cost_idx];
+                sel_center = temp_selected_views;
+                sel_dirty = true;
+                plane_intended = nb;      // registers only: memory keeps the old plane (ACMMP.cu:1307)
+            }
+        }
+    }
+    // `float4 plane_hypotheses_now;` is uninitialised in the reference (ACMMP.cu:1301).  The nvcc
+    // 12.9 / sm_100 binary keeps the best neighbour's plane there whenever that neighbour exists
+    // (as_compiled); the intended meaning is "the plane currently stored for the pixel".
+    if (!fc.as_compiled || !have_plane_now) plane_now = plane_intended;
+
+    // ---- PlaneHypothesisRefinement, ACMMP.cu:797-936 -----------------------------------------
+    if (weight_norm > 0.0f) {
+        const float perturbation = 0.02f;
+        const float angle_sigma = CUDART_PI_F * (5.0f / 180.0f);
+        const float two_angle_sigma_squared = 2 * angle_sigma * angle_sigma;
+        const bool use_prior = fc.prior && mask_c > 0;
+        float depth_prior = 0.f;
+        if (use_prior) depth_prior = plane_depth(prior_plane, px.dir);
+
+        float depth_rand = 0.f, depth_perturbed = 0.f;
+        float4 n_rand = make_float4(0.f, 0.f, 0.f, 0.f), n_pert = n_rand;
+        if (gl == 0) {
+            if (use_prior) {
+                depth_rand = sample_depth_inv(rs, fmaxf(depth_prior - 3 * depth_sigma, fc.depth_min),
+                                              fminf(depth_prior + 3 * depth_sigma, fc.depth_max));
+                n_rand = perturbed_normal(rs, px.dir, prior_plane, angle_sigma);
+            } else {
+                depth_rand = sample_depth_inv(rs, fc.depth_min, fc.depth_max);
+                n_rand = random_normal(rs, px.dir);
+            }
+            float lo = fmaxf((1.0f - perturbation) * depth_now, fc.depth_min);
+            float hi = fminf((1.0f + perturbation) * depth_now, fc.depth_max);
+            if (!(hi > lo)) { lo = fc.depth_min; hi = fc.depth_max; }
+            depth_perturbed = depth_now;
+            bool ok = false;
+            for (int k = 0; k < 32; ++k) {
+                const float cnd = sample_depth_inv(rs, lo, hi);
+                if (cnd >= fc.depth_min && cnd <= fc.depth_max) {
+                    depth_perturbed = cnd;
+                    ok = true;
+                    break;
+                }
+            }
+            if (!ok) depth_perturbed = fminf(fmaxf(depth_now, fc.depth_min), fc.depth_max);
+            n_pert = perturbed_normal(rs, px.dir, plane_now, perturbation * CUDART_PI_F);
+        }
+        depth_rand = __shfl_sync(gmask, depth_rand, gbase);
+        depth_perturbed = __shfl_sync(gmask, depth_perturbed, gbase);
+        n_rand = shfl_plane(gmask, n_rand, gbase);
+        n_pert = shfl_plane(gmask, n_pert, gbase);
+
+        // candidate gl (0..4): depths {rand, now, rand, now, pert}, normals {now, rand, rand, pert, now}
+        float cdepth = depth_now;
+        float4 temp_plane = plane_now;
+        if (gl == 0 || gl == 2) cdepth = depth_rand;
+        if (gl == 4) cdepth = depth_perturbed;
+        if (gl == 1 || gl == 2) temp_plane = n_rand;
+        if (gl == 3) temp_plane = n_pert;
+        temp_plane.w = plane_offset(temp_plane, px.dir, cdepth);
+
+        float temp_cost = 0.0f;
+        float depth_before = 0.f;
+        bool cand_ok = false;
+        float restricted_temp_cost = 0.f;
+        if (gl < 5) {
+            ncc_views<MODEL, TG::PW, TG::RW, WRS>(fc, s_vc, tile_r, aux, wr, px, temp_plane, temp_selected_views, costrow, 1);
+            for (int j = 0; j < nsrc; ++j) {
+                const float wj = vw[j];
+                if (wj > 0.0f) {
+                    if (fc.geom) {
+                        temp_cost += wj * (costrow[j] + 0.1f * geom_cost<MODEL>(fc, s_vc[j], px, temp_plane));
+                    } else {
+                        temp_cost += wj * costrow[j];
+                    }
+                }
+            }
+            temp_cost /= weight_norm;
+            depth_before = plane_depth(temp_plane, px.dir);
+            cand_ok = !(depth_before < fc.depth_min || depth_before > fc.depth_max || depth_before >= 1e6f);
+            if (use_prior) {
+                const float depth_diff = cdepth - depth_prior;
+                float angle_cos = dot3(prior_plane, temp_plane);
+                angle_cos = fminf(fmaxf(angle_cos, -1.0f), 1.0f);
+                const float angle_diff = acosf(angle_cos);
+                const float prior = gamma + expf(-depth_diff * depth_diff / two_depth_sigma_squared) *
+                                                expf(-angle_diff * angle_diff / two_angle_sigma_squared);
+                restricted_temp_cost = expf(-temp_cost * temp_cost / beta) * prior;
+            }
+        }
+        // sequential acceptance over the five candidates (ACMMP.cu:876-935)
+        int best = -1;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const float tc_i = __shfl_sync(gmask, temp_cost, gbase + i);
+            const float rc_i = __shfl_sync(gmask, restricted_temp_cost, gbase + i);
+            const int ok_i = __shfl_sync(gmask, (int)cand_ok, gbase + i);
+            if (ok_i) {
+                if (use_prior) {
+                    if (rc_i > restricted_cost) { restricted_cost = rc_i; cost_now = tc_i; best = i; }
+                } else {
+                    if (tc_i < cost_now) { cost_now = tc_i; best = i; }
+                }
+            }
+        }
+        const int src = gbase + (best < 0 ? 0 : best);
+        const float4 bp = shfl_plane(gmask, temp_plane, src);
+        const float bd = __shfl_sync(gmask, depth_before, src);
+        if (best >= 0) {
+            plane_now = bp;
+            depth_now = bd;
+        }
+    }
+
+    // ---- write-back (ACMMP.cu:1315-1324) ------------------------------------------------------
+    if (gl == 0) {
+        float4 out_plane = plane_now;
+        float out_cost = cost_now;
+        if (fc.hierarchy) {
+            if (!(cost_now < fc.pre_costs[center] - 0.1f)) {
+                out_plane = plane_center;
+                out_cost = cost_center;
+            }
+        }
+        fc.planes_alt[center] = out_plane;
+        fc.costs_alt[center] = out_cost;
+        if (sel_dirty) fc.selected_views[center] = sel_center;
+        rng_store(fc.rng + 3 * (size_t)center, rs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GetDepthandNormal, ACMMP.cu:1351-1364: (n_cam, d) -> (n_world, depth); one float4 per thread
+// ------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+k_depth_normal(const __grid_constant__ FrameConst fc)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= fc.W * fc.H) return;
+    const int x = idx % fc.W, y = idx / fc.W;
+    float4 p = fc.planes[idx];
+    p.w = plane_depth(p, pixel_dir<MODEL>(fc, x, y));
+    fc.planes[idx] = normal_to_world(fc, p);
+}
+
+// CheckerboardFilter, ACMMP.cu:1366-1480: median of up to 21 depths, in place, one colour per
+// launch.  All 20 neighbour offsets have odd Manhattan distance, i.e. the other colour, so a
+// launch never reads what it writes.
+__global__ void __launch_bounds__(256)
+k_median_filter(const __grid_constant__ FrameConst fc, const int colour)
+{
+    const int W = fc.W, H = fc.H;
+    const int half = (W + 1) / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= half * H) return;
+    const int y = idx / half;
+    const int x = 2 * (idx % half) + ((y + colour) & 1);
+    if (x >= W) return;
+    const int center = y * W + x;
+    float4 *ph = fc.planes;
+    float filter[21];
+    int index = 0;
+    filter[index++] = ph[center].w;
+    if (fc.costs[center] < 0.001f) return;
+    const int left = center - 1, leftleft = center - 3;
+    const int up = center - W, upup = center - 3 * W;
+    const int down = center + W, downdown = center + 3 * W;
+    const int right = center + 1, rightright = center + 3;
+    if (y > 0) filter[index++] = ph[up].w;
+    if (y > 2) filter[index++] = ph[upup].w;
+    if (y > 4) filter[index++] = ph[upup - W * 2].w;
+    if (y < H - 1) filter[index++] = ph[down].w;
+    if (y < H - 3) filter[index++] = ph[downdown].w;
+    if (y < H - 5) filter[index++] = ph[downdown + W * 2].w;
+    if (x > 0) filter[index++] = ph[left].w;
+    if (x > 2) filter[index++] = ph[leftleft].w;
+    if (x > 4) filter[index++] = ph[leftleft - 2].w;
+    if (x < W - 1) filter[index++] = ph[right].w;
+    if (x < W - 3) filter[index++] = ph[rightright].w;
+    if (x < W - 5) filter[index++] = ph[rightright + 2].w;
+    if (y > 0 && x < W - 2) filter[index++] = ph[up + 2].w;
+    if (y < H - 1 && x < W - 2) filter[index++] = ph[down + 2].w;
+    if (y > 0 && x > 1) filter[index++] = ph[up - 2].w;
+    if (y < H - 1 && x > 1) filter[index++] = ph[down - 2].w;
+    if (x > 0 && y > 2) filter[index++] = ph[left - W * 2].w;
+    if (x < W - 1 && y > 2) filter[index++] = ph[right - W * 2].w;
+    if (x > 0 && y < H - 2) filter[index++] = ph[left + W * 2].w;
+    if (x < W - 1 && y < H - 2) filter[index++] = ph[right + W * 2].w;
+    // sort_small, ACMMP.cu:36-45
+    for (int i = 1; i < index; i++) {
+        const float tmp = filter[i];
+        int j;
+        for (j = i; j >= 1 && tmp < filter[j - 1]; j--) filter[j] = filter[j - 1];
+        filter[j] = tmp;
+    }
+    const int median_index = index / 2;
+    if (index % 2 == 0) {
+        ph[center].w = (filter[median_index - 1] + filter[median_index]) / 2;
+    } else {
+        ph[center].w = filter[median_index];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// JBU_cu, ACMMP.cu:1558-1616.  image: fine grey image (w x h), depth_in: coarse (sw x sh).
+// Both are read at integer texel centres in the reference, i.e. exact values: plain loads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_jbu(const float *__restrict__ image, const int cols, const int rows, const float *__restrict__ depth_in, const int s_width,
+      const int s_height, const int Imagescale, float *__restrict__ depth_out)
+{
+    const int px = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int py = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (px >= cols || py >= rows) return;
+    const int center = py * cols + px;
+    const float scale = (float)(1.0 * s_width / cols);
+    const float sigmad = 0.50f, sigmar = 25.5f;
+    const int WinWidth = Imagescale * Imagescale + 1;
+    const int num_neighbors = WinWidth / 2;
+    const float o_y = py * scale, o_x = px * scale;
+    const float refPix = image[center];
+    float total_val = 0.0f, normalizing_factor = 0.0f;
+    for (int j = -num_neighbors; j <= num_neighbors; ++j) {
+        int r_y = (int)(o_y + j);
+        r_y = (r_y > 0 ? (r_y < s_height ? r_y : s_height - 1) : 0);
+        int r_ys = py + j;
+        r_ys = (r_ys > 0 ? (r_ys < rows ? r_ys : rows - 1) : 0);
+        for (int i = -num_neighbors; i <= num_neighbors; ++i) {
+            int r_x = (int)(o_x + i);
+            r_x = (r_x > 0 ? (r_x < s_width ? r_x : s_width - 1) : 0);
+            const float srcPix = __ldg(depth_in + r_y * s_width + r_x);
+            int r_xs = px + i;
+            r_xs = (r_xs > 0 ? (r_xs < cols ? r_xs : cols - 1) : 0);
+            const float neighborPix = __ldg(image + r_ys * cols + r_xs);
+            const float sgauss = spatial_gauss(o_x, o_y, (float)r_x, (float)r_y, sigmad);
+            const float rgauss = range_gauss(fabsf(refPix - neighborPix), sigmar);
+            const float totalgauss = sgauss * rgauss;
+            normalizing_factor += totalgauss;
+            total_val += srcPix * totalgauss;
+        }
+    }
+    depth_out[center] = total_val / normalizing_factor;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------
+// dense W x H image -> border-replicated pitch-linear image (clamp addressing of the reference's
+// reference-view texture, ACMMP.cpp:698-704, made explicit so that TMA never leaves the tensor)
+__global__ void __launch_bounds__(256)
+k_pad_reference(const float *__restrict__ src, const int W, const int H, float *__restrict__ dst, const int pitch)
+{
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y;
+    if (px >= pitch) return;
+    const int sx = min(max(px - kRefPad, 0), W - 1);
+    const int sy = min(max(py - kRefPad, 0), H - 1);
+    dst[(size_t)py * pitch + px] = src[(size_t)sy * W + sx];
+}
+
+// XORWOW state of every pixel right after curand_init(seed, subsequence = y, offset = x):
+// row_states[y] = state after the sequence skip (computed on the host from the 2^67-step matrix),
+// then x single steps along the row.  One thread per row.
+__global__ void __launch_bounds__(64)
+k_rng_fill(const uint32_t *__restrict__ row_states, const int W, const int H, uint2 *__restrict__ out)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= H) return;
+    Rng s;
+    s.d = row_states[6 * y + 0];
+    s.v0 = row_states[6 * y + 1]; s.v1 = row_states[6 * y + 2]; s.v2 = row_states[6 * y + 3];
+    s.v3 = row_states[6 * y + 4]; s.v4 = row_states[6 * y + 5];
+    uint2 *row = out + 3 * (size_t)y * W;
+    for (int x = 0; x < W; ++x) {
+        rng_store(row + 3 * x, s);
+        rng_next(s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_export_depth(const float4 *__restrict__ planes, const int n, float *__restrict__ depth)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) depth[idx] = planes[idx].w;
+}
+
+__global__ void __launch_bounds__(256)
+k_import_planes(const float4 *__restrict__ normals_depth, const int n, float4 *__restrict__ planes)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) planes[idx] = normals_depth[idx];
+}
+
+} // namespace acmmp

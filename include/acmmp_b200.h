@@ -1,0 +1,208 @@
+/* include/acmmp_b200.h -- C ABI of libacmmp_b200.so
+ *
+ * B200-native (sm_100a) PatchMatch depth/normal estimation, drop-in for the device side of the
+ * reference's `ACMMP` host class (reference ACMMP.h:57-111).  Plain pointers and sizes only; every
+ * entry point returns 0 on success or a negative ACMMP_E_* code (the reference prints and calls
+ * exit(), ACMMP.cpp:64-97; a library must not).  There is NO CPU fallback: every compute entry
+ * point fails with ACMMP_E_CUDA when no sm_100 device is usable.
+ *
+ * Which reference interface each entry point replaces is cited per declaration
+ * (file:line into the reference tree).
+ */
+#ifndef ACMMP_B200_H_
+#define ACMMP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACMMP_OK 0
+#define ACMMP_E_ARG (-1)       /* bad argument / call order */
+#define ACMMP_E_CUDA (-2)      /* CUDA runtime or driver failure (message: acmmp_last_error) */
+#define ACMMP_E_UNSUPPORTED (-3)
+
+#define ACMMP_MODEL_PINHOLE 0  /* reference main.h:35-38 */
+#define ACMMP_MODEL_SPHERE 11
+#define ACMMP_MAX_SRC 32       /* reference ACMMP.cu:522 (cost_vector[32]) and the 32-bit view mask */
+
+/* Byte-for-byte the reference `struct Camera` (main.h:40-54), 120 bytes. */
+typedef struct acmmp_camera {
+    int32_t model;       /* ACMMP_MODEL_* */
+    float params[4];     /* SPHERE: f, cx, cy, unused */
+    float R[9];          /* world -> camera, row major */
+    float t[3];
+    float K[9];          /* PINHOLE intrinsics, row major */
+    int32_t width, height;
+    float depth_min, depth_max;
+} acmmp_camera;
+
+/* Byte-for-byte the reference `struct PatchMatchParams` (ACMMP.h:32-55), 68 bytes.
+ * patch_size / radius_increment / sigma_* / top_k are accepted only at the reference defaults
+ * (11 / 2 / 5 / 3 / 4): the kernels are specialised for the 6x6-tap window. */
+typedef struct acmmp_params {
+    int32_t max_iterations;
+    int32_t patch_size;
+    int32_t num_images;
+    int32_t max_image_size;
+    int32_t radius_increment;
+    float sigma_spatial;
+    float sigma_color;
+    int32_t top_k;
+    float baseline;
+    float depth_min;
+    float depth_max;
+    float disparity_min;
+    float disparity_max;
+    float scaled_cols;
+    float scaled_rows;
+    uint8_t geom_consistency;
+    uint8_t planar_prior;
+    uint8_t multi_geometry;
+    uint8_t hierarchy;
+    uint8_t upsample;
+    uint8_t pad_[3];
+} acmmp_params;
+
+typedef struct acmmp_ctx acmmp_ctx;
+
+/* Fill *p with the reference defaults (ACMMP.h:33-54). */
+void acmmp_default_params(acmmp_params *p);
+
+/* Library / build information (never touches the GPU). */
+const char *acmmp_version(void);
+int acmmp_abi_sizeof_camera(void);
+int acmmp_abi_sizeof_params(void);
+
+/* One context per reference view being processed == one reference `ACMMP` object
+ * (constructor ACMMP.cpp:99, destructor :101-143).  `device` is the CUDA ordinal
+ * (the reference hard-codes cudaSetDevice(0), main.cpp:77). */
+int acmmp_create(acmmp_ctx **out, int device);
+int acmmp_destroy(acmmp_ctx *ctx);
+const char *acmmp_last_error(const acmmp_ctx *ctx);
+
+/* Replaces the upload half of ACMMP::CudaSpaceInitialization (ACMMP.cpp:685-724): image 0 is the
+ * reference view, images 1..n-1 the source views; images[i] is a dense row-major float32 array
+ * widths[i] x heights[i] in HOST memory (grey levels 0..255 as produced by InuputInitialization,
+ * ACMMP.cpp:578-581, :626-628).  cams[i].width/height are overwritten from widths/heights.
+ * Source views become R32F bilinear textures (clamp addressing, un-normalised coordinates: what
+ * ACMMP.cpp:698-704 effectively configures); the reference view additionally becomes a
+ * border-replicated pitch-linear image that the kernels stage into shared memory with TMA.
+ * params->depth_min/max and num_images are derived as ACMMP.cpp:645-648 does. */
+int acmmp_set_views(acmmp_ctx *ctx, int n, const float *const *images, const int32_t *widths,
+                    const int32_t *heights, const acmmp_camera *cams);
+
+/* Same, but images[i] are DEVICE pointers (dense row-major float32) on the context's device:
+ * the GPU-resident pipeline and bench.py's device-resident arm use this. */
+int acmmp_set_views_device(acmmp_ctx *ctx, int n, const float *const *images_dev, const int32_t *widths,
+                           const int32_t *heights, const acmmp_camera *cams);
+
+/* Mode flags, the reference setters ACMMP.cpp:548-565 (SetGeomConsistencyParams,
+ * SetHierarchyParams, SetPlanarPriorParams) plus max_iterations. */
+int acmmp_set_geom_consistency(acmmp_ctx *ctx, int multi_geometry);
+int acmmp_set_hierarchy(acmmp_ctx *ctx);
+int acmmp_set_planar_prior(acmmp_ctx *ctx);
+int acmmp_set_max_iterations(acmmp_ctx *ctx, int n);
+int acmmp_get_params(const acmmp_ctx *ctx, acmmp_params *out);
+
+/* Geometric consistency inputs: the n depth maps (index 0 = reference view, 1.. = source views)
+ * that InuputInitialization reads from depths.dmb / depths_geom.dmb (ACMMP.cpp:653-678) and
+ * CudaSpaceInitialization uploads (ACMMP.cpp:726-751).  Host pointers, dense float32. */
+int acmmp_set_depth_maps(acmmp_ctx *ctx, int n, const float *const *maps, const int32_t *widths,
+                         const int32_t *heights);
+int acmmp_set_depth_maps_device(acmmp_ctx *ctx, int n, const float *const *maps_dev, const int32_t *widths,
+                                const int32_t *heights);
+
+/* Previous-stage state of the reference view, W*H float4 (world normal xyz, depth w) + W*H costs:
+ * the reload at ACMMP.cpp:753-785 (geom mode).  Host pointers. */
+int acmmp_set_planes(acmmp_ctx *ctx, const float *planes4, const float *costs);
+
+/* Hierarchy inputs (ACMMP.cpp:788-844): coarse-level (normal xyz, w) map of size sw x sh -- w is the
+ * coarse COST when sw x sh differs from the image size (upsample mode, ACMMP.cpp:823-825), else the
+ * depth -- and the fine-level depth map (JBU output) that seeds plane.w (ACMMP.cpp:833-840; the
+ * normal part the reference leaves uninitialised is defined as 0 here). */
+int acmmp_set_hierarchy_inputs(acmmp_ctx *ctx, const float *coarse_planes4, int sw, int sh,
+                               const float *fine_depth);
+
+/* Replaces ACMMP::CudaPlanarPriorInitialization (ACMMP.cpp:847-867): plane_params = n_planes x
+ * float4 (camera-frame normal, d); masks = W*H float, 1-based triangle id or 0.  Also sets
+ * planar_prior like SetPlanarPriorParams. */
+int acmmp_set_planar_prior_inputs(acmmp_ctx *ctx, const float *plane_params4, int n_planes, const float *masks);
+
+/* The reference seeds cuRAND XORWOW with clock64() per thread (ACMMP.cu:684); here the seed is
+ * explicit: state(pixel) = curand_init(seed, subsequence = y, offset = x). */
+int acmmp_set_seed(acmmp_ctx *ctx, uint64_t seed);
+
+/* 0: plane_now is the current plane unless a neighbour is accepted (what the source intends);
+ * 1 (default): what the reference BINARY does -- `float4 plane_hypotheses_now` is uninitialised
+ * (ACMMP.cu:1301) and nvcc 12.9 keeps the best neighbour's plane in it whenever that neighbour
+ * exists, accepted or not.  See DESIGN.md "undefined behaviour". */
+int acmmp_set_plane_now_semantics(acmmp_ctx *ctx, int as_compiled);
+
+/* Replaces ACMMP::RunPatchMatch (ACMMP.cu:1506-1556): init, max_iterations x (black, red),
+ * depth/normal extraction, two median passes, device->host copy of planes and costs.
+ * Asynchronous on the context's stream up to the final copy, which it waits for. */
+int acmmp_run_patch_match(acmmp_ctx *ctx);
+
+/* The same stages one launch at a time (what RunPatchMatch launches at ACMMP.cu:1534, :1538/:1540,
+ * :1545-:1551).  colour 0 = black, 1 = red.  No host synchronisation. */
+int acmmp_random_init(acmmp_ctx *ctx);
+int acmmp_checkerboard_pass(acmmp_ctx *ctx, int colour, int iter);
+int acmmp_finalize(acmmp_ctx *ctx);
+int acmmp_synchronize(acmmp_ctx *ctx);
+
+/* Replaces ACMMP::GetPlaneHypothesis / GetCost (ACMMP.cpp:884-892) in bulk: copies the host
+ * result of the last acmmp_run_patch_match. planes4: W*H*4 floats (world normal, depth). */
+int acmmp_get_result(acmmp_ctx *ctx, float *planes4, float *costs);
+int acmmp_width(const acmmp_ctx *ctx);
+int acmmp_height(const acmmp_ctx *ctx);
+
+/* Device-resident results for chaining stages without host round trips (valid until the context
+ * is destroyed or re-configured): float4 planes, float costs. */
+int acmmp_device_buffers(acmmp_ctx *ctx, void **planes4_dev, void **costs_dev);
+/* Pack plane.w (depth) of the current state into a dense float32 device map (what a neighbour
+ * needs for geometric consistency; what depths*.dmb holds). */
+int acmmp_export_depth_device(acmmp_ctx *ctx, float *depth_dev);
+
+/* Raw device state <-> host (tests, stage chaining).  Any pointer may be NULL.
+ * rand6: 6 x uint32 per pixel = XORWOW {d, v[0..4]}. */
+int acmmp_download_state(acmmp_ctx *ctx, float *planes4, float *costs, uint32_t *selected_views,
+                         uint32_t *rand6, float *pre_costs);
+int acmmp_upload_state(acmmp_ctx *ctx, const float *planes4, const float *costs, const uint32_t *selected_views,
+                       const uint32_t *rand6, const float *pre_costs);
+
+/* Replaces RunJBU / JBU::CudaRun / JBU_cu (ACMMP.cpp:1071-1122, ACMMP.cu:1558-1649) minus the file
+ * write: joint-bilateral upsampling of a coarse depth map (sw x sh) guided by the fine grey image
+ * (w x h).  Host pointers.  Returns ACMMP_E_ARG when max(h/sh, w/sw) == 1 (the reference returns
+ * without output, ACMMP.cpp:1077-1080). */
+int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_depth, int sw, int sh,
+              float *out_depth);
+int acmmp_jbu_device(int device, const float *image_dev, int w, int h, const float *coarse_depth_dev, int sw,
+                     int sh, float *out_depth_dev, void *cuda_stream);
+
+/* Deterministic sub-kernel probes (parity tests): evaluate, for every pixel p of the reference
+ * view and a caller-supplied per-pixel plane (camera-frame normal, d), with the SAME device code
+ * the checkerboard kernel runs:
+ *   ncc      : ComputeBilateralNCC against source view `view` (1-based)      (ACMMP.cu:405-516)
+ *   geom     : ComputeGeomConsistencyCost against depth map `view`            (ACMMP.cu:646-671)
+ *   warp     : (src x, src y, src depth, ref depth) of p under the plane       (ACMMP.cu:187, :565, :602)
+ *   initcost : ComputeMultiViewInitialCostandSelectedViews                     (ACMMP.cu:519-556)
+ * Host pointers; planes4 and out4 are W*H*4 floats. */
+int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out);
+int acmmp_probe_geom(acmmp_ctx *ctx, const float *planes4, int view, float *out);
+int acmmp_probe_warp(acmmp_ctx *ctx, const float *planes4, int view, float *out4);
+int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint32_t *selected_views);
+
+/* Timing of the last launches on the context's stream, CUDA events, milliseconds:
+ * what[0]=random_init, [1]=sum of checkerboard passes, [2]=finalize, [3]=number of passes,
+ * [4]=last pass.  Valid after acmmp_synchronize / acmmp_run_patch_match. */
+int acmmp_last_timings(acmmp_ctx *ctx, float what[8]);
+
+/* How many kernels of this library were launched on the context since creation. */
+int64_t acmmp_launch_count(const acmmp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACMMP_B200_H_ */
