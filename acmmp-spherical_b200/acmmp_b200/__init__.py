@@ -77,7 +77,7 @@ _EXPORTS = [
     "acmmp_default_params", "acmmp_version", "acmmp_abi_sizeof_camera", "acmmp_abi_sizeof_params",
     "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
-    "acmmp_get_params", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
+    "acmmp_get_params", "acmmp_reset_modes", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
     "acmmp_set_hierarchy_inputs", "acmmp_set_planar_prior_inputs", "acmmp_set_seed",
     "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
@@ -106,10 +106,7 @@ def lib() -> C.CDLL:
     l.acmmp_launch_count.restype = C.c_int64
     l.acmmp_launch_count.argtypes = [C.c_void_p]
     l.acmmp_set_seed.argtypes = [C.c_void_p, C.c_uint64]
-    for name in _EXPORTS:
-        fn = getattr(l, name)
-        if fn.argtypes is None and name not in ("acmmp_version", "acmmp_abi_sizeof_camera", "acmmp_abi_sizeof_params"):
-            fn.argtypes = None    # variadic-style: rely on explicit ctypes values at call sites
+    l.acmmp_last_jbu_ms.restype = C.c_float
     _lib = l
     return l
 
@@ -192,6 +189,9 @@ class Context:
 
     def set_max_iterations(self, n):
         self._ck(self._l.acmmp_set_max_iterations(self._h, C.c_int(n)), "set_max_iterations")
+
+    def reset_modes(self):
+        self._ck(self._l.acmmp_reset_modes(self._h), "acmmp_reset_modes")
 
     def params(self) -> Params:
         p = Params()
@@ -336,3 +336,7 @@ def jbu(image, coarse_depth, device=0):
     if rc != 0:
         raise AcmmpError(f"acmmp_jbu failed ({rc})")
     return out
+
+
+def last_jbu_ms() -> float:
+    return float(lib().acmmp_last_jbu_ms())

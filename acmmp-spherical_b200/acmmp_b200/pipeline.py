@@ -1,0 +1,257 @@
+"""Per-view multi-scale pipeline driver over the C ABI.
+
+Follows the reference's schedule for ONE reference view (main.cpp:417-476 + ProcessProblem,
+main.cpp:73-210): per pyramid level, [JBU of the previous level's depth] -> photometric stage
+(hierarchy at levels > 0) -> CPU planar prior -> planar-prior stage on the same object ->
+geometric-consistency stage x 2.  The reference passes state between stages through .dmb files and
+builds a new ACMMP object per stage; here one context per level is re-used and state is handed
+over as arrays.  The C++ twin of this file is ../host/acmmp_driver.cpp.
+
+Neighbour depth maps for the geometric stages come from `neighbour_depths` (the per-view results of
+the other views in a full run; benchmark runs use rendered stand-ins).
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import Context, jbu as jbu_host, last_jbu_ms, synth
+from .prior import planar_prior
+
+
+@dataclass
+class Level:
+    images: list            # [ref, src...] float32
+    cams: list
+    neighbour_depths: list  # depth maps of the source views at this level (float32), len == n-1
+
+
+@dataclass
+class StageTimes:
+    gpu_ms: float = 0.0          # CUDA-event time of the kernels (inputs resident)
+    wall_s: float = 0.0          # wall-clock inside API calls (H2D + kernels + D2H)
+    prior_cpu_s: float = 0.0     # CPU planar-prior stage (reported separately, like the reference's)
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    launches: int = 0
+    passes: int = 0
+    pass_ms: dict = field(default_factory=dict)    # stage name -> list of per-pass ms at the finest level
+
+
+def pyramid_sizes(width, height, max_image_size=3200, size_bound=1000):
+    """ComputeMultiScaleSettings + the per-scale size (main.cpp:35-71, :420-425)."""
+    max_size = min(max(width, height), max_image_size)
+    k, m = 0, max_size
+    while m > size_bound:
+        m //= 2
+        k += 1
+    return [int(max_size / (2 ** s)) for s in range(k, -1, -1)]       # coarsest first
+
+
+def build_levels(scene, ref, n_src=None):
+    imgs, cams, ids = scene.problem(ref)
+    if n_src is not None:
+        imgs, cams, ids = imgs[: n_src + 1], cams[: n_src + 1], ids[: n_src + 1]
+    import cv2
+    H, W = imgs[0].shape
+    levels = []
+    for size in pyramid_sizes(W, H):
+        li, lc = synth.scale_problem(imgs, cams, size)
+        nd = []
+        for k, vid in enumerate(ids[1:]):
+            h, w = li[k + 1].shape
+            d = scene.depths_gt[vid]
+            nd.append(d if d.shape == (h, w) else cv2.resize(d, (w, h), interpolation=cv2.INTER_NEAREST))
+        levels.append(Level(li, lc, nd))
+    return levels
+
+
+def _nbytes(*arrays):
+    return int(sum(a.nbytes for a in arrays if a is not None))
+
+
+class B200Backend:
+    """Stages through libacmmp_b200.so."""
+    name = "b200"
+
+    def __init__(self, device=0, seed=1234, as_compiled=True):
+        self.device, self.seed, self.as_compiled = device, seed, as_compiled
+        self.ctx = None
+        self.t = StageTimes()
+
+    def _run(self, stage, finest):
+        ctx = self.ctx
+        t0 = time.perf_counter()
+        ctx.run_patch_match()
+        planes, costs = ctx.get_result()
+        self.t.wall_s += time.perf_counter() - t0
+        tm = ctx.timings()
+        self.t.gpu_ms += tm["init_ms"] + tm["pass_sum_ms"] + tm["finalize_ms"]
+        self.t.passes += tm["n_pass"]
+        self.t.d2h_bytes += _nbytes(planes, costs)
+        if finest and tm["n_pass"]:
+            self.t.pass_ms.setdefault(stage, []).append(tm["pass_sum_ms"] / tm["n_pass"])
+        return planes, costs
+
+    def begin_level(self, level: Level):
+        t0 = time.perf_counter()
+        if self.ctx is None:
+            self.ctx = Context(self.device)
+            self.ctx.set_seed(self.seed)
+            self.ctx.set_plane_now_semantics(self.as_compiled)
+        self.ctx.reset_modes()
+        self.ctx.set_views(level.images, level.cams)
+        self.t.wall_s += time.perf_counter() - t0
+        self.t.h2d_bytes += _nbytes(*level.images)
+
+    def jbu(self, image, coarse_depth):
+        t0 = time.perf_counter()
+        out = jbu_host(image, coarse_depth, self.device)
+        self.t.wall_s += time.perf_counter() - t0
+        self.t.gpu_ms += last_jbu_ms()
+        self.t.h2d_bytes += _nbytes(image, coarse_depth)
+        self.t.d2h_bytes += _nbytes(out)
+        self.t.launches += 1
+        return out
+
+    def photometric(self, level, hier=None, finest=False):
+        ctx = self.ctx
+        t0 = time.perf_counter()
+        ctx.reset_modes()
+        if hier is not None:
+            coarse4, fine_depth = hier
+            ctx.set_hierarchy()
+            ctx.set_hierarchy_inputs(coarse4, fine_depth)
+            self.t.h2d_bytes += _nbytes(coarse4, fine_depth)
+        self.t.wall_s += time.perf_counter() - t0
+        return self._run("photometric", finest)
+
+    def prior(self, level, params, masks, finest=False):
+        t0 = time.perf_counter()
+        self.ctx.set_planar_prior_inputs(params, masks)
+        self.t.wall_s += time.perf_counter() - t0
+        self.t.h2d_bytes += _nbytes(masks) + 16 * masks.size
+        return self._run("prior", finest)
+
+    def geom(self, level, multi, own_planes, own_costs, depth_maps, finest=False):
+        ctx = self.ctx
+        t0 = time.perf_counter()
+        ctx.reset_modes()
+        ctx.set_geom_consistency(multi)
+        ctx.set_depth_maps(depth_maps)
+        ctx.set_planes(own_planes, own_costs)
+        self.t.wall_s += time.perf_counter() - t0
+        self.t.h2d_bytes += _nbytes(own_planes, own_costs, *depth_maps)
+        return self._run("geom", finest)
+
+    def end(self):
+        if self.ctx is not None:
+            self.t.launches += self.ctx.launch_count()
+            self.ctx.close()
+            self.ctx = None
+
+
+class ReferenceBackend:
+    """The same stages through the UNMODIFIED reference (oracle/_ref/libacmmp_ref.so): one new
+    `ACMMP` object per ProcessProblem call, state through .dmb files, exactly like main.cpp.
+    TEST / BASELINE INFRASTRUCTURE: imported lazily so that the product never loads the oracle."""
+    name = "reference"
+
+    def __init__(self, device=0, seed=1234):
+        self.seed = seed
+        self.t = StageTimes()
+        self.obj = None
+        self.level = None
+
+    def begin_level(self, level):
+        self.level = level
+
+    def jbu(self, image, coarse_depth):
+        from oracle.ref_driver import run_jbu
+        t0 = time.perf_counter()
+        out = run_jbu(image, coarse_depth)
+        dt = time.perf_counter() - t0
+        self.t.wall_s += dt
+        self.t.gpu_ms += dt * 1e3          # RunJBU only reports a printf time; wall is what there is
+        return out
+
+    def _finish(self, stage, finest, t_setup):
+        obj = self.obj
+        t0 = time.perf_counter()
+        ms = obj.run_patch_match()
+        planes, costs = obj.get_result()
+        self.t.wall_s += t_setup + time.perf_counter() - t0
+        self.t.gpu_ms += ms
+        self.t.passes += 2 * (2 if stage == "geom" else 3)
+        if finest:
+            self.t.pass_ms.setdefault(stage, []).append(ms / (2 * (2 if stage == "geom" else 3)))
+        return planes, costs
+
+    def photometric(self, level, hier=None, finest=False):
+        from oracle.ref_driver import RefACMMP
+        if self.obj is not None:
+            self.obj.close()
+        t0 = time.perf_counter()
+        if hier is None:
+            self.obj = RefACMMP(level.images, level.cams, seed=self.seed)
+        else:
+            coarse4, fine_depth = hier
+            self.obj = RefACMMP(level.images, level.cams, seed=self.seed, hierarchy=True,
+                                coarse_normals=np.ascontiguousarray(coarse4[..., :3]),
+                                coarse_costs=np.ascontiguousarray(coarse4[..., 3]), fine_depth=fine_depth)
+        return self._finish("photometric", finest, time.perf_counter() - t0)
+
+    def prior(self, level, params, masks, finest=False):
+        t0 = time.perf_counter()
+        self.obj.set_prior(params, masks)
+        return self._finish("prior", finest, time.perf_counter() - t0)
+
+    def geom(self, level, multi, own_planes, own_costs, depth_maps, finest=False):
+        from oracle.ref_driver import RefACMMP
+        if self.obj is not None:
+            self.obj.close()
+        t0 = time.perf_counter()
+        self.obj = RefACMMP(level.images, level.cams, seed=self.seed, geom=True, multi_geom=multi, depth_maps=depth_maps,
+                            prev_planes=own_planes, prev_costs=own_costs)
+        return self._finish("geom", finest, time.perf_counter() - t0)
+
+    def end(self):
+        if self.obj is not None:
+            self.obj.close()
+            self.obj = None
+
+
+def run_view(levels, backend, prior_cache=None, first_level=0, state=None):
+    """One reference view through every level and stage.  Returns (planes, costs) of the finest level
+    -- planes = (world normal, depth) -- and leaves the timings in backend.t.
+    prior_cache: dict level index -> (params, masks); filled when empty (the CPU prior stage is
+    deterministic given the deterministic photometric stage, so later steps may reuse it)."""
+    if prior_cache is None:
+        prior_cache = {}
+    for li in range(first_level, len(levels)):
+        L = levels[li]
+        finest = li == len(levels) - 1
+        backend.begin_level(L)
+        hier = None
+        if state is not None:
+            planes_prev, costs_prev = state
+            fine_depth = backend.jbu(L.images[0], np.ascontiguousarray(planes_prev[..., 3]))
+            coarse4 = np.concatenate([planes_prev[..., :3], costs_prev[..., None]], axis=-1).astype(np.float32)
+            hier = (np.ascontiguousarray(coarse4), fine_depth)
+        planes, costs = backend.photometric(L, hier, finest)
+        if li not in prior_cache:
+            t0 = time.perf_counter()
+            p = backend.ctx.params() if hasattr(backend, "ctx") and backend.ctx is not None else None
+            dmin = np.float32(L.cams[0].depth_min) * np.float32(0.6)
+            dmax = np.float32(L.cams[0].depth_max) * np.float32(1.2)
+            prior_cache[li] = planar_prior(L.cams[0], planes[..., 3], costs, float(dmin), float(dmax))
+            backend.t.prior_cpu_s += time.perf_counter() - t0
+        params, masks = prior_cache[li]
+        planes, costs = backend.prior(L, params, masks, finest)
+        for multi in (False, True):
+            dm = [np.ascontiguousarray(planes[..., 3])] + list(L.neighbour_depths)
+            planes, costs = backend.geom(L, multi, planes, costs, dm, finest)
+        state = (planes, costs)
+    return state

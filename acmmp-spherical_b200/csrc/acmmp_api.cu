@@ -157,6 +157,7 @@ struct acmmp_ctx {
     std::string err;
     acmmp_params params;
     int as_compiled = 1;
+    int use_tma = 1;
     uint64_t seed = 0;
     bool have_seeded = false;
     uint64_t seeded_seed = 0;
@@ -386,6 +387,7 @@ FrameConst frame_const(const acmmp_ctx *ctx)
     fc.scaled_rows = ctx->scaled_rows;
     fc.as_compiled = ctx->as_compiled;
     fc.ref_pitch = ctx->ref_pitch;
+    fc.use_tma = ctx->use_tma;
     fc.ref_padded = ctx->ref_padded;
     fc.views = ctx->views_dev;
     fc.planes = ctx->planes; fc.planes_alt = ctx->planes_alt;
@@ -759,6 +761,7 @@ int acmmp_create(acmmp_ctx **out, int device)
     acmmp_ctx *ctx = new acmmp_ctx();
     ctx->device = device;
     acmmp_default_params(&ctx->params);
+    if (const char *e = std::getenv("ACMMP_NO_TMA")) ctx->use_tma = (e[0] == '1') ? 0 : 1;   // debug aid
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return ACMMP_E_CUDA;
@@ -830,6 +833,18 @@ int acmmp_get_params(const acmmp_ctx *ctx, acmmp_params *out)
 {
     if (!ctx || !out) return ACMMP_E_ARG;
     *out = ctx->params;
+    return ACMMP_OK;
+}
+
+int acmmp_reset_modes(acmmp_ctx *ctx)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    ctx->params.geom_consistency = 0;
+    ctx->params.multi_geometry = 0;
+    ctx->params.planar_prior = 0;
+    ctx->params.hierarchy = 0;
+    ctx->params.upsample = 0;
+    ctx->params.max_iterations = 3;
     return ACMMP_OK;
 }
 
@@ -1027,6 +1042,9 @@ int acmmp_jbu_device(int device, const float *image_dev, int w, int h, const flo
     return cudaGetLastError() == cudaSuccess ? ACMMP_OK : ACMMP_E_CUDA;
 }
 
+static thread_local float g_last_jbu_ms = 0.f;
+float acmmp_last_jbu_ms(void) { return g_last_jbu_ms; }
+
 int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_depth, int sw, int sh, float *out_depth)
 {
     if (!image || !coarse_depth || !out_depth || w <= 0 || h <= 0 || sw <= 0 || sh <= 0) return ACMMP_E_ARG;
@@ -1038,7 +1056,16 @@ int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_
         cudaMalloc(&dout, sizeof(float) * (size_t)w * h) == cudaSuccess &&
         cudaMemcpy(di, image, sizeof(float) * (size_t)w * h, cudaMemcpyHostToDevice) == cudaSuccess &&
         cudaMemcpy(dd, coarse_depth, sizeof(float) * (size_t)sw * sh, cudaMemcpyHostToDevice) == cudaSuccess) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, nullptr);
         rc = acmmp_jbu_device(device, di, w, h, dd, sw, sh, dout, nullptr);
+        cudaEventRecord(e1, nullptr);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&g_last_jbu_ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
         if (rc == ACMMP_OK && cudaMemcpy(out_depth, dout, sizeof(float) * (size_t)w * h, cudaMemcpyDeviceToHost) != cudaSuccess)
             rc = ACMMP_E_CUDA;
     }

@@ -58,10 +58,19 @@ __device__ __forceinline__ void stage_tile(const FrameConst &fc, const CUtensorM
 {
     typedef TileGeom<TW, TH> TG;
     const int tid = threadIdx.x;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) {
-        tma_load_tile_2d(tile_r, tmap, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, bar, TG::kTileBytes);
+    if (fc.use_tma) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            tma_load_tile_2d(tile_r, tmap, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, bar, TG::kTileBytes);
+        }
+    } else {
+        for (int idx = tid; idx < TG::RW * TG::RH; idx += NT) {
+            const int cx = idx % TG::RW, cy = idx / TG::RW;
+            const int gy = min(y0 - kHalo + kRefPad + cy, fc.H + 2 * kRefPad - 1);
+            const int gx = min(x0 - kHalo + kRefPad + cx, fc.ref_pitch - 1);
+            tile_r[cy * TG::PW + cx] = __ldg(fc.ref_padded + (size_t)gy * fc.ref_pitch + gx);
+        }
     }
     {   // view constants: nsrc * 72 words
         const uint32_t *src = reinterpret_cast<const uint32_t *>(fc.views);
@@ -74,7 +83,7 @@ __device__ __forceinline__ void stage_tile(const FrameConst &fc, const CUtensorM
         const int yy = y0 - kHalo + idx / TG::RW;
         aux[idx] = make_aux<MODEL>(fc, xx, yy);
     }
-    mbar_wait(bar, 0);
+    if (fc.use_tma) mbar_wait(bar, 0);
     __syncthreads();
 }
 

@@ -16,7 +16,9 @@ constexpr int kModelPinhole = 0;     // reference main.h:35-38
 constexpr int kModelSphere = 11;
 constexpr int kHalo = 5;             // patch_size 11 -> radius 5   (ACMMP.h:34, ACMMP.cu:415)
 constexpr int kTaps = 36;            // i,j in {-5,-3,-1,1,3,5}       (ACMMP.cu:450-451)
-constexpr int kRefPad = 8;           // border replication of the pitch-linear reference image
+constexpr int kRefPad = 9;           // border replication of the pitch-linear reference image; 9 - kHalo = 4 makes every
+                                     // TMA box start 16-byte aligned (tile origins are multiples of 8): without swizzle the
+                                     // B200 TMA unit faults ("illegal instruction") on box starts that are not 16-byte aligned
 
 // Per source view, 72 words.
 struct ViewConst {
@@ -55,6 +57,7 @@ struct FrameConst {
     int scaled_cols, scaled_rows;
     int as_compiled;       // plane_hypotheses_now semantics, see acmmp_b200.h
     int ref_pitch;         // floats per row of the padded reference image
+    int use_tma;           // 1: tile staged by a TMA bulk-tensor copy; 0: same tile by plain loads (debug aid)
     const float *ref_padded;      // (H + 2*kRefPad) rows, border replicated
     const ViewConst *views;       // nsrc entries (device)
     // state

@@ -105,6 +105,10 @@ int acmmp_set_hierarchy(acmmp_ctx *ctx);
 int acmmp_set_planar_prior(acmmp_ctx *ctx);
 int acmmp_set_max_iterations(acmmp_ctx *ctx, int n);
 int acmmp_get_params(const acmmp_ctx *ctx, acmmp_params *out);
+/* Back to a freshly constructed object's flags (geom / prior / hierarchy off, max_iterations 3) while
+ * keeping the uploaded views: lets one context serve consecutive stages of the same view and level
+ * (the reference constructs a new ACMMP object per stage and re-uploads everything, main.cpp:83-93). */
+int acmmp_reset_modes(acmmp_ctx *ctx);
 
 /* Geometric consistency inputs: the n depth maps (index 0 = reference view, 1.. = source views)
  * that InuputInitialization reads from depths.dmb / depths_geom.dmb (ACMMP.cpp:653-678) and
@@ -180,6 +184,8 @@ int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_
               float *out_depth);
 int acmmp_jbu_device(int device, const float *image_dev, int w, int h, const float *coarse_depth_dev, int sw,
                      int sh, float *out_depth_dev, void *cuda_stream);
+/* CUDA-event time (ms) of the JBU kernel launched by the last acmmp_jbu call of this thread. */
+float acmmp_last_jbu_ms(void);
 
 /* Deterministic sub-kernel probes (parity tests): evaluate, for every pixel p of the reference
  * view and a caller-supplied per-pixel plane (camera-frame normal, d), with the SAME device code
