@@ -167,12 +167,15 @@ struct acmmp_ctx {
     int W = 0, H = 0;
     std::vector<acmmp_camera> cams;
     std::vector<int> widths, heights;
-    std::vector<cudaArray_t> arrays;
-    std::vector<cudaTextureObject_t> textures;
+    cudaArray_t src_array = nullptr;       // layered: one layer per source view
+    cudaTextureObject_t src_tex = 0;
+    int src_w = 0, src_h = 0;              // layer size (largest source view)
+    bool manual_clamp = false;             // source views differ in size -> smaller ones are edge-padded
     float *ref_dense = nullptr;     // W*H
     float *ref_padded = nullptr;
     int ref_pitch = 0;
     CUtensorMap tmap_pass, tmap_tp;
+    NccTable ncc;
     std::vector<float *> depth_maps;        // owned copies (host-upload variant)
     std::vector<const float *> depth_ptrs;  // what the kernels read
     std::vector<int> depth_w, depth_h;
@@ -253,10 +256,10 @@ int make_tmap(acmmp_ctx *ctx, CUtensorMap *tm, int box_w, int box_h)
 
 void free_views(acmmp_ctx *ctx)
 {
-    for (auto t : ctx->textures) cudaDestroyTextureObject(t);
-    for (auto a : ctx->arrays) cudaFreeArray(a);
-    ctx->textures.clear();
-    ctx->arrays.clear();
+    if (ctx->src_tex) cudaDestroyTextureObject(ctx->src_tex);
+    if (ctx->src_array) cudaFreeArray(ctx->src_array);
+    ctx->src_tex = 0;
+    ctx->src_array = nullptr;
     cudaFree(ctx->ref_dense); ctx->ref_dense = nullptr;
     cudaFree(ctx->ref_padded); ctx->ref_padded = nullptr;
     cudaFree(ctx->views_dev); ctx->views_dev = nullptr;
@@ -347,7 +350,7 @@ int upload_view_consts(acmmp_ctx *ctx)
     std::vector<ViewConst> vc(nsrc > 0 ? nsrc : 1);
     for (int i = 0; i < nsrc; ++i) {
         vc[i] = fold_view(ctx->cams[0], ctx->cams[i + 1]);
-        vc[i].tex = (unsigned long long)ctx->textures[i + 1];
+        vc[i].tex = 0;
         if ((int)ctx->depth_ptrs.size() > i + 1) {
             vc[i].depth = ctx->depth_ptrs[i + 1];
             vc[i].dW = ctx->depth_w[i + 1];
@@ -388,6 +391,7 @@ FrameConst frame_const(const acmmp_ctx *ctx)
     fc.as_compiled = ctx->as_compiled;
     fc.ref_pitch = ctx->ref_pitch;
     fc.use_tma = ctx->use_tma;
+    fc.tex_src = (unsigned long long)ctx->src_tex;
     fc.ref_padded = ctx->ref_padded;
     fc.views = ctx->views_dev;
     fc.planes = ctx->planes; fc.planes_alt = ctx->planes_alt;
@@ -401,8 +405,29 @@ FrameConst frame_const(const acmmp_ctx *ctx)
     return fc;
 }
 
-template <int MODEL> size_t smem_tp(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kTpNT>(nsrc, kTpNT, 0).total; }
-template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassPix>(nsrc, kPassNT, kPassPix).total; }
+// the per-view NCC constants + texture handles that travel as a kernel parameter
+NccTable ncc_table(const acmmp_ctx *ctx)
+{
+    NccTable nt;
+    std::memset(&nt, 0, sizeof(nt));
+    for (int i = 0; i + 1 < ctx->n && i < kMaxSrc; ++i) {
+        const ViewConst c = fold_view(ctx->cams[0], ctx->cams[i + 1]);
+        float *a = nt.c[i].a;
+        if (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) {
+            for (int k = 0; k < 3; ++k) { a[k] = c.Fx[k]; a[3 + k] = c.Fy[k]; a[6 + k] = c.Fz[k]; a[9 + k] = c.fb[k]; }
+            a[12] = c.Wf + 0.5f;
+            a[13] = c.Hf + 0.5f;
+        } else {
+            for (int k = 0; k < 9; ++k) a[k] = c.R[k];
+            for (int k = 0; k < 3; ++k) a[9 + k] = c.t[k];
+            a[12] = c.cx; a[13] = c.cy; a[14] = c.Wf; a[15] = c.Hf;
+        }
+    }
+    return nt;
+}
+
+template <int MODEL> size_t smem_tp(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT>(nsrc, kTpNT, 0).total; }
+template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT>(nsrc, kPassNT, kPassPix).total; }
 
 int configure_kernels(acmmp_ctx *ctx)
 {
@@ -479,24 +504,30 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
         ctx->heights.assign(heights, heights + n);
         const size_t npx = (size_t)ctx->W * ctx->H;
         const cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
-        ctx->arrays.assign(n, nullptr);
-        ctx->textures.assign(n, 0);
-        for (int i = 0; i < n; ++i) {
-            CK(cudaMallocArray(&ctx->arrays[i], &desc, widths[i], heights[i]));
+        ctx->src_w = ctx->src_h = 0;
+        ctx->manual_clamp = false;
+        for (int i = 1; i < n; ++i) {
+            ctx->src_w = std::max(ctx->src_w, (int)widths[i]);
+            ctx->src_h = std::max(ctx->src_h, (int)heights[i]);
+            if (widths[i] != widths[1] || heights[i] != heights[1]) ctx->manual_clamp = true;
+        }
+        CK(cudaMalloc3DArray(&ctx->src_array, &desc, make_cudaExtent(ctx->src_w, ctx->src_h, n - 1), cudaArrayLayered));
+        {
             cudaResourceDesc res;
             std::memset(&res, 0, sizeof(res));
             res.resType = cudaResourceTypeArray;
-            res.res.array.array = ctx->arrays[i];
+            res.res.array.array = ctx->src_array;
             cudaTextureDesc td;
             std::memset(&td, 0, sizeof(td));
             // The reference asks for Wrap with un-normalised coordinates (ACMMP.cpp:700-704), which
             // CUDA turns into Clamp; ask for what it gets.
             td.addressMode[0] = cudaAddressModeClamp;
             td.addressMode[1] = cudaAddressModeClamp;
+            td.addressMode[2] = cudaAddressModeClamp;
             td.filterMode = cudaFilterModeLinear;
             td.readMode = cudaReadModeElementType;
             td.normalizedCoords = 0;
-            CK(cudaCreateTextureObject(&ctx->textures[i], &res, &td, nullptr));
+            CK(cudaCreateTextureObject(&ctx->src_tex, &res, &td, nullptr));
         }
         ctx->ref_pitch = (ctx->W + 2 * kRefPad + 3) & ~3;
         CK(cudaMalloc(&ctx->ref_dense, sizeof(float) * npx));
@@ -528,9 +559,37 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
         ctx->cams[i].height = heights[i];
     }
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    for (int i = 0; i < n; ++i) {
-        CK(cudaMemcpy2DToArrayAsync(ctx->arrays[i], 0, 0, images[i], sizeof(float) * widths[i], sizeof(float) * widths[i],
-                                    heights[i], kind, ctx->stream));
+    float *pad_src = nullptr, *pad_dst = nullptr;
+    if (ctx->manual_clamp) {
+        CK(cudaMalloc(&pad_src, sizeof(float) * (size_t)ctx->src_w * ctx->src_h));
+        CK(cudaMalloc(&pad_dst, sizeof(float) * (size_t)ctx->src_w * ctx->src_h));
+    }
+    for (int i = 1; i < n; ++i) {
+        cudaMemcpy3DParms cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.dstArray = ctx->src_array;
+        cp.dstPos = make_cudaPos(0, 0, i - 1);
+        if (widths[i] == ctx->src_w && heights[i] == ctx->src_h) {
+            cp.srcPtr = make_cudaPitchedPtr(const_cast<float *>(images[i]), sizeof(float) * widths[i], widths[i], heights[i]);
+            cp.extent = make_cudaExtent(widths[i], heights[i], 1);
+            cp.kind = kind;
+        } else {
+            // smaller than the layer: replicate the last column / row so that hardware clamping at the
+            // layer edge equals clamping at the image edge
+            CK(cudaMemcpyAsync(pad_src, images[i], sizeof(float) * (size_t)widths[i] * heights[i], kind, ctx->stream));
+            dim3 grid((ctx->src_w + 255) / 256, ctx->src_h);
+            k_replicate_pad<<<grid, 256, 0, ctx->stream>>>(pad_src, widths[i], heights[i], pad_dst, ctx->src_w, ctx->src_h);
+            ctx->launches++;
+            cp.srcPtr = make_cudaPitchedPtr(pad_dst, sizeof(float) * ctx->src_w, ctx->src_w, ctx->src_h);
+            cp.extent = make_cudaExtent(ctx->src_w, ctx->src_h, 1);
+            cp.kind = cudaMemcpyDeviceToDevice;
+        }
+        CK(cudaMemcpy3DAsync(&cp, ctx->stream));
+    }
+    if (ctx->manual_clamp) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(pad_src);
+        cudaFree(pad_dst);
     }
     CK(cudaMemcpyAsync(ctx->ref_dense, images[0], sizeof(float) * (size_t)ctx->W * ctx->H, kind, ctx->stream));
     {
@@ -545,6 +604,7 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
     ctx->params.num_images = n;
     ctx->params.disparity_min = ctx->cams[0].K[0] * ctx->params.baseline / ctx->params.depth_max;
     ctx->params.disparity_max = ctx->cams[0].K[0] * ctx->params.baseline / ctx->params.depth_min;
+    ctx->ncc = ncc_table(ctx);
     int rc = upload_view_consts(ctx);
     if (rc) return rc;
     return configure_kernels(ctx);
@@ -586,7 +646,7 @@ int launch_init(acmmp_ctx *ctx)
 {
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
-    k_random_init<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->tmap_tp);
+    k_random_init<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp);
     ctx->launches++;
     CK(cudaGetLastError());
     return ACMMP_OK;
@@ -597,7 +657,7 @@ int launch_pass(acmmp_ctx *ctx, int colour, int iter)
 {
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + kPassTW - 1) / kPassTW, (ctx->H + kPassTH - 1) / kPassTH);
-    k_pass<MODEL><<<grid, kPassNT, smem_pass<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->tmap_pass, colour, iter);
+    k_pass<MODEL><<<grid, kPassNT, smem_pass<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
     ctx->launches++;
     CK(cudaGetLastError());
     std::swap(ctx->planes, ctx->planes_alt);
@@ -691,7 +751,7 @@ int launch_probe(acmmp_ctx *ctx, int mode, int view, const float4 *planes_dev, f
 {
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
-    k_probe<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->tmap_tp, mode, view, planes_dev, out, out4, out_views);
+    k_probe<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp, mode, view, planes_dev, out, out4, out_views);
     ctx->launches++;
     CK(cudaGetLastError());
     return ACMMP_OK;

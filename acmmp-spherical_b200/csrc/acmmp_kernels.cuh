@@ -28,11 +28,11 @@ namespace acmmp {
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-template <int MODEL, int TW, int TH, int NPIX>
+template <int MODEL, int TW, int TH, int NPIX, int NT>
 struct SmemLayout {
     typedef TileGeom<TW, TH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
-    size_t off_tile, off_aux, off_wr, off_vc, off_bar, off_cost, off_vw, off_probs, total;
+    size_t off_tile, off_aux, off_wr, off_tq, off_vc, off_bar, off_cost, off_vw, off_probs, total;
     __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows)
     {
         const int nvp = nsrc | 1;
@@ -40,6 +40,7 @@ struct SmemLayout {
         off_tile = o; o += align_up(TG::kTileBytes, 128);
         off_aux = o; o += align_up(sizeof(AuxT) * TG::RW * TG::RH, 16);
         off_wr = o; o += sizeof(float2) * kTaps * NPIX;
+        off_tq = o; o += sizeof(float) * kTaps * NT;
         off_vc = o; o += sizeof(ViewConst) * (size_t)nsrc;
         off_bar = o; o += 16;
         off_cost = o; o += sizeof(float) * (size_t)cost_rows * nvp;
@@ -101,15 +102,15 @@ __device__ __forceinline__ PixCtx make_pix(const FrameConst &fc, const int x, co
 }
 
 // ComputeMultiViewInitialCostandSelectedViews, ACMMP.cu:519-556.  costrow: nsrc floats (scratch).
-template <int MODEL, int PW, int RW, int WRS>
-__device__ __forceinline__ float init_cost_and_views(const FrameConst &fc, const ViewConst *s_vc, const float *tile_r,
+template <int MODEL, int PW, int RW, int WRS, int TQS>
+__device__ __forceinline__ float init_cost_and_views(const FrameConst &fc, const NccTable &nt, const float *tile_r,
                                                      const typename AuxType<MODEL>::type *aux, const float2 *wr,
                                                      const PixCtx &px, const float4 &plane, float *costrow,
-                                                     uint32_t &selected)
+                                                     uint32_t &selected, const unsigned wmask, float *tq)
 {
     const float cost_max = 2.0f;
     const uint32_t all = (fc.nsrc >= 32) ? 0xffffffffu : ((1u << fc.nsrc) - 1u);
-    ncc_views<MODEL, PW, RW, WRS>(fc, s_vc, tile_r, aux, wr, px, plane, all, costrow, 1);
+    ncc_views<MODEL, PW, RW, WRS, TQS>(fc, nt, tile_r, aux, wr, px, plane, all, costrow, 1, wmask, tq);
     int num_valid = 0;
     for (int i = 0; i < fc.nsrc; ++i) num_valid += (costrow[i] < cost_max) ? 1 : 0;
     selected = 0;
@@ -144,16 +145,17 @@ constexpr int kTpTW = 16, kTpTH = 8, kTpNT = 128;
 
 template <int MODEL>
 __global__ void __launch_bounds__(kTpNT)
-k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMap tmap, const int mode, const int view,
+k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap, const int mode, const int view,
         const float4 *__restrict__ planes, float *__restrict__ out, float4 *__restrict__ out4, uint32_t *__restrict__ out_views)
 {
     typedef TileGeom<kTpTW, kTpTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT> L(fc.nsrc, kTpNT, 0);
+    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT> L(fc.nsrc, kTpNT, 0);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
     float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr);
+    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
     float *cost = reinterpret_cast<float *>(smem + L.off_cost);
@@ -164,6 +166,7 @@ k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorM
     const int tid = threadIdx.x;
     const int x = x0 + (tid % kTpTW), y = y0 + (tid / kTpTW);
     if (x >= fc.W || y >= fc.H) return;
+    const unsigned wm = __activemask();       // the lanes that walk the view loops together
     const int center = y * fc.W + x;
     PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
     fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, wr + tid, 0, 1);
@@ -173,7 +176,7 @@ k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorM
     float *costrow = cost + tid * nvp;
 
     if (mode == 0) {
-        ncc_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, wr + tid, px, plane, 1u << (view - 1), costrow, 1);
+        ncc_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, wr + tid, px, plane, 1u << (view - 1), costrow, 1, wm, tq);
         out[center] = costrow[view - 1];
     } else if (mode == 1) {
         out[center] = geom_cost<MODEL>(fc, s_vc[view - 1], px, plane);
@@ -184,7 +187,7 @@ k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorM
         out4[center] = make_float4(sx, sy, sd, depth);
     } else {
         uint32_t sel;
-        out[center] = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, wr + tid, px, plane, costrow, sel);
+        out[center] = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, wr + tid, px, plane, costrow, sel, wm, tq);
         out_views[center] = sel;
     }
 }
@@ -207,15 +210,16 @@ __device__ __forceinline__ float range_gauss(float x, float sigma)
 
 template <int MODEL>
 __global__ void __launch_bounds__(kTpNT)
-k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMap tmap)
+k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap)
 {
     typedef TileGeom<kTpTW, kTpTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT> L(fc.nsrc, kTpNT, 0);
+    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT> L(fc.nsrc, kTpNT, 0);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
     float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr);
+    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
     float *cost = reinterpret_cast<float *>(smem + L.off_cost);
@@ -226,6 +230,7 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ CUt
     const int tid = threadIdx.x;
     const int x = x0 + (tid % kTpTW), y = y0 + (tid / kTpTW);
     if (x >= fc.W || y >= fc.H) return;
+    const unsigned wm = __activemask();       // the lanes that walk the view loops together
     const int center = y * fc.W + x;
     PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
     const float2 *mywr = wr + tid;
@@ -243,7 +248,7 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ CUt
         const float depth = rng_uniform(rs) * (fc.depth_max - fc.depth_min) + fc.depth_min;
         plane = random_normal(rs, px.dir);
         plane.w = plane_offset(plane, px.dir, depth);
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
     } else if (fc.prior) {
         if (fc.plane_masks[center] > 0 && fc.costs[center] >= 0.1f) {      // ACMMP.cu:691-703
             const float perturbation = 0.02f;
@@ -259,7 +264,7 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ CUt
             const float depth = plane.w;
             plane.w = plane_offset(plane, px.dir, depth);
         }
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
     } else if (fc.upsample) {
         // joint-bilateral NORMAL upsampling from the coarse level, ACMMP.cu:713-779
         const float scaled_cols = (float)fc.scaled_cols, scaled_rows = (float)fc.scaled_rows;
@@ -300,18 +305,18 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ CUt
         // cost of the plane exactly as uploaded (normal part defined as 0 here) -> pre_costs, :770-771
         const float4 uploaded = fc.planes[center];
         uint32_t sel0;
-        const float c0 = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, uploaded, costrow, sel0);
+        const float c0 = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, uploaded, costrow, sel0, wm, tq);
         fc.pre_costs[center] = c0;
         plane = normal_to_cam(fc, n_total);
         plane.w = plane_offset(plane, px.dir, uploaded.w);
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
     } else {
         // reload, ACMMP.cu:780-793
         plane = fc.hierarchy ? fc.coarse_planes[center] : fc.planes[center];
         plane = normal_to_cam(fc, plane);
         const float depth = plane.w;
         plane.w = plane_offset(plane, px.dir, depth);
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT>(fc, s_vc, tile_r, aux, mywr, px, plane, costrow, sel);
+        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
     }
     fc.planes[center] = plane;
     fc.costs[center] = c;
@@ -358,16 +363,18 @@ __device__ __forceinline__ float4 shfl_plane(const unsigned gmask, const float4 
 
 template <int MODEL>
 __global__ void __launch_bounds__(kPassNT, 2)
-k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMap tmap, const int colour, const int iter)
+k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap,
+       const int colour, const int iter)
 {
     typedef TileGeom<kPassTW, kPassTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     constexpr int WRS = kPassPix;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kPassTW, kPassTH, kPassPix> L(fc.nsrc, kPassNT, kPassPix);
+    const SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT> L(fc.nsrc, kPassNT, kPassPix);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
     float2 *wr_all = reinterpret_cast<float2 *>(smem + L.off_wr);
+    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
     float *cost_all = reinterpret_cast<float *>(smem + L.off_cost);
@@ -396,9 +403,13 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMa
     const int lane = tid & 31;
     const int gbase = lane & ~7;       // first lane of the group inside the warp
     const unsigned gmask = 0xFFu << gbase;
-    const int y = y0 + (g >> 2);
-    const int x = x0 + 2 * (g & 3) + ((y + colour) & 1);
-    if (x >= W || y >= H) return;      // whole groups leave together; no block-wide sync below
+    const int yy_ = y0 + (g >> 2);
+    const int xx_ = x0 + 2 * (g & 3) + ((yy_ + colour) & 1);
+    // Groups that fall outside the image stay alive (clamped coordinates, nothing stored) so that the
+    // warp walks the view loops convergently; see ncc_views.
+    const bool valid = xx_ < W && yy_ < H;
+    const int x = min(xx_, W - 1), y = min(yy_, H - 1);
+    constexpr unsigned FULL = 0xffffffffu;
 
     const int center = y * W + x;
     const int nsrc = fc.nsrc;
@@ -477,9 +488,8 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMa
 
     // ---- phase A: 8 neighbour hypotheses x all views (ACMMP.cu:981-1142) ---------------------
     const uint32_t all_views = (nsrc >= 32) ? 0xffffffffu : ((1u << nsrc) - 1u);
-    if (flag) {
-        ncc_views<MODEL, TG::PW, TG::RW, WRS>(fc, s_vc, tile_r, aux, wr, px, cand, all_views, costrow, 1);
-    } else {
+    ncc_views<MODEL, TG::PW, TG::RW, WRS, kPassNT>(fc, nt, tile_r, aux, wr, px, cand, (flag && valid) ? all_views : 0u, costrow, 1, FULL, tq);
+    if (!flag) {
         // `float cost_array[8][32] = {2.0f}` (ACMMP.cu:957): only element [0][0] is 2, the rest 0
         for (int v = 0; v < nsrc; ++v) costrow[v] = (gl == 0 && v == 0) ? 2.0f : 0.0f;
     }
@@ -581,17 +591,17 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMa
     // ---- cost of the current plane, taps split over the group (ACMMP.cu:1232-1245) -----------
     const float4 cur_plane = planes_in[center];
     float cost_now = 0.0f;
-    for (int j = 0; j < nsrc; ++j) {
-        const float wj = vw[j];
-        if (wj > 0) {       // zero-weight views contribute exactly 0 in the reference's sum
-            const float cj = ncc_tapsplit<MODEL, TG::PW, TG::RW, WRS>(fc, s_vc[j], tile_r, aux, wr, px, cur_plane, gl, gmask);
+    // zero-weight views contribute exactly 0 to the reference's sum, so only selected views are evaluated
+    ncc_tapsplit_views<MODEL, TG::PW, TG::RW, WRS>(
+        fc, nt, tile_r, aux, wr, px, cur_plane, valid ? temp_selected_views : 0u, gl, gmask, FULL,
+        [&](const int j, const float cj) {
+            const float wj = vw[j];
             if (fc.geom) {
                 cost_now += wj * (cj + 0.2f * geom_cost<MODEL>(fc, s_vc[j], px, cur_plane));
             } else {
                 cost_now += wj * cj;
             }
-        }
-    }
+        });
     cost_now /= weight_norm;
     float depth_now = plane_depth(cur_plane, px.dir);
 
@@ -694,12 +704,17 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMa
     if (!fc.as_compiled || !have_plane_now) plane_now = plane_intended;
 
     // ---- PlaneHypothesisRefinement, ACMMP.cu:797-936 -----------------------------------------
-    if (weight_norm > 0.0f) {
+    const bool do_refine = weight_norm > 0.0f;      // group-uniform
+    float cdepth = depth_now;
+    float4 temp_plane = plane_now;
+    bool use_prior = false;
+    float depth_prior = 0.f;
+    const float angle_sigma_r = CUDART_PI_F * (5.0f / 180.0f);
+    const float two_angle_sigma_squared_r = 2 * angle_sigma_r * angle_sigma_r;
+    if (do_refine) {
         const float perturbation = 0.02f;
-        const float angle_sigma = CUDART_PI_F * (5.0f / 180.0f);
-        const float two_angle_sigma_squared = 2 * angle_sigma * angle_sigma;
-        const bool use_prior = fc.prior && mask_c > 0;
-        float depth_prior = 0.f;
+        const float angle_sigma = angle_sigma_r;
+        use_prior = fc.prior && mask_c > 0;
         if (use_prior) depth_prior = plane_depth(prior_plane, px.dir);
 
         float depth_rand = 0.f, depth_perturbed = 0.f;
@@ -735,20 +750,22 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMa
         n_pert = shfl_plane(gmask, n_pert, gbase);
 
         // candidate gl (0..4): depths {rand, now, rand, now, pert}, normals {now, rand, rand, pert, now}
-        float cdepth = depth_now;
-        float4 temp_plane = plane_now;
         if (gl == 0 || gl == 2) cdepth = depth_rand;
         if (gl == 4) cdepth = depth_perturbed;
         if (gl == 1 || gl == 2) temp_plane = n_rand;
         if (gl == 3) temp_plane = n_pert;
         temp_plane.w = plane_offset(temp_plane, px.dir, cdepth);
-
+    }
+    // the five refinement hypotheses on lanes 0..4 of every group, selected views only
+    ncc_views<MODEL, TG::PW, TG::RW, WRS, kPassNT>(fc, nt, tile_r, aux, wr, px, temp_plane,
+                                                   (do_refine && valid && gl < 5) ? temp_selected_views : 0u, costrow, 1, FULL, tq);
+    if (do_refine) {
+        const float two_angle_sigma_squared = two_angle_sigma_squared_r;
         float temp_cost = 0.0f;
         float depth_before = 0.f;
         bool cand_ok = false;
         float restricted_temp_cost = 0.f;
         if (gl < 5) {
-            ncc_views<MODEL, TG::PW, TG::RW, WRS>(fc, s_vc, tile_r, aux, wr, px, temp_plane, temp_selected_views, costrow, 1);
             for (int j = 0; j < nsrc; ++j) {
                 const float wj = vw[j];
                 if (wj > 0.0f) {
@@ -797,7 +814,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ CUtensorMa
     }
 
     // ---- write-back (ACMMP.cu:1315-1324) ------------------------------------------------------
-    if (gl == 0) {
+    if (gl == 0 && valid) {
         float4 out_plane = plane_now;
         float out_cost = cost_now;
         if (fc.hierarchy) {
@@ -960,6 +977,16 @@ k_rng_fill(const uint32_t *__restrict__ row_states, const int W, const int H, ui
         rng_store(row + 3 * x, s);
         rng_next(s);
     }
+}
+
+// w x h image -> W x H image with the last column / row replicated (layer padding, see fetch_src)
+__global__ void __launch_bounds__(256)
+k_replicate_pad(const float *__restrict__ src, const int w, const int h, float *__restrict__ dst, const int W, const int H)
+{
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y;
+    if (px >= W || py >= H) return;
+    dst[(size_t)py * W + px] = src[(size_t)min(py, h - 1) * w + min(px, w - 1)];
 }
 
 __global__ void __launch_bounds__(256)

@@ -43,6 +43,22 @@ struct ViewConst {
 };
 static_assert(sizeof(ViewConst) == 72 * 4, "ViewConst layout");
 
+// Per source view, what the NCC sample loop needs, 16 floats.  Lives in KERNEL PARAMETER space
+// (constant bank) so that a warp-uniform view index turns into uniform-register operands and a
+// uniform texture handle -- no per-lane register copies, no non-uniform-handle replay loop.
+//   PINHOLE: a[0..2]=Fx a[3..5]=Fy a[6..8]=Fz a[9..11]=fb a[12]=W+0.5 a[13]=H+0.5
+//   SPHERE : a[0..8]=R  a[9..11]=t a[12]=cx a[13]=cy a[14]=W a[15]=H
+struct NccConst {
+    float a[16];
+};
+// All source views live in ONE layered R32F texture (layer = view index): a single handle that is
+// trivially warp-uniform.  (One texture object per view makes ptxas wrap every TEX in a
+// non-uniform-handle replay loop, ~8 extra instructions per sample.)
+struct NccTable {
+    NccConst c[kMaxSrc];
+};
+static_assert(sizeof(NccTable) == kMaxSrc * 64, "NccTable layout");
+
 // Per reference view + stage; passed by value (__grid_constant__).
 struct FrameConst {
     int W, H;              // reference image size
@@ -58,6 +74,7 @@ struct FrameConst {
     int as_compiled;       // plane_hypotheses_now semantics, see acmmp_b200.h
     int ref_pitch;         // floats per row of the padded reference image
     int use_tma;           // 1: tile staged by a TMA bulk-tensor copy; 0: same tile by plain loads (debug aid)
+    unsigned long long tex_src;   // layered R32F bilinear texture of the source views
     const float *ref_padded;      // (H + 2*kRefPad) rows, border replicated
     const ViewConst *views;       // nsrc entries (device)
     // state
