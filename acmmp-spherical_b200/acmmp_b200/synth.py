@@ -127,8 +127,10 @@ def _render(quads, model, R, t, width, height, K=None, cx=None, cy=None, chunk_r
 
 
 def make_pinhole_scene(n_views=5, width=640, height=480, focal=500.0, seed=1, n_src=None, depth0=3.0,
-                       baseline_ratio=0.07, ring=False) -> Scene:
-    """Background plane + three tilted foreground quads, cameras on an arc (or ring) around them."""
+                       baseline_ratio=0.07, ring=False, render_ids=None) -> Scene:
+    """Background plane + three tilted foreground quads, cameras on an arc (or ring) around them.
+    render_ids: render only these reference views and their sources (the others get None images / depths): a rank of a multi-GPU
+    job only needs its own reference view and that view's sources."""
     rng = np.random.default_rng(seed)
     texel = 0.7 * depth0 / focal
     halfw = 0.5 * width / focal * depth0 * 1.9 + baseline_ratio * depth0 * n_views
@@ -149,13 +151,25 @@ def make_pinhole_scene(n_views=5, width=640, height=480, focal=500.0, seed=1, n_
             off = (i - (n_views - 1) / 2.0) * step
             C = np.array([off, 0.15 * step * ((i % 3) - 1), 0.05 * step * ((i % 2) * 2 - 1)])
         R, t = _look_at(C, (0.15 * C[0], 0.1 * C[1], depth0))
-        img, dep = _render(quads, MODEL_PINHOLE, R, t, width, height, K=K)
-        Rs.append(R); ts.append(t); images.append(img); depths.append(dep)
-    dmin = min(float(d[d > 0].min()) for d in depths) * 0.9
-    dmax = max(float(d.max()) for d in depths) * 1.1
+        Rs.append(R); ts.append(t)
+    pairs = _nearest_pairs(Rs, ts, n_views, n_src if n_src is not None else n_views - 1)
+    if render_ids is not None:
+        render_ids = set(render_ids)
+        for r in list(render_ids):
+            render_ids.update(pairs[r][1])
+    for i in range(n_views):
+        if render_ids is None or i in render_ids:
+            img, dep = _render(quads, MODEL_PINHOLE, Rs[i], ts[i], width, height, K=K)
+        else:
+            img, dep = None, None
+        images.append(img); depths.append(dep)
+    if render_ids is None:
+        dmin = min(float(d[d > 0].min()) for d in depths) * 0.9
+        dmax = max(float(d.max()) for d in depths) * 1.1
+    else:       # the same range on every rank: from the scene geometry, not from the rendered subset
+        dmin, dmax = 0.6 * depth0, 1.5 * depth0
     for i in range(n_views):
         cams.append(make_camera(MODEL_PINHOLE, Rs[i], ts[i], K=K, width=width, height=height, depth_min=dmin, depth_max=dmax))
-    pairs = _nearest_pairs(Rs, ts, n_views, n_src if n_src is not None else n_views - 1)
     return Scene(MODEL_PINHOLE, images, cams, depths, pairs, Rs, ts, [K] * n_views, quads)
 
 
