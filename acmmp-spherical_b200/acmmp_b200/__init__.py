@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent.parent
-LIB_PATH = PKG_DIR / "lib" / "libacmmp_b200.so"
+LIB_PATH = Path(os.environ.get("ACMMP_B200_LIB", PKG_DIR / "lib" / "libacmmp_b200.so"))     # override: development aid
 
 MODEL_PINHOLE = 0
 MODEL_SPHERE = 11
@@ -78,7 +78,7 @@ _EXPORTS = [
     "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
     "acmmp_get_params", "acmmp_reset_modes", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
-    "acmmp_set_hierarchy_inputs", "acmmp_set_planar_prior_inputs", "acmmp_set_seed",
+    "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_set_seed",
     "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_download_state", "acmmp_upload_state",
@@ -199,12 +199,33 @@ class Context:
         return p
 
     def set_depth_maps(self, maps):
+        """maps[0] may be None: the reference view's depth map is then taken from the device-resident state."""
         n = len(maps)
-        ms = [_f32(m) for m in maps]
-        ptrs = (C.POINTER(C.c_float) * n)(*[_fp(m) for m in ms])
-        ws = (C.c_int32 * n)(*[m.shape[1] for m in ms])
-        hs = (C.c_int32 * n)(*[m.shape[0] for m in ms])
+        ms = [None if m is None else _f32(m) for m in maps]
+        ptrs = (C.POINTER(C.c_float) * n)(*[C.POINTER(C.c_float)() if m is None else _fp(m) for m in ms])
+        ws = (C.c_int32 * n)(*[self.W if m is None else m.shape[1] for m in ms])
+        hs = (C.c_int32 * n)(*[self.H if m is None else m.shape[0] for m in ms])
         self._ck(self._l.acmmp_set_depth_maps(self._h, C.c_int(n), ptrs, ws, hs), "acmmp_set_depth_maps")
+
+    def next_level(self, images, cams):
+        """Move to the next pyramid level on the device (JBU + hierarchy inputs), see acmmp_next_level."""
+        n = len(images)
+        imgs = [_f32(im) for im in images]
+        ptrs = (C.POINTER(C.c_float) * n)(*[_fp(im) for im in imgs])
+        ws = (C.c_int32 * n)(*[im.shape[1] for im in imgs])
+        hs = (C.c_int32 * n)(*[im.shape[0] for im in imgs])
+        carr = (Camera * n)(*cams)
+        self._ck(self._l.acmmp_next_level(self._h, C.c_int(n), ptrs, ws, hs, carr), "acmmp_next_level")
+        self.H, self.W = imgs[0].shape
+        self.n = n
+
+    def result_host(self):
+        """Zero-copy numpy views of the pinned host result buffers (valid until the next run)."""
+        pp, pc = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+        self._ck(self._l.acmmp_result_host(self._h, C.byref(pp), C.byref(pc)), "acmmp_result_host")
+        planes = np.ctypeslib.as_array(pp, shape=(self.H, self.W, 4))
+        costs = np.ctypeslib.as_array(pc, shape=(self.H, self.W))
+        return planes, costs
 
     def set_depth_maps_device(self, dev_ptrs, widths, heights):
         n = len(dev_ptrs)
@@ -320,7 +341,7 @@ class Context:
     def timings(self):
         t = (C.c_float * 8)()
         self._ck(self._l.acmmp_last_timings(self._h, t), "acmmp_last_timings")
-        return dict(init_ms=t[0], pass_sum_ms=t[1], finalize_ms=t[2], n_pass=int(t[3]), last_pass_ms=t[4])
+        return dict(init_ms=t[0], pass_sum_ms=t[1], finalize_ms=t[2], n_pass=int(t[3]), last_pass_ms=t[4], jbu_ms=t[5])
 
     def launch_count(self):
         return int(self._l.acmmp_launch_count(self._h))

@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import Context, jbu as jbu_host, last_jbu_ms, synth
+from . import Context, synth
 from .prior import planar_prior
 
 
@@ -73,7 +73,9 @@ def _nbytes(*arrays):
 
 
 class B200Backend:
-    """Stages through libacmmp_b200.so."""
+    """Stages through libacmmp_b200.so, GPU-resident: one context per view, the state of a stage is handed
+    to the next one on the device (acmmp_next_level, acmmp_set_depth_maps with maps[0] == NULL); per level
+    the host only sends the images, the neighbours' depth maps and the prior, and reads each stage's result."""
     name = "b200"
 
     def __init__(self, device=0, seed=1234, as_compiled=True):
@@ -85,7 +87,7 @@ class B200Backend:
         ctx = self.ctx
         t0 = time.perf_counter()
         ctx.run_patch_match()
-        planes, costs = ctx.get_result()
+        planes, costs = ctx.result_host()
         self.t.wall_s += time.perf_counter() - t0
         tm = ctx.timings()
         self.t.gpu_ms += tm["init_ms"] + tm["pass_sum_ms"] + tm["finalize_ms"]
@@ -95,55 +97,39 @@ class B200Backend:
             self.t.pass_ms.setdefault(stage, []).append(tm["pass_sum_ms"] / tm["n_pass"])
         return planes, costs
 
-    def begin_level(self, level: Level):
+    def begin_level(self, level: Level, prev=None):
         t0 = time.perf_counter()
         if self.ctx is None:
             self.ctx = Context(self.device)
             self.ctx.set_seed(self.seed)
             self.ctx.set_plane_now_semantics(self.as_compiled)
-        self.ctx.reset_modes()
-        self.ctx.set_views(level.images, level.cams)
+        if prev is None:
+            self.ctx.reset_modes()
+            self.ctx.set_views(level.images, level.cams)
+        else:
+            self.ctx.next_level(level.images, level.cams)      # JBU + hierarchy hand-over on the device
+            self.t.gpu_ms += self.ctx.timings()["jbu_ms"]
         self.t.wall_s += time.perf_counter() - t0
         self.t.h2d_bytes += _nbytes(*level.images)
 
-    def jbu(self, image, coarse_depth):
-        t0 = time.perf_counter()
-        out = jbu_host(image, coarse_depth, self.device)
-        self.t.wall_s += time.perf_counter() - t0
-        self.t.gpu_ms += last_jbu_ms()
-        self.t.h2d_bytes += _nbytes(image, coarse_depth)
-        self.t.d2h_bytes += _nbytes(out)
-        self.t.launches += 1
-        return out
-
-    def photometric(self, level, hier=None, finest=False):
-        ctx = self.ctx
-        t0 = time.perf_counter()
-        ctx.reset_modes()
-        if hier is not None:
-            coarse4, fine_depth = hier
-            ctx.set_hierarchy()
-            ctx.set_hierarchy_inputs(coarse4, fine_depth)
-            self.t.h2d_bytes += _nbytes(coarse4, fine_depth)
-        self.t.wall_s += time.perf_counter() - t0
+    def photometric(self, level, finest=False):
         return self._run("photometric", finest)
 
     def prior(self, level, params, masks, finest=False):
         t0 = time.perf_counter()
         self.ctx.set_planar_prior_inputs(params, masks)
         self.t.wall_s += time.perf_counter() - t0
-        self.t.h2d_bytes += _nbytes(masks) + 16 * masks.size
+        self.t.h2d_bytes += _nbytes(masks, params)
         return self._run("prior", finest)
 
-    def geom(self, level, multi, own_planes, own_costs, depth_maps, finest=False):
+    def geom(self, level, multi, neighbour_depths, finest=False):
         ctx = self.ctx
         t0 = time.perf_counter()
         ctx.reset_modes()
         ctx.set_geom_consistency(multi)
-        ctx.set_depth_maps(depth_maps)
-        ctx.set_planes(own_planes, own_costs)
+        ctx.set_depth_maps([None] + list(neighbour_depths))     # own map: from the device-resident state
         self.t.wall_s += time.perf_counter() - t0
-        self.t.h2d_bytes += _nbytes(own_planes, own_costs, *depth_maps)
+        self.t.h2d_bytes += _nbytes(*neighbour_depths)
         return self._run("geom", finest)
 
     def end(self):
@@ -163,19 +149,11 @@ class ReferenceBackend:
         self.seed = seed
         self.t = StageTimes()
         self.obj = None
-        self.level = None
+        self.prev = None
+        self.last = None
 
-    def begin_level(self, level):
-        self.level = level
-
-    def jbu(self, image, coarse_depth):
-        from oracle.ref_driver import run_jbu
-        t0 = time.perf_counter()
-        out = run_jbu(image, coarse_depth)
-        dt = time.perf_counter() - t0
-        self.t.wall_s += dt
-        self.t.gpu_ms += dt * 1e3          # RunJBU only reports a printf time; wall is what there is
-        return out
+    def begin_level(self, level, prev=None):
+        self.prev = prev
 
     def _finish(self, stage, finest, t_setup):
         obj = self.obj
@@ -184,23 +162,28 @@ class ReferenceBackend:
         planes, costs = obj.get_result()
         self.t.wall_s += t_setup + time.perf_counter() - t0
         self.t.gpu_ms += ms
-        self.t.passes += 2 * (2 if stage == "geom" else 3)
+        n_pass = 2 * (2 if stage == "geom" else 3)
+        self.t.passes += n_pass
         if finest:
-            self.t.pass_ms.setdefault(stage, []).append(ms / (2 * (2 if stage == "geom" else 3)))
+            self.t.pass_ms.setdefault(stage, []).append(ms / n_pass)      # includes init + finalize (~5 %)
+        self.last = (planes, costs)
         return planes, costs
 
-    def photometric(self, level, hier=None, finest=False):
-        from oracle.ref_driver import RefACMMP
+    def photometric(self, level, finest=False):
+        from oracle.ref_driver import RefACMMP, run_jbu
         if self.obj is not None:
             self.obj.close()
         t0 = time.perf_counter()
-        if hier is None:
+        if self.prev is None:
             self.obj = RefACMMP(level.images, level.cams, seed=self.seed)
         else:
-            coarse4, fine_depth = hier
+            planes_prev, costs_prev = self.prev
+            tj = time.perf_counter()
+            fine_depth = run_jbu(level.images[0], np.ascontiguousarray(planes_prev[..., 3]))     # RunJBU, ACMMP.cpp:1071
+            self.t.gpu_ms += (time.perf_counter() - tj) * 1e3      # RunJBU only printf's its time; wall is what there is
             self.obj = RefACMMP(level.images, level.cams, seed=self.seed, hierarchy=True,
-                                coarse_normals=np.ascontiguousarray(coarse4[..., :3]),
-                                coarse_costs=np.ascontiguousarray(coarse4[..., 3]), fine_depth=fine_depth)
+                                coarse_normals=np.ascontiguousarray(planes_prev[..., :3]),
+                                coarse_costs=np.ascontiguousarray(costs_prev), fine_depth=fine_depth)
         return self._finish("photometric", finest, time.perf_counter() - t0)
 
     def prior(self, level, params, masks, finest=False):
@@ -208,12 +191,14 @@ class ReferenceBackend:
         self.obj.set_prior(params, masks)
         return self._finish("prior", finest, time.perf_counter() - t0)
 
-    def geom(self, level, multi, own_planes, own_costs, depth_maps, finest=False):
+    def geom(self, level, multi, neighbour_depths, finest=False):
         from oracle.ref_driver import RefACMMP
+        own_planes, own_costs = self.last
         if self.obj is not None:
             self.obj.close()
         t0 = time.perf_counter()
-        self.obj = RefACMMP(level.images, level.cams, seed=self.seed, geom=True, multi_geom=multi, depth_maps=depth_maps,
+        dm = [np.ascontiguousarray(own_planes[..., 3])] + list(neighbour_depths)
+        self.obj = RefACMMP(level.images, level.cams, seed=self.seed, geom=True, multi_geom=multi, depth_maps=dm,
                             prev_planes=own_planes, prev_costs=own_costs)
         return self._finish("geom", finest, time.perf_counter() - t0)
 
@@ -223,35 +208,29 @@ class ReferenceBackend:
             self.obj = None
 
 
-def run_view(levels, backend, prior_cache=None, first_level=0, state=None):
+def run_view(levels, backend, prior_cache=None, neighbour_depths_fn=None):
     """One reference view through every level and stage.  Returns (planes, costs) of the finest level
     -- planes = (world normal, depth) -- and leaves the timings in backend.t.
     prior_cache: dict level index -> (params, masks); filled when empty (the CPU prior stage is
-    deterministic given the deterministic photometric stage, so later steps may reuse it)."""
+    deterministic given the deterministic photometric stage, so later steps may reuse it).
+    neighbour_depths_fn(level, own_depth) -> list of source-view depth maps (default: level.neighbour_depths)."""
     if prior_cache is None:
         prior_cache = {}
-    for li in range(first_level, len(levels)):
-        L = levels[li]
+    state = None
+    for li, L in enumerate(levels):
         finest = li == len(levels) - 1
-        backend.begin_level(L)
-        hier = None
-        if state is not None:
-            planes_prev, costs_prev = state
-            fine_depth = backend.jbu(L.images[0], np.ascontiguousarray(planes_prev[..., 3]))
-            coarse4 = np.concatenate([planes_prev[..., :3], costs_prev[..., None]], axis=-1).astype(np.float32)
-            hier = (np.ascontiguousarray(coarse4), fine_depth)
-        planes, costs = backend.photometric(L, hier, finest)
+        backend.begin_level(L, state)
+        planes, costs = backend.photometric(L, finest)
         if li not in prior_cache:
             t0 = time.perf_counter()
-            p = backend.ctx.params() if hasattr(backend, "ctx") and backend.ctx is not None else None
-            dmin = np.float32(L.cams[0].depth_min) * np.float32(0.6)
-            dmax = np.float32(L.cams[0].depth_max) * np.float32(1.2)
-            prior_cache[li] = planar_prior(L.cams[0], planes[..., 3], costs, float(dmin), float(dmax))
+            dmin = float(np.float32(L.cams[0].depth_min) * np.float32(0.6))
+            dmax = float(np.float32(L.cams[0].depth_max) * np.float32(1.2))
+            prior_cache[li] = planar_prior(L.cams[0], np.array(planes[..., 3]), np.array(costs), dmin, dmax)
             backend.t.prior_cpu_s += time.perf_counter() - t0
         params, masks = prior_cache[li]
         planes, costs = backend.prior(L, params, masks, finest)
         for multi in (False, True):
-            dm = [np.ascontiguousarray(planes[..., 3])] + list(L.neighbour_depths)
-            planes, costs = backend.geom(L, multi, planes, costs, dm, finest)
-        state = (planes, costs)
+            nd = L.neighbour_depths if neighbour_depths_fn is None else neighbour_depths_fn(L, planes[..., 3])
+            planes, costs = backend.geom(L, multi, nd, finest)
+        state = (np.array(planes), np.array(costs))
     return state

@@ -198,7 +198,7 @@ struct acmmp_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pass_events;
     int pass_events_used = 0;
-    float t_init = 0.f, t_pass_sum = 0.f, t_finalize = 0.f, t_last_pass = 0.f;
+    float t_init = 0.f, t_pass_sum = 0.f, t_finalize = 0.f, t_last_pass = 0.f, t_jbu = 0.f;
     int n_pass = 0;
     bool timed_init = false, timed_final = false;
     int64_t launches = 0;
@@ -620,7 +620,19 @@ int set_depths_common(acmmp_ctx *ctx, int n, const float *const *maps, bool on_d
     for (int i = 0; i < n; ++i) {
         ctx->depth_w.push_back(widths[i]);
         ctx->depth_h.push_back(heights[i]);
-        if (on_device) {
+        if (i == 0 && maps[0] == nullptr) {
+            // the reference view's own depth map = depth of the device-resident state
+            if (widths[0] != ctx->W || heights[0] != ctx->H) return fail(ctx, ACMMP_E_ARG, "own depth map must have the view's size");
+            float *d = nullptr;
+            const int npx = ctx->W * ctx->H;
+            CK(cudaMalloc(&d, sizeof(float) * (size_t)npx));
+            k_export_depth<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(ctx->planes, npx, d);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            ctx->depth_maps.push_back(d);
+            ctx->depth_ptrs.push_back(d);
+            ctx->depth_owned.push_back(true);
+        } else if (on_device) {
             ctx->depth_maps.push_back(nullptr);
             ctx->depth_ptrs.push_back(maps[i]);
             ctx->depth_owned.push_back(false);
@@ -959,23 +971,87 @@ int acmmp_set_planar_prior_inputs(acmmp_ctx *ctx, const float *plane_params4, in
     if (!ctx || !ctx->planes || !masks || (n_planes > 0 && !plane_params4))
         return fail(ctx, ACMMP_E_ARG, "acmmp_set_planar_prior_inputs: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    const size_t npx = (size_t)ctx->W * ctx->H;
-    std::vector<float> pp(4 * npx, 0.f);
-    std::vector<uint32_t> mk(npx, 0u);
-    for (size_t i = 0; i < npx; ++i) {                 // ACMMP.cpp:855-863
-        mk[i] = (uint32_t)masks[i];
-        if (masks[i] > 0) {
-            const int id = (int)(masks[i] - 1);
-            if (id < 0 || id >= n_planes) return fail(ctx, ACMMP_E_ARG, "prior mask refers to a plane that was not supplied");
-            std::memcpy(&pp[4 * i], &plane_params4[4 * (size_t)id], 4 * sizeof(float));
-        }
-    }
-    if (!ctx->prior_planes) CK(cudaMalloc(&ctx->prior_planes, sizeof(float4) * npx));
-    if (!ctx->plane_masks) CK(cudaMalloc(&ctx->plane_masks, sizeof(uint32_t) * npx));
-    CK(cudaMemcpyAsync(ctx->prior_planes, pp.data(), sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->plane_masks, mk.data(), sizeof(uint32_t) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    const int npx = ctx->W * ctx->H;
+    float *masks_dev = nullptr;
+    float4 *params_dev = nullptr;
+    CK(cudaMalloc(&masks_dev, sizeof(float) * (size_t)npx));
+    CK(cudaMalloc(&params_dev, sizeof(float4) * (size_t)std::max(n_planes, 1)));
+    CK(cudaMemcpyAsync(masks_dev, masks, sizeof(float) * (size_t)npx, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_planes > 0)
+        CK(cudaMemcpyAsync(params_dev, plane_params4, sizeof(float4) * (size_t)n_planes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->prior_planes) CK(cudaMalloc(&ctx->prior_planes, sizeof(float4) * (size_t)npx));
+    if (!ctx->plane_masks) CK(cudaMalloc(&ctx->plane_masks, sizeof(uint32_t) * (size_t)npx));
+    k_expand_prior<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(masks_dev, params_dev, std::max(n_planes, 1), npx, ctx->prior_planes,
+                                                              ctx->plane_masks);
+    ctx->launches++;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(masks_dev);
+    cudaFree(params_dev);
     ctx->params.planar_prior = 1;
+    return ACMMP_OK;
+}
+
+int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const int32_t *widths, const int32_t *heights,
+                     const acmmp_camera *cams)
+{
+    if (!ctx || !ctx->planes) return fail(ctx, ACMMP_E_ARG, "acmmp_next_level: no previous level on this context");
+    CK(cudaSetDevice(ctx->device));
+    const int sw = ctx->W, sh = ctx->H, snpx = sw * sh;
+    float4 *coarse = nullptr;
+    float *coarse_depth = nullptr;
+    CK(cudaMalloc(&coarse, sizeof(float4) * (size_t)snpx));
+    CK(cudaMalloc(&coarse_depth, sizeof(float) * (size_t)snpx));
+    k_make_coarse<<<(snpx + 255) / 256, 256, 0, ctx->stream>>>(ctx->planes, ctx->costs, snpx, coarse, coarse_depth);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    acmmp_reset_modes(ctx);
+    int rc = set_views_common(ctx, n, images, false, widths, heights, cams);      // re-allocates at the new size
+    if (rc) { cudaFree(coarse); cudaFree(coarse_depth); return rc; }
+    const int npx = ctx->W * ctx->H;
+    const int Imagescale = std::max(ctx->H / sh, ctx->W / sw);
+    float *fine_depth = nullptr;
+    CK(cudaMalloc(&fine_depth, sizeof(float) * (size_t)npx));
+    if (Imagescale == 1) {
+        // RunJBU produces nothing in this case (ACMMP.cpp:1077-1080) and the reference would re-read the old
+        // depths.dmb; same size here means the coarse depth is the depth
+        if (npx != snpx) { cudaFree(coarse); cudaFree(coarse_depth); cudaFree(fine_depth); return fail(ctx, ACMMP_E_UNSUPPORTED, "level size ratio < 2"); }
+        CK(cudaMemcpyAsync(fine_depth, coarse_depth, sizeof(float) * (size_t)npx, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+        rc = acmmp_jbu_device(ctx->device, ctx->ref_dense, ctx->W, ctx->H, coarse_depth, sw, sh, fine_depth, ctx->stream);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ctx->t_jbu, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        ctx->launches++;
+        if (rc) { cudaFree(coarse); cudaFree(coarse_depth); cudaFree(fine_depth); return fail(ctx, rc, "JBU failed"); }
+    }
+    k_seed_planes_from_depth<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(fine_depth, npx, ctx->planes);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    cudaFree(ctx->coarse_planes);
+    ctx->coarse_planes = coarse;
+    ctx->scaled_cols = sw;
+    ctx->scaled_rows = sh;
+    ctx->params.hierarchy = 1;
+    ctx->params.upsample = (sw != ctx->W || sh != ctx->H) ? 1 : 0;
+    ctx->params.scaled_cols = (float)sw;
+    ctx->params.scaled_rows = (float)sh;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(coarse_depth);
+    cudaFree(fine_depth);
+    return ACMMP_OK;
+}
+
+int acmmp_result_host(acmmp_ctx *ctx, const float **planes4, const float **costs)
+{
+    if (!ctx || !ctx->have_result) return fail(ctx, ACMMP_E_ARG, "acmmp_result_host: no completed acmmp_run_patch_match");
+    if (planes4) *planes4 = reinterpret_cast<const float *>(ctx->planes_host);
+    if (costs) *costs = ctx->costs_host;
     return ACMMP_OK;
 }
 
@@ -1150,6 +1226,7 @@ int acmmp_last_timings(acmmp_ctx *ctx, float what[8])
     what[2] = ctx->t_finalize;
     what[3] = (float)ctx->n_pass;
     what[4] = ctx->t_last_pass;
+    what[5] = ctx->t_jbu;
     return ACMMP_OK;
 }
 

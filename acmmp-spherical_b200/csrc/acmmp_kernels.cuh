@@ -32,7 +32,7 @@ template <int MODEL, int TW, int TH, int NPIX, int NT>
 struct SmemLayout {
     typedef TileGeom<TW, TH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
-    size_t off_tile, off_aux, off_wr, off_tq, off_vc, off_bar, off_cost, off_vw, off_probs, total;
+    size_t off_tile, off_aux, off_wr, off_tq, off_vc, off_ncc, off_bar, off_cost, off_vw, off_probs, total;
     __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows)
     {
         const int nvp = nsrc | 1;
@@ -42,6 +42,7 @@ struct SmemLayout {
         off_wr = o; o += sizeof(float2) * kTaps * NPIX;
         off_tq = o; o += sizeof(float) * kTaps * NT;
         off_vc = o; o += sizeof(ViewConst) * (size_t)nsrc;
+        off_ncc = o; o += sizeof(NccConst) * (size_t)nsrc;
         off_bar = o; o += 16;
         off_cost = o; o += sizeof(float) * (size_t)cost_rows * nvp;
         off_vw = o; o += sizeof(float) * (size_t)group_rows * nvp;
@@ -327,6 +328,9 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
 // ------------------------------------------------------------------------------------------
 // checkerboard pass
 // ------------------------------------------------------------------------------------------
+#ifndef ACMMP_PASS_MIN_CTAS
+#define ACMMP_PASS_MIN_CTAS 2
+#endif
 constexpr int kPassTW = 8, kPassTH = 8, kPassNT = 256, kPassPix = 32;
 
 // FindMinCostIndex / FindMaxCostIndex, ACMMP.cu:62-86 (ties -> last index)
@@ -362,7 +366,7 @@ __device__ __forceinline__ float4 shfl_plane(const unsigned gmask, const float4 
 }
 
 template <int MODEL>
-__global__ void __launch_bounds__(kPassNT, 2)
+__global__ void __launch_bounds__(kPassNT, ACMMP_PASS_MIN_CTAS)
 k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap,
        const int colour, const int iter)
 {
@@ -376,6 +380,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     float2 *wr_all = reinterpret_cast<float2 *>(smem + L.off_wr);
     float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
+    NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
     float *cost_all = reinterpret_cast<float *>(smem + L.off_cost);
     float *vw_all = reinterpret_cast<float *>(smem + L.off_vw);
@@ -396,6 +401,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         }
     }
 
+    for (int i = tid; i < fc.nsrc * 16; i += kPassNT) s_ncc[i >> 4].a[i & 15] = nt.c[i >> 4].a[i & 15];
     stage_tile<MODEL, kPassTW, kPassTH, kPassNT>(fc, &tmap, x0, y0, tile_r, aux, s_vc, bar);
 
     const int g = tid >> 3;            // pixel slot in the CTA
@@ -756,9 +762,26 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         if (gl == 3) temp_plane = n_pert;
         temp_plane.w = plane_offset(temp_plane, px.dir, cdepth);
     }
-    // the five refinement hypotheses on lanes 0..4 of every group, selected views only
-    ncc_views<MODEL, TG::PW, TG::RW, WRS, kPassNT>(fc, nt, tile_r, aux, wr, px, temp_plane,
-                                                   (do_refine && valid && gl < 5) ? temp_selected_views : 0u, costrow, 1, FULL, tq);
+    // The 5 refinement hypotheses x selected views of the pixel are dealt out to the 8 lanes of its group as
+    // (hypothesis, view) pairs: pair p -> hypothesis p % 5, view = (p / 5)-th selected view.  The reference
+    // evaluates every view for every hypothesis and then ignores the zero-weight ones (ACMMP.cu:882-897).
+    {
+        const int n_pairs = (do_refine && valid) ? 5 * __popc(temp_selected_views) : 0;
+        int rounds = (n_pairs + 7) >> 3;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(FULL, rounds, off));
+        for (int r = 0; r < rounds; ++r) {
+            const int pidx = gl + 8 * r;
+            const bool want = pidx < n_pairs;
+            const int h = want ? pidx % 5 : 0;
+            const int vsel = want ? (int)__fns(temp_selected_views, 0, pidx / 5 + 1) : 0;
+            const float4 hp = shfl_plane(gmask, temp_plane, gbase + h);
+            const NccConst cl = s_ncc[vsel];
+            const float cst = ncc_pair<MODEL, TG::PW, TG::RW, WRS>(fc, cl, vsel, tile_r, aux, wr, px, hp, want);
+            if (want) cost_grp[h * nvp + vsel] = cst;
+        }
+        __syncwarp(FULL);
+    }
     if (do_refine) {
         const float two_angle_sigma_squared = two_angle_sigma_squared_r;
         float temp_cost = 0.0f;
@@ -994,6 +1017,45 @@ k_export_depth(const float4 *__restrict__ planes, const int n, float *__restrict
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n) depth[idx] = planes[idx].w;
+}
+
+// CudaPlanarPriorInitialization, ACMMP.cpp:855-863, on the device: masks (1-based triangle id as float)
+// -> plane_masks (u32) and the per-pixel prior plane
+__global__ void __launch_bounds__(256)
+k_expand_prior(const float *__restrict__ masks, const float4 *__restrict__ params, const int n_planes, const int n,
+               float4 *__restrict__ prior_planes, uint32_t *__restrict__ plane_masks)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float m = masks[idx];
+    plane_masks[idx] = (uint32_t)m;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m > 0) {
+        const int id = min(max((int)(m - 1), 0), n_planes - 1);
+        p = params[id];
+    }
+    prior_planes[idx] = p;
+}
+
+// hierarchy hand-over between pyramid levels, all on the device (ACMMP.cpp:816-840):
+// coarse (normal, cost) from the previous level's (n_world, depth) planes + costs
+__global__ void __launch_bounds__(256)
+k_make_coarse(const float4 *__restrict__ planes, const float *__restrict__ costs, const int n, float4 *__restrict__ coarse,
+              float *__restrict__ coarse_depth)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float4 p = planes[idx];
+    coarse[idx] = make_float4(p.x, p.y, p.z, costs[idx]);
+    coarse_depth[idx] = p.w;
+}
+
+// plane = (0, 0, 0, fine depth): what the reference uploads in hierarchy mode (ACMMP.cpp:833-840)
+__global__ void __launch_bounds__(256)
+k_seed_planes_from_depth(const float *__restrict__ depth, const int n, float4 *__restrict__ planes)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) planes[idx] = make_float4(0.f, 0.f, 0.f, depth[idx]);
 }
 
 __global__ void __launch_bounds__(256)

@@ -116,6 +116,11 @@ def make_levels(rank, seed=2):
                                      render_ids=[rank])
     levels = pipeline.build_levels(scene, rank)
     ids = [rank] + list(scene.pairs[rank][1])
+    # the step's host inputs live in pinned memory (contract: H2D from pinned host memory)
+    import torch
+    for L in levels:
+        L.images = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory().numpy() for im in L.images]
+        L.neighbour_depths = [torch.from_numpy(np.ascontiguousarray(d)).pin_memory().numpy() for d in L.neighbour_depths]
     return scene, levels, ids
 
 
@@ -139,7 +144,7 @@ class Exchange:
             return list(level.neighbour_depths)
         torch, dist = self.torch, self.dist
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        mine = torch.from_numpy(np.ascontiguousarray(own_depth)).to(self.dev, non_blocking=False)
+        mine = torch.from_numpy(np.array(own_depth, np.float32)).to(self.dev, non_blocking=False)
         out = [torch.empty_like(mine) for _ in range(self.world)]
         t0.record()
         dist.all_gather(out, mine)
@@ -155,33 +160,9 @@ class Exchange:
 
 
 def run_step(levels, backend, prior_cache, exch):
-    """pipeline.run_view with the depth exchange hooked in before each geometric stage."""
-    from acmmp_b200.pipeline import planar_prior
-    state = None
-    for li, L in enumerate(levels):
-        finest = li == len(levels) - 1
-        backend.begin_level(L)
-        hier = None
-        if state is not None:
-            planes_prev, costs_prev = state
-            fine_depth = backend.jbu(L.images[0], np.ascontiguousarray(planes_prev[..., 3]))
-            coarse4 = np.ascontiguousarray(np.concatenate([planes_prev[..., :3], costs_prev[..., None]], axis=-1), np.float32)
-            hier = (coarse4, fine_depth)
-        planes, costs = backend.photometric(L, hier, finest)
-        if li not in prior_cache:
-            t0 = time.perf_counter()
-            dmin = float(np.float32(L.cams[0].depth_min) * np.float32(0.6))
-            dmax = float(np.float32(L.cams[0].depth_max) * np.float32(1.2))
-            prior_cache[li] = planar_prior(L.cams[0], planes[..., 3], costs, dmin, dmax)
-            backend.t.prior_cpu_s += time.perf_counter() - t0
-        params, masks = prior_cache[li]
-        planes, costs = backend.prior(L, params, masks, finest)
-        for multi in (False, True):
-            own = np.ascontiguousarray(planes[..., 3])
-            dm = [own] + exch.neighbour_depths(L, own)
-            planes, costs = backend.geom(L, multi, planes, costs, dm, finest)
-        state = (planes, costs)
-    return state
+    """One reference view through the whole schedule, with the depth exchange before each geometric stage."""
+    from acmmp_b200.pipeline import run_view
+    return run_view(levels, backend, prior_cache, neighbour_depths_fn=exch.neighbour_depths)
 
 
 # ------------------------------------------------------------------------------------------
@@ -219,13 +200,16 @@ def main():
     rank, local_rank, world = dist_env()
     if world != a.gpus and world > 1:
         a.gpus = world
+    # the reference printf()s progress lines to stdout (ACMMP.cu:1542): keep fd 1 clean for the ONE JSON line
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     if a.impl == "reference" and rank != 0:
         return 0            # the reference is single-GPU: rank 0 alone runs and prints it
 
     import torch
     if not torch.cuda.is_available():
-        print(json.dumps({"impl": a.impl, "error": "no CUDA device: this benchmark has no CPU fallback"}))
+        os.write(json_fd, (json.dumps({"impl": a.impl, "error": "no CUDA device: this benchmark has no CPU fallback"}) + "\n").encode())
         return 1
     torch.cuda.set_device(local_rank)
     use_dist = world > 1 and a.impl == "b200"
@@ -341,7 +325,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline_port(levels)
             except Exception as e:      # the checker is optional for the number, never for the product
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()

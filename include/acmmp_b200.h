@@ -129,6 +129,23 @@ int acmmp_set_planes(acmmp_ctx *ctx, const float *planes4, const float *costs);
 int acmmp_set_hierarchy_inputs(acmmp_ctx *ctx, const float *coarse_planes4, int sw, int sh,
                                const float *fine_depth);
 
+/* GPU-resident stage chaining: what the reference does through .dmb files and a
+ * fresh ACMMP object per stage (main.cpp:199-208 -> ACMMP.cpp:753-801), without leaving the device.
+ *
+ * acmmp_set_depth_maps / _device accept maps[0] == NULL: "the reference view's depth map is the depth of
+ * the state currently on the device" (the planes left by the previous stage, which are also exactly what
+ * the geometric stage reloads, ACMMP.cpp:772-785, so no acmmp_set_planes is needed).
+ *
+ * acmmp_next_level: move the context to the next (finer) pyramid level.  Takes the new level's views like
+ * acmmp_set_views; the previous level's result is joint-bilaterally upsampled on the device (RunJBU) and
+ * becomes the hierarchy input (SetHierarchyParams + ACMMP.cpp:788-844).  Leaves the context in hierarchy
+ * mode, ready for acmmp_run_patch_match. */
+int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const int32_t *widths,
+                     const int32_t *heights, const acmmp_camera *cams);
+/* Pinned host buffers holding the result of the last acmmp_run_patch_match (W*H float4 planes, W*H float
+ * costs); valid until the next run or re-configuration.  Saves the copy acmmp_get_result makes. */
+int acmmp_result_host(acmmp_ctx *ctx, const float **planes4, const float **costs);
+
 /* Replaces ACMMP::CudaPlanarPriorInitialization (ACMMP.cpp:847-867): plane_params = n_planes x
  * float4 (camera-frame normal, d); masks = W*H float, 1-based triangle id or 0.  Also sets
  * planar_prior like SetPlanarPriorParams. */
@@ -202,7 +219,8 @@ int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint3
 
 /* Timing of the last launches on the context's stream, CUDA events, milliseconds:
  * what[0]=random_init, [1]=sum of checkerboard passes, [2]=finalize, [3]=number of passes,
- * [4]=last pass.  Valid after acmmp_synchronize / acmmp_run_patch_match. */
+ * [4]=last pass, [5]=JBU kernel of the last acmmp_next_level.  Valid after acmmp_synchronize /
+ * acmmp_run_patch_match. */
 int acmmp_last_timings(acmmp_ctx *ctx, float what[8]);
 
 /* How many kernels of this library were launched on the context since creation. */
