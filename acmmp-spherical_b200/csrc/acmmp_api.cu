@@ -169,6 +169,8 @@ struct acmmp_ctx {
     std::vector<int> widths, heights;
     cudaArray_t src_array = nullptr;       // layered: one layer per source view
     cudaTextureObject_t src_tex = 0;
+    std::vector<cudaArray_t> view_arrays;          // the same images, one 2-D array + texture per view
+    std::vector<cudaTextureObject_t> view_tex;
     int src_w = 0, src_h = 0;              // layer size (largest source view)
     bool manual_clamp = false;             // source views differ in size -> smaller ones are edge-padded
     float *ref_dense = nullptr;     // W*H
@@ -258,6 +260,10 @@ void free_views(acmmp_ctx *ctx)
 {
     if (ctx->src_tex) cudaDestroyTextureObject(ctx->src_tex);
     if (ctx->src_array) cudaFreeArray(ctx->src_array);
+    for (cudaTextureObject_t t : ctx->view_tex) cudaDestroyTextureObject(t);
+    for (cudaArray_t a : ctx->view_arrays) cudaFreeArray(a);
+    ctx->view_tex.clear();
+    ctx->view_arrays.clear();
     ctx->src_tex = 0;
     ctx->src_array = nullptr;
     cudaFree(ctx->ref_dense); ctx->ref_dense = nullptr;
@@ -422,12 +428,13 @@ NccTable ncc_table(const acmmp_ctx *ctx)
             for (int k = 0; k < 3; ++k) a[9 + k] = c.t[k];
             a[12] = c.cx; a[13] = c.cy; a[14] = c.Wf; a[15] = c.Hf;
         }
+        nt.tex[i] = (unsigned long long)ctx->view_tex[i];
     }
     return nt;
 }
 
 template <int MODEL> size_t smem_tp(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT>(nsrc, kTpNT, 0).total; }
-template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT>(nsrc, kPassNT, kPassPix).total; }
+template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT>(nsrc, kPassNT, kPassPix, kPassTq).total; }
 
 int configure_kernels(acmmp_ctx *ctx)
 {
@@ -528,6 +535,15 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
             td.readMode = cudaReadModeElementType;
             td.normalizedCoords = 0;
             CK(cudaCreateTextureObject(&ctx->src_tex, &res, &td, nullptr));
+            for (int i = 1; i < n; ++i) {
+                cudaArray_t arr = nullptr;
+                CK(cudaMallocArray(&arr, &desc, widths[i], heights[i]));
+                ctx->view_arrays.push_back(arr);
+                res.res.array.array = arr;
+                cudaTextureObject_t t = 0;
+                CK(cudaCreateTextureObject(&t, &res, &td, nullptr));
+                ctx->view_tex.push_back(t);
+            }
         }
         ctx->ref_pitch = (ctx->W + 2 * kRefPad + 3) & ~3;
         CK(cudaMalloc(&ctx->ref_dense, sizeof(float) * npx));
@@ -585,6 +601,8 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
             cp.kind = cudaMemcpyDeviceToDevice;
         }
         CK(cudaMemcpy3DAsync(&cp, ctx->stream));
+        CK(cudaMemcpy2DToArrayAsync(ctx->view_arrays[i - 1], 0, 0, images[i], sizeof(float) * widths[i], sizeof(float) * widths[i],
+                                    heights[i], kind, ctx->stream));
     }
     if (ctx->manual_clamp) {
         CK(cudaStreamSynchronize(ctx->stream));

@@ -12,8 +12,8 @@
 // Work decomposition of k_pass (the kernel that is >95 % of the time): a CTA owns an 8x8 pixel
 // tile = 32 pixels of the active colour; each pixel is served by a GROUP OF 8 LANES (4 pixels per
 // warp).  Lane l evaluates candidate direction l of the adaptive checkerboard (8 neighbour
-// hypotheses in parallel, argmin by warp shuffles); the five refinement hypotheses run on lanes
-// 0..4; the current plane's cost is evaluated with the 36 taps split over the 8 lanes.  The
+// hypotheses in parallel, argmin by warp shuffles); the current plane's cost and the five refinement
+// hypotheses are evaluated as (hypothesis, selected view) pairs dealt out to the 8 lanes.  The
 // reference tile (+5 px halo) arrives in shared memory by one TMA bulk-tensor copy; bilateral
 // weights and tap rays are computed once per pixel visit; source views are bilinear R32F
 // texture fetches (identical filtering to the reference's textures by construction).
@@ -32,15 +32,16 @@ template <int MODEL, int TW, int TH, int NPIX, int NT>
 struct SmemLayout {
     typedef TileGeom<TW, TH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
-    size_t off_tile, off_aux, off_wr, off_tq, off_vc, off_ncc, off_bar, off_cost, off_vw, off_probs, total;
-    __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows)
+    size_t off_tile, off_aux, off_wr, off_rr, off_tq, off_vc, off_ncc, off_bar, off_cost, off_vw, off_probs, total;
+    __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows, int tq_entries = kTaps)
     {
         const int nvp = nsrc | 1;
         size_t o = 0;
         off_tile = o; o += align_up(TG::kTileBytes, 128);
         off_aux = o; o += align_up(sizeof(AuxT) * TG::RW * TG::RH, 16);
         off_wr = o; o += sizeof(float2) * kTaps * NPIX;
-        off_tq = o; o += sizeof(float) * kTaps * NT;
+        off_rr = o; o += sizeof(float) * kTaps * NPIX;
+        off_tq = o; o += sizeof(float) * (size_t)tq_entries * NT;
         off_vc = o; o += sizeof(ViewConst) * (size_t)nsrc;
         off_ncc = o; o += sizeof(NccConst) * (size_t)nsrc;
         off_bar = o; o += 16;
@@ -54,9 +55,9 @@ struct SmemLayout {
 // Stage the per-view constants and the reference tile; build the per-tile-pixel ray table.
 // Must be called by every thread of the CTA.
 template <int MODEL, int TW, int TH, int NT>
-__device__ __forceinline__ void stage_tile(const FrameConst &fc, const CUtensorMap *tmap, const int x0, const int y0,
-                                           float *tile_r, typename AuxType<MODEL>::type *aux, ViewConst *s_vc,
-                                           unsigned long long *bar)
+__device__ __forceinline__ void stage_tile(const FrameConst &fc, const NccTable &nt, const CUtensorMap *tmap, const int x0,
+                                           const int y0, float *tile_r, typename AuxType<MODEL>::type *aux, ViewConst *s_vc,
+                                           NccConst *s_ncc, unsigned long long *bar)
 {
     typedef TileGeom<TW, TH> TG;
     const int tid = threadIdx.x;
@@ -74,6 +75,7 @@ __device__ __forceinline__ void stage_tile(const FrameConst &fc, const CUtensorM
             tile_r[cy * TG::PW + cx] = __ldg(fc.ref_padded + (size_t)gy * fc.ref_pitch + gx);
         }
     }
+    for (int i = tid; i < fc.nsrc * 16; i += NT) s_ncc[i >> 4].a[i & 15] = nt.c[i >> 4].a[i & 15];
     {   // view constants: nsrc * 72 words
         const uint32_t *src = reinterpret_cast<const uint32_t *>(fc.views);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_vc);
@@ -103,15 +105,16 @@ __device__ __forceinline__ PixCtx make_pix(const FrameConst &fc, const int x, co
 }
 
 // ComputeMultiViewInitialCostandSelectedViews, ACMMP.cu:519-556.  costrow: nsrc floats (scratch).
-template <int MODEL, int PW, int RW, int WRS, int TQS>
-__device__ __forceinline__ float init_cost_and_views(const FrameConst &fc, const NccTable &nt, const float *tile_r,
-                                                     const typename AuxType<MODEL>::type *aux, const float2 *wr,
-                                                     const PixCtx &px, const float4 &plane, float *costrow,
-                                                     uint32_t &selected, const unsigned wmask, float *tq)
+// Must be called by all 32 lanes.
+template <int MODEL, int RW, int WRS, int TQS>
+__device__ __forceinline__ float init_cost_and_views(const FrameConst &fc, const NccTable &nt, const NccConst *s_ncc,
+                                                     const typename AuxType<MODEL>::type *aux, const float2 *wr, const float *rr,
+                                                     const PixCtx &px, const float4 &plane, float *costrow, uint32_t &selected,
+                                                     float *tq)
 {
     const float cost_max = 2.0f;
     const uint32_t all = (fc.nsrc >= 32) ? 0xffffffffu : ((1u << fc.nsrc) - 1u);
-    ncc_views<MODEL, PW, RW, WRS, TQS>(fc, nt, tile_r, aux, wr, px, plane, all, costrow, 1, wmask, tq);
+    ncc_views<MODEL, RW, WRS, TQS>(fc, nt, s_ncc, aux, wr, rr, px, plane, all, costrow, 1, tq);
     int num_valid = 0;
     for (int i = 0; i < fc.nsrc; ++i) num_valid += (costrow[i] < cost_max) ? 1 : 0;
     selected = 0;
@@ -155,41 +158,48 @@ k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable 
     const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT> L(fc.nsrc, kTpNT, 0);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
-    float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr);
+    float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr) + threadIdx.x;
+    float *rr = reinterpret_cast<float *>(smem + L.off_rr) + threadIdx.x;
     float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
+    NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
     float *cost = reinterpret_cast<float *>(smem + L.off_cost);
 
     const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
-    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, &tmap, x0, y0, tile_r, aux, s_vc, bar);
+    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
 
+    // Threads that fall outside the image stay alive on a clamped pixel (nothing stored): the warp
+    // walks the view loops in lock step, see ncc_views.
     const int tid = threadIdx.x;
-    const int x = x0 + (tid % kTpTW), y = y0 + (tid / kTpTW);
-    if (x >= fc.W || y >= fc.H) return;
-    const unsigned wm = __activemask();       // the lanes that walk the view loops together
+    const int xx = x0 + (tid % kTpTW), yy = y0 + (tid / kTpTW);
+    const bool valid = xx < fc.W && yy < fc.H;
+    const int x = min(xx, fc.W - 1), y = min(yy, fc.H - 1);
     const int center = y * fc.W + x;
     PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
-    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, wr + tid, 0, 1);
-    full_sums<kTpNT>(wr + tid, px);
+    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, wr, rr, 0, 1);
+    full_sums<kTpNT>(wr, rr, px);
     const float4 plane = planes[center];
     const int nvp = fc.nsrc | 1;
     float *costrow = cost + tid * nvp;
 
     if (mode == 0) {
-        ncc_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, wr + tid, px, plane, 1u << (view - 1), costrow, 1, wm, tq);
-        out[center] = costrow[view - 1];
+        ncc_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, wr, rr, px, plane, 1u << (view - 1), costrow, 1, tq);
+        if (valid) out[center] = costrow[view - 1];
     } else if (mode == 1) {
-        out[center] = geom_cost<MODEL>(fc, s_vc[view - 1], px, plane);
+        if (valid) out[center] = geom_cost<MODEL>(fc, s_vc[view - 1], px, plane);
     } else if (mode == 2) {
         const float depth = plane_depth(plane, px.dir);
         float sx, sy, sd;
         forward_project<MODEL>(fc, s_vc[view - 1], px, depth, sx, sy, sd);
-        out4[center] = make_float4(sx, sy, sd, depth);
+        if (valid) out4[center] = make_float4(sx, sy, sd, depth);
     } else {
         uint32_t sel;
-        out[center] = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, wr + tid, px, plane, costrow, sel, wm, tq);
-        out_views[center] = sel;
+        const float c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, wr, rr, px, plane, costrow, sel, tq);
+        if (valid) {
+            out[center] = c;
+            out_views[center] = sel;
+        }
     }
 }
 
@@ -219,24 +229,26 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
     const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT> L(fc.nsrc, kTpNT, 0);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
-    float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr);
+    float2 *mywr = reinterpret_cast<float2 *>(smem + L.off_wr) + threadIdx.x;
+    float *myrr = reinterpret_cast<float *>(smem + L.off_rr) + threadIdx.x;
     float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
+    NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
     float *cost = reinterpret_cast<float *>(smem + L.off_cost);
 
     const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
-    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, &tmap, x0, y0, tile_r, aux, s_vc, bar);
+    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
 
+    // threads outside the image work on a clamped pixel and store nothing (lock-step view loops)
     const int tid = threadIdx.x;
-    const int x = x0 + (tid % kTpTW), y = y0 + (tid / kTpTW);
-    if (x >= fc.W || y >= fc.H) return;
-    const unsigned wm = __activemask();       // the lanes that walk the view loops together
+    const int xx = x0 + (tid % kTpTW), yy = y0 + (tid / kTpTW);
+    const bool valid = xx < fc.W && yy < fc.H;
+    const int x = min(xx, fc.W - 1), y = min(yy, fc.H - 1);
     const int center = y * fc.W + x;
     PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
-    const float2 *mywr = wr + tid;
-    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, wr + tid, 0, 1);
-    full_sums<kTpNT>(mywr, px);
+    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, mywr, myrr, 0, 1);
+    full_sums<kTpNT>(mywr, myrr, px);
     float *costrow = cost + tid * (fc.nsrc | 1);
 
     Rng rs = rng_load(fc.rng_seeded + 3 * (size_t)center);     // curand_init(seed, y, x), ACMMP.cu:684
@@ -249,7 +261,7 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
         const float depth = rng_uniform(rs) * (fc.depth_max - fc.depth_min) + fc.depth_min;
         plane = random_normal(rs, px.dir);
         plane.w = plane_offset(plane, px.dir, depth);
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
+        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
     } else if (fc.prior) {
         if (fc.plane_masks[center] > 0 && fc.costs[center] >= 0.1f) {      // ACMMP.cu:691-703
             const float perturbation = 0.02f;
@@ -265,7 +277,7 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
             const float depth = plane.w;
             plane.w = plane_offset(plane, px.dir, depth);
         }
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
+        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
     } else if (fc.upsample) {
         // joint-bilateral NORMAL upsampling from the coarse level, ACMMP.cu:713-779
         const float scaled_cols = (float)fc.scaled_cols, scaled_rows = (float)fc.scaled_rows;
@@ -306,23 +318,25 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
         // cost of the plane exactly as uploaded (normal part defined as 0 here) -> pre_costs, :770-771
         const float4 uploaded = fc.planes[center];
         uint32_t sel0;
-        const float c0 = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, uploaded, costrow, sel0, wm, tq);
-        fc.pre_costs[center] = c0;
+        const float c0 = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, uploaded, costrow, sel0, tq);
+        if (valid) fc.pre_costs[center] = c0;
         plane = normal_to_cam(fc, n_total);
         plane.w = plane_offset(plane, px.dir, uploaded.w);
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
+        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
     } else {
         // reload, ACMMP.cu:780-793
         plane = fc.hierarchy ? fc.coarse_planes[center] : fc.planes[center];
         plane = normal_to_cam(fc, plane);
         const float depth = plane.w;
         plane.w = plane_offset(plane, px.dir, depth);
-        c = init_cost_and_views<MODEL, TG::PW, TG::RW, kTpNT, kTpNT>(fc, nt, tile_r, aux, mywr, px, plane, costrow, sel, wm, tq);
+        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
     }
-    fc.planes[center] = plane;
-    fc.costs[center] = c;
-    fc.selected_views[center] = sel;
-    rng_store(fc.rng + 3 * (size_t)center, rs);
+    if (valid) {
+        fc.planes[center] = plane;
+        fc.costs[center] = c;
+        fc.selected_views[center] = sel;
+        rng_store(fc.rng + 3 * (size_t)center, rs);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -332,6 +346,7 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
 #define ACMMP_PASS_MIN_CTAS 2
 #endif
 constexpr int kPassTW = 8, kPassTH = 8, kPassNT = 256, kPassPix = 32;
+constexpr int kPassTq = 5 * kTqPerHyp;      // tap-depth table entries per lane: up to 5 hypotheses x (9 taps + centre)
 
 // FindMinCostIndex / FindMaxCostIndex, ACMMP.cu:62-86 (ties -> last index)
 __device__ __forceinline__ int find_min_idx(const float (&c)[8])
@@ -373,12 +388,14 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     typedef TileGeom<kPassTW, kPassTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     constexpr int WRS = kPassPix;
+    constexpr int TQS = kPassNT;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT> L(fc.nsrc, kPassNT, kPassPix);
+    const SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT> L(fc.nsrc, kPassNT, kPassPix, kPassTq);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
     float2 *wr_all = reinterpret_cast<float2 *>(smem + L.off_wr);
-    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
+    float *rr_all = reinterpret_cast<float *>(smem + L.off_rr);
+    float *tq_all = reinterpret_cast<float *>(smem + L.off_tq);
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
     NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
@@ -401,8 +418,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         }
     }
 
-    for (int i = tid; i < fc.nsrc * 16; i += kPassNT) s_ncc[i >> 4].a[i & 15] = nt.c[i >> 4].a[i & 15];
-    stage_tile<MODEL, kPassTW, kPassTH, kPassNT>(fc, &tmap, x0, y0, tile_r, aux, s_vc, bar);
+    stage_tile<MODEL, kPassTW, kPassTH, kPassNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
 
     const int g = tid >> 3;            // pixel slot in the CTA
     const int gl = tid & 7;            // lane in the pixel group == candidate direction
@@ -412,7 +428,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     const int yy_ = y0 + (g >> 2);
     const int xx_ = x0 + 2 * (g & 3) + ((yy_ + colour) & 1);
     // Groups that fall outside the image stay alive (clamped coordinates, nothing stored) so that the
-    // warp walks the view loops convergently; see ncc_views.
+    // warp walks the view loops in lock step; see ncc_views.
     const bool valid = xx_ < W && yy_ < H;
     const int x = min(xx_, W - 1), y = min(yy_, H - 1);
     constexpr unsigned FULL = 0xffffffffu;
@@ -422,6 +438,8 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     const int nvp = nsrc | 1;
     PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
     float2 *wr = wr_all + g;
+    float *rr = rr_all + g;
+    float *tq = tq_all + tid;                  // this lane's column of the tap-depth table
     float *costrow = cost_all + (g * 8 + gl) * nvp;
     float *cost_grp = cost_all + (g * 8) * nvp;
     float *vw = vw_all + g * nvp;
@@ -429,7 +447,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     const float4 *planes_in = fc.planes;
     const float *costs_in = fc.costs;
 
-    fill_weights<MODEL, TG::PW, WRS>(fc, tile_r, px, wr, gl, 8);
+    fill_weights<MODEL, TG::PW, WRS>(fc, tile_r, px, wr, rr, gl, 8);
 
     // ---- adaptive checkerboard sampling: lane l scans direction l (ACMMP.cu:965-1143) -------
     // 0 up_near 1 up_far 2 down_near 3 down_far 4 left_near 5 left_far 6 right_near 7 right_far
@@ -487,26 +505,43 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         const int nb = (gl < 4) ? center + ((gl & 2) ? W : -W) : center + ((gl & 2) ? 1 : -1);
         nbsel = fc.selected_views[nb];
     }
-    const unsigned flagbits = (__ballot_sync(gmask, flag) >> gbase) & 0xFFu;
+    const unsigned flagbits = (__ballot_sync(FULL, flag) >> gbase) & 0xFFu;
 
-    __syncwarp(gmask);
-    full_sums<WRS>(wr, px);
+    __syncwarp(FULL);
+    full_sums<WRS>(wr, rr, px);
 
     // ---- phase A: 8 neighbour hypotheses x all views (ACMMP.cu:981-1142) ---------------------
-    const uint32_t all_views = (nsrc >= 32) ? 0xffffffffu : ((1u << nsrc) - 1u);
-    ncc_views<MODEL, TG::PW, TG::RW, WRS, kPassNT>(fc, nt, tile_r, aux, wr, px, cand, (flag && valid) ? all_views : 0u, costrow, 1, FULL, tq);
+    // quad Q of the group evaluates candidates 4Q..4Q+3 (the planes its own four lanes hold), tap-split
+    const int Q = gl >> 2, q = gl & 3;
+    const int qbase = lane & ~3;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        const float4 hp = shfl_plane(FULL, cand, qbase + h);
+        quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, hp, q, tq + h * kTqPerHyp * TQS);
+    }
+    {
+        const unsigned wantA = valid ? ((flagbits >> (4 * Q)) & 0xFu) : 0u;
+        for (int v = 0; v < nsrc; ++v) {
+            const ViewK c = load_view(s_ncc + v);
+            FetchView fetch;
+            fetch.tex = (cudaTextureObject_t)nt.tex[v];
+            quad_ncc<MODEL, 4, TG::RW, WRS, TQS>(
+                c, px, aux, wr, rr, tq, fetch, q, wantA, [](const int h) { return h * kTqPerHyp * TQS; },
+                [&](const int h, const float cst) { cost_grp[(4 * Q + h) * nvp + v] = cst; });
+        }
+    }
     if (!flag) {
         // `float cost_array[8][32] = {2.0f}` (ACMMP.cu:957): only element [0][0] is 2, the rest 0
         for (int v = 0; v < nsrc; ++v) costrow[v] = (gl == 0 && v == 0) ? 2.0f : 0.0f;
     }
-    __syncwarp(gmask);
+    __syncwarp(FULL);
 
     // ---- multi-hypothesis joint view selection (ACMMP.cu:1146-1208) --------------------------
     {
         const float cost_threshold = (float)(0.8 * (double)expf((iter) * (iter) / (-90.0f)));
         uint32_t nsel[4];
 #pragma unroll
-        for (int n = 0; n < 4; ++n) nsel[n] = __shfl_sync(gmask, nbsel, gbase + 2 * n);
+        for (int n = 0; n < 4; ++n) nsel[n] = __shfl_sync(FULL, nbsel, gbase + 2 * n);
         for (int i = gl; i < nsrc; i += 8) {
             float prior = 0.0f;
 #pragma unroll
@@ -534,11 +569,13 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             probs[i] = prob * prior;
         }
     }
-    __syncwarp(gmask);
+    __syncwarp(FULL);
 
     Rng rs;
     uint32_t temp_selected_views = 0;
     float weight_norm = 0;
+    // Lane 0 of the group builds the CDF and draws the 15 uniforms (the XORWOW stream is sequential); the 15
+    // inverse-CDF searches are then spread over the 8 lanes and the per-view counts come from ballots.
     if (gl == 0) {
         rs = rng_load(fc.rng + 3 * (size_t)center);
         // TransformPDFToCDF, ACMMP.cu:137-151
@@ -550,27 +587,38 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             const float prob = probs[i] * inv_prob_sum;
             cum_prob += prob;
             probs[i] = cum_prob;
-            vw[i] = 0.0f;
         }
-        for (int sample = 0; sample < 15; ++sample) {
-            const float rand_prob = rng_uniform(rs) - FLT_EPSILON;
+#pragma unroll
+        for (int sample = 0; sample < 15; ++sample) tq[sample * TQS] = rng_uniform(rs) - FLT_EPSILON;     // ACMMP.cu:1188
+    }
+    __syncwarp(FULL);
+    {
+        const float *draws = tq - gl;              // column of lane 0 of the group
+        int id_a = -1, id_b = -1;
+        {
+            const float ra = draws[gl * TQS];
             for (int image_id = 0; image_id < nsrc; ++image_id) {
-                if (probs[image_id] > rand_prob) {
-                    vw[image_id] += 1.0f;
-                    break;
+                if (probs[image_id] > ra) { id_a = image_id; break; }
+            }
+            if (gl < 7) {
+                const float rb = draws[(gl + 8) * TQS];
+                for (int image_id = 0; image_id < nsrc; ++image_id) {
+                    if (probs[image_id] > rb) { id_b = image_id; break; }
                 }
             }
         }
+        __syncwarp(FULL);
         for (int i = 0; i < nsrc; ++i) {
-            if (vw[i] > 0) {
+            const unsigned ba = __ballot_sync(FULL, id_a == i), bb = __ballot_sync(FULL, id_b == i);
+            const int cnt = __popc(ba & gmask) + __popc(bb & gmask);
+            if (gl == 0) vw[i] = (float)cnt;
+            if (cnt > 0) {
                 temp_selected_views |= 1u << i;
-                weight_norm += vw[i];
+                weight_norm += (float)cnt;          // small integers: exact in any order
             }
         }
     }
-    temp_selected_views = __shfl_sync(gmask, temp_selected_views, gbase);
-    weight_norm = __shfl_sync(gmask, weight_norm, gbase);
-    __syncwarp(gmask);
+    __syncwarp(FULL);
 
     // ---- weighted neighbour costs and arg-min over the 8 lanes (ACMMP.cu:1210-1230) ----------
     float final_cost = 0.0f;
@@ -591,23 +639,43 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     final_cost /= weight_norm;
     float final_costs[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) final_costs[k] = __shfl_sync(gmask, final_cost, gbase + k);
+    for (int k = 0; k < 8; ++k) final_costs[k] = __shfl_sync(FULL, final_cost, gbase + k);
     const int min_cost_idx = find_min_idx(final_costs);
+    __syncwarp(FULL);          // the group's cost rows and tap-depth columns are free from here on
 
-    // ---- cost of the current plane, taps split over the group (ACMMP.cu:1232-1245) -----------
+    // ---- cost of the current plane (ACMMP.cu:1232-1245) --------------------------------------
+    // zero-weight views contribute exactly 0 to the reference's sum, so only the selected views are
+    // evaluated: the k-th selected view goes to lane k of the group (one (plane, view) pair per lane).
     const float4 cur_plane = planes_in[center];
     float cost_now = 0.0f;
-    // zero-weight views contribute exactly 0 to the reference's sum, so only selected views are evaluated
-    ncc_tapsplit_views<MODEL, TG::PW, TG::RW, WRS>(
-        fc, nt, tile_r, aux, wr, px, cur_plane, valid ? temp_selected_views : 0u, gl, gmask, FULL,
-        [&](const int j, const float cj) {
-            const float wj = vw[j];
-            if (fc.geom) {
-                cost_now += wj * (cj + 0.2f * geom_cost<MODEL>(fc, s_vc[j], px, cur_plane));
-            } else {
-                cost_now += wj * cj;
-            }
-        });
+    {
+        // quad Q takes the selected views Q, Q+2, ... (tap-split inside the quad)
+        quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, cur_plane, q, tq);
+        const int n_sel = valid ? __popc(temp_selected_views) : 0;
+        int rounds = (n_sel + 1) >> 1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(FULL, rounds, off));
+        float *row_now = cost_grp + 5 * nvp;
+        for (int r = 0; r < rounds; ++r) {
+            const int idx = 2 * r + Q;
+            const bool want = idx < n_sel;
+            const int vsel = want ? (int)__fns(temp_selected_views, 0, idx + 1) : 0;
+            const ViewK c = load_view(s_ncc + vsel);
+            FetchLayer fetch;
+            fetch.tex = (cudaTextureObject_t)fc.tex_src;
+            fetch.layer = vsel;
+            quad_ncc<MODEL, 1, TG::RW, WRS, TQS>(
+                c, px, aux, wr, rr, tq, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
+                [&](const int, float cst) {
+                    if (fc.geom) cst += 0.2f * geom_cost<MODEL>(fc, s_vc[vsel], px, cur_plane);
+                    row_now[vsel] = vw[vsel] * cst;
+                });
+        }
+        __syncwarp(FULL);
+        for (int j = 0; j < nsrc; ++j) {
+            if (vw[j] > 0) cost_now += row_now[j];
+        }
+    }
     cost_now /= weight_norm;
     float depth_now = plane_depth(cur_plane, px.dir);
 
@@ -708,6 +776,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     // 12.9 / sm_100 binary keeps the best neighbour's plane there whenever that neighbour exists
     // (as_compiled); the intended meaning is "the plane currently stored for the pixel".
     if (!fc.as_compiled || !have_plane_now) plane_now = plane_intended;
+    __syncwarp(FULL);
 
     // ---- PlaneHypothesisRefinement, ACMMP.cu:797-936 -----------------------------------------
     const bool do_refine = weight_norm > 0.0f;      // group-uniform
@@ -762,23 +831,42 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         if (gl == 3) temp_plane = n_pert;
         temp_plane.w = plane_offset(temp_plane, px.dir, cdepth);
     }
-    // The 5 refinement hypotheses x selected views of the pixel are dealt out to the 8 lanes of its group as
-    // (hypothesis, view) pairs: pair p -> hypothesis p % 5, view = (p / 5)-th selected view.  The reference
-    // evaluates every view for every hypothesis and then ignores the zero-weight ones (ACMMP.cu:882-897).
+    __syncwarp(FULL);
+    // The 5 refinement hypotheses are evaluated view by view, only for the selected views (the reference
+    // evaluates every view and then ignores the zero-weight ones, ACMMP.cu:882-897): quad Q of the group
+    // takes the selected views Q, Q+2, ... with all five hypotheses at once (tap-split inside the quad).
+    // Tap depths: lanes of quad 0 fill hypotheses 0-2, lanes of quad 1 hypotheses 3-4; both quads read both.
+    // What is stored per (hypothesis, view) is ncc + 0.1 * geometric cost, the bracket of ACMMP.cu:890.
     {
-        const int n_pairs = (do_refine && valid) ? 5 * __popc(temp_selected_views) : 0;
-        int rounds = (n_pairs + 7) >> 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int h = 3 * Q + k;
+            const float4 hp = shfl_plane(FULL, temp_plane, gbase + min(h, 4));
+            if (h < 5) quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, hp, q, tq + k * kTqPerHyp * TQS);
+        }
+        // the plane of the hypothesis this lane finishes (lane q: hypothesis q; lane 0 also hypothesis 4)
+        const float4 hp_q = shfl_plane(FULL, temp_plane, gbase + q);
+        const float4 hp_4 = shfl_plane(FULL, temp_plane, gbase + 4);
+        __syncwarp(FULL);
+        const int n_sel = (do_refine && valid) ? __popc(temp_selected_views) : 0;
+        int rounds = (n_sel + 1) >> 1;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(FULL, rounds, off));
         for (int r = 0; r < rounds; ++r) {
-            const int pidx = gl + 8 * r;
-            const bool want = pidx < n_pairs;
-            const int h = want ? pidx % 5 : 0;
-            const int vsel = want ? (int)__fns(temp_selected_views, 0, pidx / 5 + 1) : 0;
-            const float4 hp = shfl_plane(gmask, temp_plane, gbase + h);
-            const NccConst cl = s_ncc[vsel];
-            const float cst = ncc_pair<MODEL, TG::PW, TG::RW, WRS>(fc, cl, vsel, tile_r, aux, wr, px, hp, want);
-            if (want) cost_grp[h * nvp + vsel] = cst;
+            const int idx = 2 * r + Q;
+            const bool want = idx < n_sel;
+            const int vsel = want ? (int)__fns(temp_selected_views, 0, idx + 1) : 0;
+            const ViewK c = load_view(s_ncc + vsel);
+            FetchLayer fetch;
+            fetch.tex = (cudaTextureObject_t)fc.tex_src;
+            fetch.layer = vsel;
+            quad_ncc<MODEL, 5, TG::RW, WRS, TQS>(
+                c, px, aux, wr, rr, tq, fetch, q, want ? 0x1Fu : 0u,
+                [&](const int h) { return (h < 3 ? h : h - 3) * kTqPerHyp * TQS + ((h < 3 ? 0 : 1) - Q) * 4; },
+                [&](const int h, float cst) {
+                    if (fc.geom) cst += 0.1f * geom_cost<MODEL>(fc, s_vc[vsel], px, h == 4 ? hp_4 : hp_q);
+                    cost_grp[h * nvp + vsel] = cst;
+                });
         }
         __syncwarp(FULL);
     }
@@ -791,13 +879,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         if (gl < 5) {
             for (int j = 0; j < nsrc; ++j) {
                 const float wj = vw[j];
-                if (wj > 0.0f) {
-                    if (fc.geom) {
-                        temp_cost += wj * (costrow[j] + 0.1f * geom_cost<MODEL>(fc, s_vc[j], px, temp_plane));
-                    } else {
-                        temp_cost += wj * costrow[j];
-                    }
-                }
+                if (wj > 0.0f) temp_cost += wj * costrow[j];
             }
             temp_cost /= weight_norm;
             depth_before = plane_depth(temp_plane, px.dir);

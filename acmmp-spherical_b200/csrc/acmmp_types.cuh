@@ -48,16 +48,18 @@ static_assert(sizeof(ViewConst) == 72 * 4, "ViewConst layout");
 // uniform texture handle -- no per-lane register copies, no non-uniform-handle replay loop.
 //   PINHOLE: a[0..2]=Fx a[3..5]=Fy a[6..8]=Fz a[9..11]=fb a[12]=W+0.5 a[13]=H+0.5
 //   SPHERE : a[0..8]=R  a[9..11]=t a[12]=cx a[13]=cy a[14]=W a[15]=H
-struct NccConst {
+struct alignas(16) NccConst {
     float a[16];
 };
-// All source views live in ONE layered R32F texture (layer = view index): a single handle that is
-// trivially warp-uniform.  (One texture object per view makes ptxas wrap every TEX in a
-// non-uniform-handle replay loop, ~8 extra instructions per sample.)
+// The source views exist twice on the device: as one 2-D R32F texture per view (tex[v]: the handle is
+// warp-uniform in the view loops, the fetch is a plain TEX.LZ with no extra operands) and as the layers of
+// ONE layered texture (FrameConst::tex_src) for the places where the lanes of a warp work on different
+// views at the same time (one handle, per-lane layer).
 struct NccTable {
     NccConst c[kMaxSrc];
+    unsigned long long tex[kMaxSrc];
 };
-static_assert(sizeof(NccTable) == kMaxSrc * 64, "NccTable layout");
+static_assert(sizeof(NccTable) == kMaxSrc * 72, "NccTable layout");
 
 // Per reference view + stage; passed by value (__grid_constant__).
 struct FrameConst {
