@@ -79,7 +79,7 @@ _EXPORTS = [
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
     "acmmp_get_params", "acmmp_reset_modes", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
     "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_set_seed",
-    "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_random_init", "acmmp_checkerboard_pass",
+    "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_download_state", "acmmp_upload_state",
     "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_geom", "acmmp_probe_warp",
@@ -257,8 +257,15 @@ class Context:
         self._ck(self._l.acmmp_set_plane_now_semantics(self._h, C.c_int(1 if as_compiled else 0)), "set_plane_now_semantics")
 
     # ---- compute ------------------------------------------------------------------------
-    def run_patch_match(self):
-        self._ck(self._l.acmmp_run_patch_match(self._h), "acmmp_run_patch_match")
+    def run_patch_match(self, download=True):
+        """One stage (RunPatchMatch).  download=False keeps the result on the device (GPU-resident chaining)."""
+        if download:
+            self._ck(self._l.acmmp_run_patch_match(self._h), "acmmp_run_patch_match")
+        else:
+            self._ck(self._l.acmmp_run_patch_match_resident(self._h), "acmmp_run_patch_match_resident")
+
+    def download_result(self):
+        self._ck(self._l.acmmp_download_result(self._h), "acmmp_download_result")
 
     def random_init(self):
         self._ck(self._l.acmmp_random_init(self._h), "acmmp_random_init")

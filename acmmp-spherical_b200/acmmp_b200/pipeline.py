@@ -75,35 +75,44 @@ def _nbytes(*arrays):
 class B200Backend:
     """Stages through libacmmp_b200.so, GPU-resident: one context per view, the state of a stage is handed
     to the next one on the device (acmmp_next_level, acmmp_set_depth_maps with maps[0] == NULL); per level
-    the host only sends the images, the neighbours' depth maps and the prior, and reads each stage's result."""
+    the host only sends the images, the neighbours' depth maps and the prior.  Results come back to the host
+    where the host needs them: after the photometric stage (input of the CPU planar-prior stage) and after the
+    last stage of the finest level (the view's output); `download_all=True` fetches every stage like the
+    reference's RunPatchMatch does.  The context (and its buffer pool) can be kept for the next view."""
     name = "b200"
 
-    def __init__(self, device=0, seed=1234, as_compiled=True):
+    def __init__(self, device=0, seed=1234, as_compiled=True, ctx=None, download_all=False):
         self.device, self.seed, self.as_compiled = device, seed, as_compiled
-        self.ctx = None
+        self.ctx = ctx
+        self.keep_ctx = ctx is not None
+        self.download_all = download_all
+        self.launches0 = ctx.launch_count() if ctx is not None else 0
         self.t = StageTimes()
 
-    def _run(self, stage, finest):
+    def _run(self, stage, finest, download):
         ctx = self.ctx
+        download = download or self.download_all
         t0 = time.perf_counter()
-        ctx.run_patch_match()
-        planes, costs = ctx.result_host()
+        ctx.run_patch_match(download=download)
+        planes = costs = None
+        if download:
+            planes, costs = ctx.result_host()
+            self.t.d2h_bytes += _nbytes(planes, costs)
         self.t.wall_s += time.perf_counter() - t0
         tm = ctx.timings()
         self.t.gpu_ms += tm["init_ms"] + tm["pass_sum_ms"] + tm["finalize_ms"]
         self.t.passes += tm["n_pass"]
-        self.t.d2h_bytes += _nbytes(planes, costs)
         if finest and tm["n_pass"]:
             self.t.pass_ms.setdefault(stage, []).append(tm["pass_sum_ms"] / tm["n_pass"])
         return planes, costs
 
-    def begin_level(self, level: Level, prev=None):
+    def begin_level(self, level: Level, prev=None, first=True):
         t0 = time.perf_counter()
         if self.ctx is None:
             self.ctx = Context(self.device)
+        if first:
             self.ctx.set_seed(self.seed)
             self.ctx.set_plane_now_semantics(self.as_compiled)
-        if prev is None:
             self.ctx.reset_modes()
             self.ctx.set_views(level.images, level.cams)
         else:
@@ -113,30 +122,41 @@ class B200Backend:
         self.t.h2d_bytes += _nbytes(*level.images)
 
     def photometric(self, level, finest=False):
-        return self._run("photometric", finest)
+        return self._run("photometric", finest, download=True)      # the CPU prior stage reads it
 
     def prior(self, level, params, masks, finest=False):
         t0 = time.perf_counter()
         self.ctx.set_planar_prior_inputs(params, masks)
         self.t.wall_s += time.perf_counter() - t0
         self.t.h2d_bytes += _nbytes(masks, params)
-        return self._run("prior", finest)
+        return self._run("prior", finest, download=False)
 
-    def geom(self, level, multi, neighbour_depths, finest=False):
+    def own_depth_to(self, dev_ptr):
+        """Current depth map -> a caller-owned device buffer (what a neighbour needs); waits for it."""
+        self.ctx.export_depth_device(dev_ptr)
+        self.ctx.synchronize()
+
+    def geom(self, level, multi, neighbour_depths, finest=False, last=False, device_ptrs=None):
+        """neighbour_depths: host arrays (uploaded here), or device_ptrs = [(ptr, w, h), ...] already on the device."""
         ctx = self.ctx
         t0 = time.perf_counter()
         ctx.reset_modes()
         ctx.set_geom_consistency(multi)
-        ctx.set_depth_maps([None] + list(neighbour_depths))     # own map: from the device-resident state
+        if device_ptrs is not None:
+            ctx.set_depth_maps_device([0] + [p for p, _, _ in device_ptrs], [ctx.W] + [w for _, w, _ in device_ptrs],
+                                      [ctx.H] + [h for _, _, h in device_ptrs])
+        else:
+            ctx.set_depth_maps([None] + list(neighbour_depths))     # own map: from the device-resident state
+            self.t.h2d_bytes += _nbytes(*neighbour_depths)
         self.t.wall_s += time.perf_counter() - t0
-        self.t.h2d_bytes += _nbytes(*neighbour_depths)
-        return self._run("geom", finest)
+        return self._run("geom", finest, download=last)
 
     def end(self):
         if self.ctx is not None:
-            self.t.launches += self.ctx.launch_count()
-            self.ctx.close()
-            self.ctx = None
+            self.t.launches += self.ctx.launch_count() - self.launches0
+            if not self.keep_ctx:
+                self.ctx.close()
+                self.ctx = None
 
 
 class ReferenceBackend:
@@ -152,7 +172,7 @@ class ReferenceBackend:
         self.prev = None
         self.last = None
 
-    def begin_level(self, level, prev=None):
+    def begin_level(self, level, prev=None, first=True):
         self.prev = prev
 
     def _finish(self, stage, finest, t_setup):
@@ -191,7 +211,7 @@ class ReferenceBackend:
         self.obj.set_prior(params, masks)
         return self._finish("prior", finest, time.perf_counter() - t0)
 
-    def geom(self, level, multi, neighbour_depths, finest=False):
+    def geom(self, level, multi, neighbour_depths, finest=False, last=False, device_ptrs=None):
         from oracle.ref_driver import RefACMMP
         own_planes, own_costs = self.last
         if self.obj is not None:
@@ -208,18 +228,20 @@ class ReferenceBackend:
             self.obj = None
 
 
-def run_view(levels, backend, prior_cache=None, neighbour_depths_fn=None):
+def run_view(levels, backend, prior_cache=None, exchange=None):
     """One reference view through every level and stage.  Returns (planes, costs) of the finest level
     -- planes = (world normal, depth) -- and leaves the timings in backend.t.
     prior_cache: dict level index -> (params, masks); filled when empty (the CPU prior stage is
     deterministic given the deterministic photometric stage, so later steps may reuse it).
-    neighbour_depths_fn(level, own_depth) -> list of source-view depth maps (default: level.neighbour_depths)."""
+    exchange: object with neighbour_depths(level_index, level, backend) -> (host_maps, device_ptrs), one of them
+    None: the source views' depth maps for the next geometric stage (default: level.neighbour_depths)."""
     if prior_cache is None:
         prior_cache = {}
     state = None
+    out = None
     for li, L in enumerate(levels):
         finest = li == len(levels) - 1
-        backend.begin_level(L, state)
+        backend.begin_level(L, state, first=(li == 0))
         planes, costs = backend.photometric(L, finest)
         if li not in prior_cache:
             t0 = time.perf_counter()
@@ -230,7 +252,12 @@ def run_view(levels, backend, prior_cache=None, neighbour_depths_fn=None):
         params, masks = prior_cache[li]
         planes, costs = backend.prior(L, params, masks, finest)
         for multi in (False, True):
-            nd = L.neighbour_depths if neighbour_depths_fn is None else neighbour_depths_fn(L, planes[..., 3])
-            planes, costs = backend.geom(L, multi, nd, finest)
-        state = (np.array(planes), np.array(costs))
-    return state
+            if exchange is None:
+                host_maps, dev = L.neighbour_depths, None
+            else:
+                host_maps, dev = exchange.neighbour_depths(li, L, backend)
+            planes, costs = backend.geom(L, multi, host_maps, finest, last=(finest and multi), device_ptrs=dev)
+        if planes is not None:
+            out = (np.array(planes), np.array(costs))
+        state = True if out is None else out        # the reference backend hands the host arrays to the next level
+    return out

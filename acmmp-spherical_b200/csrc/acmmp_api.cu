@@ -8,8 +8,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda.h>
@@ -151,7 +154,75 @@ inline M3 kproj(const float K[9])
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
+// Size-keyed free lists for device memory, pinned host memory and CUDA arrays.  A view walks through the
+// same three pyramid-level shapes over and over (and a context is re-used for consecutive views), so after
+// the first level visit nothing is cudaMalloc'ed / cudaMallocHost'ed again (the reference allocates and
+// frees everything per ProcessProblem call, ACMMP.cpp:685-724 / :101-143).
+struct MemPool {
+    std::multimap<size_t, void *> dev_free, host_free;
+    std::unordered_map<void *, size_t> dev_size, host_size;
+    typedef std::tuple<int, int, int> ArrKey;
+    std::multimap<ArrKey, cudaArray_t> arr_free;
+    std::map<cudaArray_t, ArrKey> arr_key;
+
+    cudaError_t dmalloc(void **p, size_t bytes)
+    {
+        auto it = dev_free.find(bytes);
+        if (it != dev_free.end()) { *p = it->second; dev_free.erase(it); return cudaSuccess; }
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) dev_size[*p] = bytes;
+        return e;
+    }
+    void dfree(void *p)
+    {
+        if (!p) return;
+        auto it = dev_size.find(p);
+        if (it == dev_size.end()) { cudaFree(p); return; }
+        dev_free.insert(std::make_pair(it->second, p));
+    }
+    cudaError_t hmalloc(void **p, size_t bytes)
+    {
+        auto it = host_free.find(bytes);
+        if (it != host_free.end()) { *p = it->second; host_free.erase(it); return cudaSuccess; }
+        cudaError_t e = cudaMallocHost(p, bytes);
+        if (e == cudaSuccess) host_size[*p] = bytes;
+        return e;
+    }
+    void hfree(void *p)
+    {
+        if (!p) return;
+        auto it = host_size.find(p);
+        if (it == host_size.end()) { cudaFreeHost(p); return; }
+        host_free.insert(std::make_pair(it->second, p));
+    }
+    cudaError_t amalloc(cudaArray_t *a, const cudaChannelFormatDesc *desc, int w, int h, int layers)
+    {
+        const ArrKey k(w, h, layers);
+        auto it = arr_free.find(k);
+        if (it != arr_free.end()) { *a = it->second; arr_free.erase(it); return cudaSuccess; }
+        cudaError_t e = layers > 0 ? cudaMalloc3DArray(a, desc, make_cudaExtent(w, h, layers), cudaArrayLayered)
+                                   : cudaMallocArray(a, desc, w, h);
+        if (e == cudaSuccess) arr_key[*a] = k;
+        return e;
+    }
+    void afree(cudaArray_t a)
+    {
+        if (!a) return;
+        auto it = arr_key.find(a);
+        if (it == arr_key.end()) { cudaFreeArray(a); return; }
+        arr_free.insert(std::make_pair(it->second, a));
+    }
+    void release_all()
+    {
+        for (auto &kv : dev_size) cudaFree(kv.first);
+        for (auto &kv : host_size) cudaFreeHost(kv.first);
+        for (auto &kv : arr_key) cudaFreeArray(kv.first);
+        dev_free.clear(); host_free.clear(); dev_size.clear(); host_size.clear(); arr_free.clear(); arr_key.clear();
+    }
+};
+
 struct acmmp_ctx {
+    MemPool pool;
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -160,6 +231,7 @@ struct acmmp_ctx {
     int use_tma = 1;
     uint64_t seed = 0;
     bool have_seeded = false;
+    std::map<std::tuple<uint64_t, int, int>, uint2 *> seeded_cache;   // curand_init states per (seed, W, H), kept across levels
     uint64_t seeded_seed = 0;
     int seeded_w = 0, seeded_h = 0;
 
@@ -207,6 +279,9 @@ struct acmmp_ctx {
 };
 
 namespace {
+
+template <typename T> cudaError_t pmalloc(acmmp_ctx *ctx, T **p, size_t bytes) { return ctx->pool.dmalloc(reinterpret_cast<void **>(p), bytes); }
+template <typename T> cudaError_t phmalloc(acmmp_ctx *ctx, T **p, size_t bytes) { return ctx->pool.hmalloc(reinterpret_cast<void **>(p), bytes); }
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
@@ -259,26 +334,26 @@ int make_tmap(acmmp_ctx *ctx, CUtensorMap *tm, int box_w, int box_h)
 void free_views(acmmp_ctx *ctx)
 {
     if (ctx->src_tex) cudaDestroyTextureObject(ctx->src_tex);
-    if (ctx->src_array) cudaFreeArray(ctx->src_array);
+    if (ctx->src_array) ctx->pool.afree(ctx->src_array);
     for (cudaTextureObject_t t : ctx->view_tex) cudaDestroyTextureObject(t);
-    for (cudaArray_t a : ctx->view_arrays) cudaFreeArray(a);
+    for (cudaArray_t a : ctx->view_arrays) ctx->pool.afree(a);
     ctx->view_tex.clear();
     ctx->view_arrays.clear();
     ctx->src_tex = 0;
     ctx->src_array = nullptr;
-    cudaFree(ctx->ref_dense); ctx->ref_dense = nullptr;
-    cudaFree(ctx->ref_padded); ctx->ref_padded = nullptr;
-    cudaFree(ctx->views_dev); ctx->views_dev = nullptr;
-    cudaFree(ctx->planes); cudaFree(ctx->planes_alt); cudaFree(ctx->costs); cudaFree(ctx->costs_alt);
-    cudaFree(ctx->pre_costs); cudaFree(ctx->selected_views); cudaFree(ctx->rng); cudaFree(ctx->rng_seeded);
-    cudaFree(ctx->prior_planes); cudaFree(ctx->plane_masks); cudaFree(ctx->coarse_planes);
+    ctx->pool.dfree(ctx->ref_dense); ctx->ref_dense = nullptr;
+    ctx->pool.dfree(ctx->ref_padded); ctx->ref_padded = nullptr;
+    ctx->pool.dfree(ctx->views_dev); ctx->views_dev = nullptr;
+    ctx->pool.dfree(ctx->planes); ctx->pool.dfree(ctx->planes_alt); ctx->pool.dfree(ctx->costs); ctx->pool.dfree(ctx->costs_alt);
+    ctx->pool.dfree(ctx->pre_costs); ctx->pool.dfree(ctx->selected_views); ctx->pool.dfree(ctx->rng);
+    ctx->pool.dfree(ctx->prior_planes); ctx->pool.dfree(ctx->plane_masks); ctx->pool.dfree(ctx->coarse_planes);
     ctx->planes = ctx->planes_alt = nullptr;
     ctx->costs = ctx->costs_alt = ctx->pre_costs = nullptr;
     ctx->selected_views = nullptr;
     ctx->rng = ctx->rng_seeded = nullptr;
     ctx->prior_planes = nullptr; ctx->plane_masks = nullptr; ctx->coarse_planes = nullptr;
-    if (ctx->planes_host) cudaFreeHost(ctx->planes_host);
-    if (ctx->costs_host) cudaFreeHost(ctx->costs_host);
+    if (ctx->planes_host) ctx->pool.hfree(ctx->planes_host);
+    if (ctx->costs_host) ctx->pool.hfree(ctx->costs_host);
     ctx->planes_host = nullptr; ctx->costs_host = nullptr;
     ctx->have_seeded = false;
     ctx->have_result = false;
@@ -287,7 +362,7 @@ void free_views(acmmp_ctx *ctx)
 void free_depths(acmmp_ctx *ctx)
 {
     for (size_t i = 0; i < ctx->depth_maps.size(); ++i)
-        if (ctx->depth_owned[i]) cudaFree(ctx->depth_maps[i]);
+        if (ctx->depth_owned[i]) ctx->pool.dfree(ctx->depth_maps[i]);
     ctx->depth_maps.clear();
     ctx->depth_ptrs.clear();
     ctx->depth_w.clear();
@@ -363,7 +438,7 @@ int upload_view_consts(acmmp_ctx *ctx)
             vc[i].dH = ctx->depth_h[i + 1];
         }
     }
-    if (!ctx->views_dev) CK(cudaMalloc(&ctx->views_dev, sizeof(ViewConst) * kMaxSrc));
+    if (!ctx->views_dev) CK(pmalloc(ctx, &ctx->views_dev, sizeof(ViewConst) * kMaxSrc));
     CK(cudaMemcpyAsync(ctx->views_dev, vc.data(), sizeof(ViewConst) * (size_t)(nsrc > 0 ? nsrc : 1), cudaMemcpyHostToDevice,
                        ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));       // vc is a stack-lifetime staging buffer
@@ -456,16 +531,24 @@ int configure_kernels(acmmp_ctx *ctx)
 int ensure_seeded(acmmp_ctx *ctx)
 {
     if (ctx->have_seeded && ctx->seeded_seed == ctx->seed && ctx->seeded_w == ctx->W && ctx->seeded_h == ctx->H) return ACMMP_OK;
-    std::vector<uint32_t> rows;
-    xorwow_row_states(ctx->seed, ctx->H, rows);
-    uint32_t *rows_dev = nullptr;
-    CK(cudaMalloc(&rows_dev, rows.size() * sizeof(uint32_t)));
-    CK(cudaMemcpyAsync(rows_dev, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    k_rng_fill<<<(ctx->H + 63) / 64, 64, 0, ctx->stream>>>(rows_dev, ctx->W, ctx->H, ctx->rng_seeded);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaFree(rows_dev));
+    const auto key = std::make_tuple(ctx->seed, ctx->W, ctx->H);
+    auto it = ctx->seeded_cache.find(key);
+    if (it == ctx->seeded_cache.end()) {
+        uint2 *buf = nullptr;
+        CK(pmalloc(ctx, &buf, sizeof(uint2) * 3 * (size_t)ctx->W * ctx->H));
+        std::vector<uint32_t> rows;
+        xorwow_row_states(ctx->seed, ctx->H, rows);
+        uint32_t *rows_dev = nullptr;
+        CK(pmalloc(ctx, &rows_dev, rows.size() * sizeof(uint32_t)));
+        CK(cudaMemcpyAsync(rows_dev, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        k_rng_fill<<<(ctx->H + 63) / 64, 64, 0, ctx->stream>>>(rows_dev, ctx->W, ctx->H, buf);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->pool.dfree(rows_dev);
+        it = ctx->seeded_cache.insert(std::make_pair(key, buf)).first;
+    }
+    ctx->rng_seeded = it->second;
     ctx->have_seeded = true;
     ctx->seeded_seed = ctx->seed;
     ctx->seeded_w = ctx->W;
@@ -518,7 +601,7 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
             ctx->src_h = std::max(ctx->src_h, (int)heights[i]);
             if (widths[i] != widths[1] || heights[i] != heights[1]) ctx->manual_clamp = true;
         }
-        CK(cudaMalloc3DArray(&ctx->src_array, &desc, make_cudaExtent(ctx->src_w, ctx->src_h, n - 1), cudaArrayLayered));
+        CK(ctx->pool.amalloc(&ctx->src_array, &desc, ctx->src_w, ctx->src_h, n - 1));
         {
             cudaResourceDesc res;
             std::memset(&res, 0, sizeof(res));
@@ -537,7 +620,7 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
             CK(cudaCreateTextureObject(&ctx->src_tex, &res, &td, nullptr));
             for (int i = 1; i < n; ++i) {
                 cudaArray_t arr = nullptr;
-                CK(cudaMallocArray(&arr, &desc, widths[i], heights[i]));
+                CK(ctx->pool.amalloc(&arr, &desc, widths[i], heights[i], 0));
                 ctx->view_arrays.push_back(arr);
                 res.res.array.array = arr;
                 cudaTextureObject_t t = 0;
@@ -546,22 +629,21 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
             }
         }
         ctx->ref_pitch = (ctx->W + 2 * kRefPad + 3) & ~3;
-        CK(cudaMalloc(&ctx->ref_dense, sizeof(float) * npx));
-        CK(cudaMalloc(&ctx->ref_padded, sizeof(float) * (size_t)ctx->ref_pitch * (ctx->H + 2 * kRefPad)));
-        CK(cudaMalloc(&ctx->planes, sizeof(float4) * npx));
-        CK(cudaMalloc(&ctx->planes_alt, sizeof(float4) * npx));
-        CK(cudaMalloc(&ctx->costs, sizeof(float) * npx));
-        CK(cudaMalloc(&ctx->costs_alt, sizeof(float) * npx));
-        CK(cudaMalloc(&ctx->pre_costs, sizeof(float) * npx));
-        CK(cudaMalloc(&ctx->selected_views, sizeof(uint32_t) * npx));
-        CK(cudaMalloc(&ctx->rng, sizeof(uint2) * 3 * npx));
-        CK(cudaMalloc(&ctx->rng_seeded, sizeof(uint2) * 3 * npx));
+        CK(pmalloc(ctx, &ctx->ref_dense, sizeof(float) * npx));
+        CK(pmalloc(ctx, &ctx->ref_padded, sizeof(float) * (size_t)ctx->ref_pitch * (ctx->H + 2 * kRefPad)));
+        CK(pmalloc(ctx, &ctx->planes, sizeof(float4) * npx));
+        CK(pmalloc(ctx, &ctx->planes_alt, sizeof(float4) * npx));
+        CK(pmalloc(ctx, &ctx->costs, sizeof(float) * npx));
+        CK(pmalloc(ctx, &ctx->costs_alt, sizeof(float) * npx));
+        CK(pmalloc(ctx, &ctx->pre_costs, sizeof(float) * npx));
+        CK(pmalloc(ctx, &ctx->selected_views, sizeof(uint32_t) * npx));
+        CK(pmalloc(ctx, &ctx->rng, sizeof(uint2) * 3 * npx));
         CK(cudaMemsetAsync(ctx->planes, 0, sizeof(float4) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->costs, 0, sizeof(float) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->pre_costs, 0, sizeof(float) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->selected_views, 0, sizeof(uint32_t) * npx, ctx->stream));
-        CK(cudaMallocHost(&ctx->planes_host, sizeof(float4) * npx));
-        CK(cudaMallocHost(&ctx->costs_host, sizeof(float) * npx));
+        CK(phmalloc(ctx, &ctx->planes_host, sizeof(float4) * npx));
+        CK(phmalloc(ctx, &ctx->costs_host, sizeof(float) * npx));
         typedef TileGeom<kPassTW, kPassTH> TGp;
         typedef TileGeom<kTpTW, kTpTH> TGt;
         int rc = make_tmap(ctx, &ctx->tmap_pass, TGp::PW, TGp::RH);
@@ -575,40 +657,40 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
         ctx->cams[i].height = heights[i];
     }
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    float *pad_src = nullptr, *pad_dst = nullptr;
-    if (ctx->manual_clamp) {
-        CK(cudaMalloc(&pad_src, sizeof(float) * (size_t)ctx->src_w * ctx->src_h));
-        CK(cudaMalloc(&pad_dst, sizeof(float) * (size_t)ctx->src_w * ctx->src_h));
-    }
+    float *pad_dst = nullptr;
+    if (ctx->manual_clamp) CK(pmalloc(ctx, &pad_dst, sizeof(float) * (size_t)ctx->src_w * ctx->src_h));
+    // host images cross PCIe once, into a linear staging buffer; both texture copies are device-to-device
+    float *stage = nullptr;
+    if (!on_device) CK(pmalloc(ctx, &stage, sizeof(float) * (size_t)ctx->src_w * ctx->src_h));
     for (int i = 1; i < n; ++i) {
+        const float *src_dev = images[i];
+        if (!on_device) {
+            CK(cudaMemcpyAsync(stage, images[i], sizeof(float) * (size_t)widths[i] * heights[i], cudaMemcpyHostToDevice, ctx->stream));
+            src_dev = stage;
+        }
         cudaMemcpy3DParms cp;
         std::memset(&cp, 0, sizeof(cp));
         cp.dstArray = ctx->src_array;
         cp.dstPos = make_cudaPos(0, 0, i - 1);
+        cp.kind = cudaMemcpyDeviceToDevice;
         if (widths[i] == ctx->src_w && heights[i] == ctx->src_h) {
-            cp.srcPtr = make_cudaPitchedPtr(const_cast<float *>(images[i]), sizeof(float) * widths[i], widths[i], heights[i]);
+            cp.srcPtr = make_cudaPitchedPtr(const_cast<float *>(src_dev), sizeof(float) * widths[i], widths[i], heights[i]);
             cp.extent = make_cudaExtent(widths[i], heights[i], 1);
-            cp.kind = kind;
         } else {
             // smaller than the layer: replicate the last column / row so that hardware clamping at the
             // layer edge equals clamping at the image edge
-            CK(cudaMemcpyAsync(pad_src, images[i], sizeof(float) * (size_t)widths[i] * heights[i], kind, ctx->stream));
             dim3 grid((ctx->src_w + 255) / 256, ctx->src_h);
-            k_replicate_pad<<<grid, 256, 0, ctx->stream>>>(pad_src, widths[i], heights[i], pad_dst, ctx->src_w, ctx->src_h);
+            k_replicate_pad<<<grid, 256, 0, ctx->stream>>>(src_dev, widths[i], heights[i], pad_dst, ctx->src_w, ctx->src_h);
             ctx->launches++;
             cp.srcPtr = make_cudaPitchedPtr(pad_dst, sizeof(float) * ctx->src_w, ctx->src_w, ctx->src_h);
             cp.extent = make_cudaExtent(ctx->src_w, ctx->src_h, 1);
-            cp.kind = cudaMemcpyDeviceToDevice;
         }
         CK(cudaMemcpy3DAsync(&cp, ctx->stream));
-        CK(cudaMemcpy2DToArrayAsync(ctx->view_arrays[i - 1], 0, 0, images[i], sizeof(float) * widths[i], sizeof(float) * widths[i],
-                                    heights[i], kind, ctx->stream));
+        CK(cudaMemcpy2DToArrayAsync(ctx->view_arrays[i - 1], 0, 0, src_dev, sizeof(float) * widths[i], sizeof(float) * widths[i],
+                                    heights[i], cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    if (ctx->manual_clamp) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(pad_src);
-        cudaFree(pad_dst);
-    }
+    if (stage) ctx->pool.dfree(stage);      // stream-ordered reuse: later users enqueue on the same stream
+    if (ctx->manual_clamp) ctx->pool.dfree(pad_dst);
     CK(cudaMemcpyAsync(ctx->ref_dense, images[0], sizeof(float) * (size_t)ctx->W * ctx->H, kind, ctx->stream));
     {
         dim3 grid((ctx->ref_pitch + 255) / 256, ctx->H + 2 * kRefPad);
@@ -643,7 +725,7 @@ int set_depths_common(acmmp_ctx *ctx, int n, const float *const *maps, bool on_d
             if (widths[0] != ctx->W || heights[0] != ctx->H) return fail(ctx, ACMMP_E_ARG, "own depth map must have the view's size");
             float *d = nullptr;
             const int npx = ctx->W * ctx->H;
-            CK(cudaMalloc(&d, sizeof(float) * (size_t)npx));
+            CK(pmalloc(ctx, &d, sizeof(float) * (size_t)npx));
             k_export_depth<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(ctx->planes, npx, d);
             ctx->launches++;
             CK(cudaGetLastError());
@@ -656,7 +738,7 @@ int set_depths_common(acmmp_ctx *ctx, int n, const float *const *maps, bool on_d
             ctx->depth_owned.push_back(false);
         } else {
             float *d = nullptr;
-            CK(cudaMalloc(&d, sizeof(float) * (size_t)widths[i] * heights[i]));
+            CK(pmalloc(ctx, &d, sizeof(float) * (size_t)widths[i] * heights[i]));
             CK(cudaMemcpyAsync(d, maps[i], sizeof(float) * (size_t)widths[i] * heights[i], cudaMemcpyHostToDevice, ctx->stream));
             ctx->depth_maps.push_back(d);
             ctx->depth_ptrs.push_back(d);
@@ -799,10 +881,10 @@ int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *o
     float4 *dp = nullptr, *do4 = nullptr;
     float *dout = nullptr;
     uint32_t *dv = nullptr;
-    CK(cudaMalloc(&dp, sizeof(float4) * npx));
-    CK(cudaMalloc(&do4, sizeof(float4) * npx));
-    CK(cudaMalloc(&dout, sizeof(float) * npx));
-    CK(cudaMalloc(&dv, sizeof(uint32_t) * npx));
+    CK(pmalloc(ctx, &dp, sizeof(float4) * npx));
+    CK(pmalloc(ctx, &do4, sizeof(float4) * npx));
+    CK(pmalloc(ctx, &dout, sizeof(float) * npx));
+    CK(pmalloc(ctx, &dv, sizeof(uint32_t) * npx));
     CK(cudaMemcpyAsync(dp, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
     rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe<kModelPinhole>(ctx, mode, view, dp, dout, do4, dv)
                                                      : launch_probe<kModelSphere>(ctx, mode, view, dp, dout, do4, dv);
@@ -812,7 +894,7 @@ int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *o
         if (out_views) CK(cudaMemcpyAsync(out_views, dv, sizeof(uint32_t) * npx, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    cudaFree(dp); cudaFree(do4); cudaFree(dout); cudaFree(dv);
+    ctx->pool.dfree(dp); ctx->pool.dfree(do4); ctx->pool.dfree(dout); ctx->pool.dfree(dv);
     return rc;
 }
 
@@ -870,6 +952,7 @@ int acmmp_destroy(acmmp_ctx *ctx)
     free_depths(ctx);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
     for (auto &pe : ctx->pass_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+    ctx->pool.release_all();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ACMMP_OK;
@@ -966,9 +1049,9 @@ int acmmp_set_hierarchy_inputs(acmmp_ctx *ctx, const float *coarse_planes4, int 
         return fail(ctx, ACMMP_E_ARG, "acmmp_set_hierarchy_inputs: bad arguments");
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)ctx->W * ctx->H;
-    cudaFree(ctx->coarse_planes);
+    ctx->pool.dfree(ctx->coarse_planes);
     ctx->coarse_planes = nullptr;
-    CK(cudaMalloc(&ctx->coarse_planes, sizeof(float4) * (size_t)sw * sh));
+    CK(pmalloc(ctx, &ctx->coarse_planes, sizeof(float4) * (size_t)sw * sh));
     CK(cudaMemcpyAsync(ctx->coarse_planes, coarse_planes4, sizeof(float4) * (size_t)sw * sh, cudaMemcpyHostToDevice, ctx->stream));
     ctx->scaled_cols = sw;
     ctx->scaled_rows = sh;
@@ -992,20 +1075,20 @@ int acmmp_set_planar_prior_inputs(acmmp_ctx *ctx, const float *plane_params4, in
     const int npx = ctx->W * ctx->H;
     float *masks_dev = nullptr;
     float4 *params_dev = nullptr;
-    CK(cudaMalloc(&masks_dev, sizeof(float) * (size_t)npx));
-    CK(cudaMalloc(&params_dev, sizeof(float4) * (size_t)std::max(n_planes, 1)));
+    CK(pmalloc(ctx, &masks_dev, sizeof(float) * (size_t)npx));
+    CK(pmalloc(ctx, &params_dev, sizeof(float4) * (size_t)std::max(n_planes, 1)));
     CK(cudaMemcpyAsync(masks_dev, masks, sizeof(float) * (size_t)npx, cudaMemcpyHostToDevice, ctx->stream));
     if (n_planes > 0)
         CK(cudaMemcpyAsync(params_dev, plane_params4, sizeof(float4) * (size_t)n_planes, cudaMemcpyHostToDevice, ctx->stream));
-    if (!ctx->prior_planes) CK(cudaMalloc(&ctx->prior_planes, sizeof(float4) * (size_t)npx));
-    if (!ctx->plane_masks) CK(cudaMalloc(&ctx->plane_masks, sizeof(uint32_t) * (size_t)npx));
+    if (!ctx->prior_planes) CK(pmalloc(ctx, &ctx->prior_planes, sizeof(float4) * (size_t)npx));
+    if (!ctx->plane_masks) CK(pmalloc(ctx, &ctx->plane_masks, sizeof(uint32_t) * (size_t)npx));
     k_expand_prior<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(masks_dev, params_dev, std::max(n_planes, 1), npx, ctx->prior_planes,
                                                               ctx->plane_masks);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(masks_dev);
-    cudaFree(params_dev);
+    ctx->pool.dfree(masks_dev);
+    ctx->pool.dfree(params_dev);
     ctx->params.planar_prior = 1;
     return ACMMP_OK;
 }
@@ -1018,23 +1101,23 @@ int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const in
     const int sw = ctx->W, sh = ctx->H, snpx = sw * sh;
     float4 *coarse = nullptr;
     float *coarse_depth = nullptr;
-    CK(cudaMalloc(&coarse, sizeof(float4) * (size_t)snpx));
-    CK(cudaMalloc(&coarse_depth, sizeof(float) * (size_t)snpx));
+    CK(pmalloc(ctx, &coarse, sizeof(float4) * (size_t)snpx));
+    CK(pmalloc(ctx, &coarse_depth, sizeof(float) * (size_t)snpx));
     k_make_coarse<<<(snpx + 255) / 256, 256, 0, ctx->stream>>>(ctx->planes, ctx->costs, snpx, coarse, coarse_depth);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     acmmp_reset_modes(ctx);
     int rc = set_views_common(ctx, n, images, false, widths, heights, cams);      // re-allocates at the new size
-    if (rc) { cudaFree(coarse); cudaFree(coarse_depth); return rc; }
+    if (rc) { ctx->pool.dfree(coarse); ctx->pool.dfree(coarse_depth); return rc; }
     const int npx = ctx->W * ctx->H;
     const int Imagescale = std::max(ctx->H / sh, ctx->W / sw);
     float *fine_depth = nullptr;
-    CK(cudaMalloc(&fine_depth, sizeof(float) * (size_t)npx));
+    CK(pmalloc(ctx, &fine_depth, sizeof(float) * (size_t)npx));
     if (Imagescale == 1) {
         // RunJBU produces nothing in this case (ACMMP.cpp:1077-1080) and the reference would re-read the old
         // depths.dmb; same size here means the coarse depth is the depth
-        if (npx != snpx) { cudaFree(coarse); cudaFree(coarse_depth); cudaFree(fine_depth); return fail(ctx, ACMMP_E_UNSUPPORTED, "level size ratio < 2"); }
+        if (npx != snpx) { ctx->pool.dfree(coarse); ctx->pool.dfree(coarse_depth); ctx->pool.dfree(fine_depth); return fail(ctx, ACMMP_E_UNSUPPORTED, "level size ratio < 2"); }
         CK(cudaMemcpyAsync(fine_depth, coarse_depth, sizeof(float) * (size_t)npx, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
         cudaEvent_t e0, e1;
@@ -1046,12 +1129,12 @@ int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const in
         cudaEventElapsedTime(&ctx->t_jbu, e0, e1);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         ctx->launches++;
-        if (rc) { cudaFree(coarse); cudaFree(coarse_depth); cudaFree(fine_depth); return fail(ctx, rc, "JBU failed"); }
+        if (rc) { ctx->pool.dfree(coarse); ctx->pool.dfree(coarse_depth); ctx->pool.dfree(fine_depth); return fail(ctx, rc, "JBU failed"); }
     }
     k_seed_planes_from_depth<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(fine_depth, npx, ctx->planes);
     ctx->launches++;
     CK(cudaGetLastError());
-    cudaFree(ctx->coarse_planes);
+    ctx->pool.dfree(ctx->coarse_planes);
     ctx->coarse_planes = coarse;
     ctx->scaled_cols = sw;
     ctx->scaled_rows = sh;
@@ -1060,8 +1143,8 @@ int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const in
     ctx->params.scaled_cols = (float)sw;
     ctx->params.scaled_rows = (float)sh;
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(coarse_depth);
-    cudaFree(fine_depth);
+    ctx->pool.dfree(coarse_depth);
+    ctx->pool.dfree(fine_depth);
     return ACMMP_OK;
 }
 
@@ -1104,7 +1187,7 @@ int acmmp_synchronize(acmmp_ctx *ctx)
     return collect_timings(ctx);
 }
 
-int acmmp_run_patch_match(acmmp_ctx *ctx)
+static int run_stage(acmmp_ctx *ctx, bool download)
 {
     int rc = do_init(ctx);
     if (rc) return rc;
@@ -1113,12 +1196,31 @@ int acmmp_run_patch_match(acmmp_ctx *ctx)
         if ((rc = do_pass(ctx, 1, i))) return rc;
     }
     if ((rc = do_finalize(ctx))) return rc;
-    const size_t npx = (size_t)ctx->W * ctx->H;
-    CK(cudaMemcpyAsync(ctx->planes_host, ctx->planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->costs_host, ctx->costs, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->have_result = false;
+    if (download) {
+        const size_t npx = (size_t)ctx->W * ctx->H;
+        CK(cudaMemcpyAsync(ctx->planes_host, ctx->planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->costs_host, ctx->costs, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     rc = collect_timings(ctx);
     if (rc) return rc;
     CK(cudaGetLastError());
+    ctx->have_result = download;
+    return ACMMP_OK;
+}
+
+int acmmp_run_patch_match(acmmp_ctx *ctx) { return ctx ? run_stage(ctx, true) : ACMMP_E_ARG; }
+
+int acmmp_run_patch_match_resident(acmmp_ctx *ctx) { return ctx ? run_stage(ctx, false) : ACMMP_E_ARG; }
+
+int acmmp_download_result(acmmp_ctx *ctx)
+{
+    if (!ctx || !ctx->planes) return ACMMP_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    CK(cudaMemcpyAsync(ctx->planes_host, ctx->planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->costs_host, ctx->costs, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_result = true;
     return ACMMP_OK;
 }

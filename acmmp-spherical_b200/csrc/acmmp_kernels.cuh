@@ -345,7 +345,10 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
 #ifndef ACMMP_PASS_MIN_CTAS
 #define ACMMP_PASS_MIN_CTAS 2
 #endif
-constexpr int kPassTW = 8, kPassTH = 8, kPassNT = 256, kPassPix = 32;
+#ifndef ACMMP_PASS_TH
+#define ACMMP_PASS_TH 8
+#endif
+constexpr int kPassTW = 8, kPassTH = ACMMP_PASS_TH, kPassPix = kPassTW * kPassTH / 2, kPassNT = 8 * kPassPix;
 constexpr int kPassTq = 5 * kTqPerHyp;      // tap-depth table entries per lane: up to 5 hypotheses x (9 taps + centre)
 
 // FindMinCostIndex / FindMaxCostIndex, ACMMP.cu:62-86 (ties -> last index)

@@ -125,44 +125,57 @@ def make_levels(rank, seed=2):
 
 
 class Exchange:
-    """NCCL all-gather of the per-rank depth maps between stages (north_star: the only collective)."""
+    """Depth-map exchange between the stages (north_star: the only collective).  With N ranks every rank
+    exports its view's depth map on the device, the maps are all-gathered over NCCL, and every source view that
+    is some rank's reference view reads that rank's fresh map straight from the gathered device buffer; the other
+    source views use the step's stand-in maps (inputs: copied host -> device inside the timed region)."""
 
     def __init__(self, world, rank, local_rank, ids):
         self.world, self.rank, self.ids = world, rank, ids
         self.bytes = 0
         self.ms = 0.0
+        self.h2d = 0
         if world > 1:
             import torch
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
             self.dev = torch.device("cuda", local_rank)
+            self.keep = []
 
-    def neighbour_depths(self, level, own_depth):
-        """Replace the stand-in maps of source views that are some rank's reference view by that rank's
-        freshly computed map."""
+    def neighbour_depths(self, li, level, backend):
         if self.world == 1:
-            return list(level.neighbour_depths)
+            return list(level.neighbour_depths), None
         torch, dist = self.torch, self.dist
+        H, W = level.images[0].shape
+        mine = torch.empty((H, W), dtype=torch.float32, device=self.dev)
+        backend.own_depth_to(mine.data_ptr())                      # device -> device, waits for the stage
+        gathered = torch.empty((self.world, H, W), dtype=torch.float32, device=self.dev)
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        mine = torch.from_numpy(np.array(own_depth, np.float32)).to(self.dev, non_blocking=False)
-        out = [torch.empty_like(mine) for _ in range(self.world)]
         t0.record()
-        dist.all_gather(out, mine)
+        dist.all_gather_into_tensor(gathered, mine)
         t1.record()
+        standins = []
+        ptrs = []
+        for k, vid in enumerate(self.ids[1:]):
+            d = level.neighbour_depths[k]
+            if vid < self.world and d.shape == (H, W):
+                ptrs.append((gathered[vid].data_ptr(), W, H))
+            else:
+                t = torch.from_numpy(d).to(self.dev, non_blocking=True)      # pinned host -> device
+                standins.append(t)
+                self.h2d += d.nbytes
+                ptrs.append((t.data_ptr(), d.shape[1], d.shape[0]))
         torch.cuda.synchronize()
         self.ms += t0.elapsed_time(t1)
         self.bytes += mine.numel() * 4 * (self.world - 1)
-        nd = list(level.neighbour_depths)
-        for k, vid in enumerate(self.ids[1:]):
-            if vid < self.world and out[vid].shape == mine.shape:
-                nd[k] = out[vid].cpu().numpy()
-        return nd
+        self.keep = [mine, gathered, standins]                     # alive until the next exchange
+        return None, ptrs
 
 
 def run_step(levels, backend, prior_cache, exch):
     """One reference view through the whole schedule, with the depth exchange before each geometric stage."""
     from acmmp_b200.pipeline import run_view
-    return run_view(levels, backend, prior_cache, neighbour_depths_fn=exch.neighbour_depths)
+    return run_view(levels, backend, prior_cache, exchange=exch)
 
 
 # ------------------------------------------------------------------------------------------
@@ -222,10 +235,15 @@ def main():
     exch = Exchange(world if use_dist else 1, rank, local_rank, ids)
     prior_cache = {}
 
+    ctx = None
+    if a.impl == "b200":
+        from acmmp_b200 import Context
+        ctx = Context(local_rank)        # one context (and its buffer pool) serves every view this rank processes
+
     def new_backend():
         if a.impl == "reference":
             return pipeline.ReferenceBackend(local_rank, seed=1234)
-        return pipeline.B200Backend(local_rank, seed=1234)
+        return pipeline.B200Backend(local_rank, seed=1234, ctx=ctx)
 
     def barrier():
         torch.cuda.synchronize()
@@ -241,7 +259,7 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    exch.ms, exch.bytes = 0.0, 0
+    exch.ms, exch.bytes, exch.h2d = 0.0, 0, 0
     barrier()
     t0 = time.perf_counter()
     tot = pipeline.StageTimes()
@@ -289,7 +307,7 @@ def main():
                        "neighbour_depths": "other ranks' maps via NCCL all-gather where available, else rendered stand-ins",
                        "cpu_prior_stage": "run once in warm-up, reused (out of scope, timed separately)"},
             "clocks": clocks,
-            "e2e": {"value": n_gpus / wall_step, "unit": UNIT, "h2d_bytes_per_step": tot.h2d_bytes // a.steps,
+            "e2e": {"value": n_gpus / wall_step, "unit": UNIT, "h2d_bytes_per_step": (tot.h2d_bytes + exch.h2d) // a.steps,
                     "d2h_bytes_per_step": tot.d2h_bytes // a.steps, "ms_per_step": wall_step * 1e3},
             "gpu_launches": tot.launches,
             "ms_per_checkerboard_pass": pass_ms,

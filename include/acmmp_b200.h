@@ -165,6 +165,12 @@ int acmmp_set_plane_now_semantics(acmmp_ctx *ctx, int as_compiled);
  * depth/normal extraction, two median passes, device->host copy of planes and costs.
  * Asynchronous on the context's stream up to the final copy, which it waits for. */
 int acmmp_run_patch_match(acmmp_ctx *ctx);
+/* The same stage without the device->host copy: the result stays on the device for the next stage of the
+ * GPU-resident chain (acmmp_set_depth_maps with maps[0] == NULL, acmmp_next_level, acmmp_export_depth_device).
+ * acmmp_download_result fetches it into the pinned host buffers when the host does need it (what
+ * RunPatchMatch's cudaMemcpy at ACMMP.cu:1553-1554 does unconditionally). */
+int acmmp_run_patch_match_resident(acmmp_ctx *ctx);
+int acmmp_download_result(acmmp_ctx *ctx);
 
 /* The same stages one launch at a time (what RunPatchMatch launches at ACMMP.cu:1534, :1538/:1540,
  * :1545-:1551).  colour 0 = black, 1 = red.  No host synchronisation. */
