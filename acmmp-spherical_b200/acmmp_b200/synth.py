@@ -278,12 +278,16 @@ def gt_planes(scene: Scene, view: int):
     return planes
 
 
-def write_dense_folder(scene: Scene, folder: str, jpeg_quality=95):
-    """cams/%08d_cam.txt, images/%08d.jpg, pair.txt in the formats the reference reads."""
+def write_dense_folder(scene: Scene, folder: str, jpeg_quality=95, pgm=False):
+    """cams/%08d_cam.txt, images/%08d.jpg, pair.txt in the formats the reference reads.
+    pgm=True also writes lossless images/%08d.pgm twins (the C++ host prefers them: identical pixels
+    for every decoder)."""
     os.makedirs(os.path.join(folder, "cams"), exist_ok=True)
     os.makedirs(os.path.join(folder, "images"), exist_ok=True)
     for i, (img, cam) in enumerate(zip(scene.images, scene.cams)):
         cv2.imwrite(os.path.join(folder, "images", "%08d.jpg" % i), img.astype(np.uint8), [cv2.IMWRITE_JPEG_QUALITY, jpeg_quality])
+        if pgm:
+            cv2.imwrite(os.path.join(folder, "images", "%08d.pgm" % i), img.astype(np.uint8))
         with open(os.path.join(folder, "cams", "%08d_cam.txt" % i), "w") as f:
             f.write("extrinsic\n")
             for r in range(3):

@@ -1,0 +1,324 @@
+// acmmp_host.cpp -- `class ACMMP` over the C ABI (see acmmp_host.h).  Which reference lines each method
+// replaces is cited per method; the reference is /root/reference (read-only), nothing is copied from it.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+#include "acmmp_host.h"
+
+namespace {
+
+std::string result_folder_of(const std::string &dense_folder, int ref_id)
+{
+    std::stringstream s;
+    s << dense_folder << "/ACMMP/2333_" << std::setw(8) << std::setfill('0') << ref_id;
+    return s.str();
+}
+
+} // namespace
+
+ACMMP::ACMMP(int device) : device_(device)
+{
+    acmmp_default_params(&params_);
+    const int rc = acmmp_create(&ctx_, device);
+    if (rc != ACMMP_OK) throw std::runtime_error("acmmp_create failed: no usable sm_100 CUDA device (there is no CPU fallback)");
+}
+
+ACMMP::~ACMMP()
+{
+    if (ctx_) acmmp_destroy(ctx_);
+}
+
+void ACMMP::check(int rc, const char *what)
+{
+    if (rc != ACMMP_OK) throw std::runtime_error(std::string(what) + ": " + acmmp_last_error(ctx_));
+}
+
+// reference ACMMP.cpp:548-565
+void ACMMP::SetGeomConsistencyParams(bool multi_geometry)
+{
+    params_.geom_consistency = 1;
+    params_.max_iterations = 2;
+    if (multi_geometry) params_.multi_geometry = 1;
+    check(acmmp_set_geom_consistency(ctx_, multi_geometry ? 1 : 0), "SetGeomConsistencyParams");
+}
+
+void ACMMP::SetHierarchyParams()
+{
+    params_.hierarchy = 1;
+    check(acmmp_set_hierarchy(ctx_), "SetHierarchyParams");
+}
+
+void ACMMP::SetPlanarPriorParams()
+{
+    params_.planar_prior = 1;
+    check(acmmp_set_planar_prior(ctx_), "SetPlanarPriorParams");
+}
+
+void ACMMP::SetSeed(uint64_t seed) { check(acmmp_set_seed(ctx_, seed), "SetSeed"); }
+
+// reference ACMMP.cpp:567-679: disk -> host.  Reference + source images as float grey levels, each scaled to its
+// own view's cur_image_size with bilinear resampling, intrinsics scaled with it; in geometric mode also the
+// depth maps of the reference and source views (depths.dmb, or depths_geom.dmb in the second geometric round).
+void ACMMP::InuputInitialization(const std::string &dense_folder, const std::vector<Problem> &problems, const int idx)
+{
+    images_.clear();
+    cameras_.clear();
+    const Problem &problem = problems[idx];
+    std::vector<int> ids;
+    ids.push_back(problem.ref_image_id);
+    ids.insert(ids.end(), problem.src_image_ids.begin(), problem.src_image_ids.end());
+    for (int id : ids) {
+        cv::Mat_<float> img;
+        if (!LoadGreyImage(dense_folder, id, img)) std::cerr << "Error: could not read image " << id << std::endl;
+        std::stringstream cam_path;
+        cam_path << dense_folder << "/cams/" << std::setw(8) << std::setfill('0') << id << "_cam.txt";
+        Camera cam = ReadCamera(cam_path.str());
+        cam.height = img.rows;
+        cam.width = img.cols;
+        images_.push_back(img);
+        cameras_.push_back(cam);
+    }
+    for (size_t i = 0; i < images_.size(); ++i) {
+        // note: the reference indexes the problem vector BY IMAGE ID here (ACMMP.cpp:609)
+        const int max_image_size = (i == 0) ? problems[idx].cur_image_size : problems[problem.src_image_ids[i - 1]].cur_image_size;
+        if (images_[i].cols <= max_image_size && images_[i].rows <= max_image_size) continue;
+        const float factor_x = static_cast<float>(max_image_size) / images_[i].cols;
+        const float factor_y = static_cast<float>(max_image_size) / images_[i].rows;
+        const float factor = std::min(factor_x, factor_y);
+        const int new_cols = (int)std::round(images_[i].cols * factor);
+        const int new_rows = (int)std::round(images_[i].rows * factor);
+        const float scale_x = new_cols / static_cast<float>(images_[i].cols);
+        const float scale_y = new_rows / static_cast<float>(images_[i].rows);
+        cv::Mat_<float> scaled;
+        ResizeLinear(images_[i], scaled, new_cols, new_rows);
+        images_[i] = scaled;
+        if (cameras_[i].model == SPHERE) {
+            cameras_[i].params[1] *= scale_x;
+            cameras_[i].params[2] *= scale_y;
+        } else {
+            cameras_[i].K[0] *= scale_x; cameras_[i].K[2] *= scale_x;
+            cameras_[i].K[4] *= scale_y; cameras_[i].K[5] *= scale_y;
+        }
+        cameras_[i].height = new_rows;
+        cameras_[i].width = new_cols;
+    }
+    params_.depth_min = cameras_[0].depth_min * 0.6f;
+    params_.depth_max = cameras_[0].depth_max * 1.2f;
+    params_.num_images = (int)images_.size();
+    std::cout << "depthe range: " << params_.depth_min << " " << params_.depth_max << std::endl;
+    std::cout << "num images: " << params_.num_images << std::endl;
+
+    if (params_.geom_consistency) {
+        depths_.clear();
+        const std::string suffix = params_.multi_geometry ? "/depths_geom.dmb" : "/depths.dmb";
+        for (int id : ids) {
+            cv::Mat_<float> d;
+            readDepthDmb(result_folder_of(dense_folder, id) + suffix, d);
+            depths_.push_back(d);
+        }
+    }
+}
+
+// reference ACMMP.cpp:681-845: host -> device, plus the reload of the previous stage's state from .dmb files
+void ACMMP::CudaSpaceInitialization(const std::string &dense_folder, const Problem &problem)
+{
+    const int n = (int)images_.size();
+    std::vector<const float *> ptrs(n);
+    std::vector<int32_t> ws(n), hs(n);
+    for (int i = 0; i < n; ++i) {
+        ptrs[i] = images_[i].ptr();
+        ws[i] = images_[i].cols;
+        hs[i] = images_[i].rows;
+    }
+    check(acmmp_set_views(ctx_, n, ptrs.data(), ws.data(), hs.data(), cameras_.data()), "CudaSpaceInitialization (views)");
+    const std::string folder = result_folder_of(dense_folder, problem.ref_image_id);
+    const int W = cameras_[0].width, H = cameras_[0].height;
+
+    if (params_.geom_consistency) {                          // ACMMP.cpp:726-785
+        std::vector<const float *> dp(n);
+        std::vector<int32_t> dw(n), dh(n);
+        for (int i = 0; i < n; ++i) {
+            dp[i] = depths_[i].ptr();
+            dw[i] = depths_[i].cols;
+            dh[i] = depths_[i].rows;
+        }
+        check(acmmp_set_depth_maps(ctx_, n, dp.data(), dw.data(), dh.data()), "CudaSpaceInitialization (depth maps)");
+        const std::string suffix = params_.multi_geometry ? "/depths_geom.dmb" : "/depths.dmb";
+        cv::Mat_<float> ref_depth, ref_cost;
+        cv::Mat_<cv::Vec3f> ref_normal;
+        readDepthDmb(folder + suffix, ref_depth);
+        readNormalDmb(folder + "/normals.dmb", ref_normal);
+        readDepthDmb(folder + "/costs.dmb", ref_cost);
+        if (ref_depth.rows != H || ref_depth.cols != W || ref_normal.rows != H || ref_cost.rows != H)
+            throw std::runtime_error("geometric stage: previous-stage .dmb files do not match the image size");
+        std::vector<float> planes((size_t)4 * W * H);
+        for (size_t i = 0; i < (size_t)W * H; ++i) {
+            const cv::Vec3f &nr = ref_normal.ptr()[i];
+            planes[4 * i + 0] = nr[0]; planes[4 * i + 1] = nr[1]; planes[4 * i + 2] = nr[2];
+            planes[4 * i + 3] = ref_depth.ptr()[i];
+        }
+        check(acmmp_set_planes(ctx_, planes.data(), ref_cost.ptr()), "CudaSpaceInitialization (planes)");
+    }
+    if (params_.hierarchy) {                                 // ACMMP.cpp:788-844
+        cv::Mat_<float> fine_depth, coarse_cost;
+        cv::Mat_<cv::Vec3f> coarse_normal;
+        readDepthDmb(folder + "/depths.dmb", fine_depth);             // JBU output, already at this level's size
+        readNormalDmb(folder + "/normals.dmb", coarse_normal);        // previous (coarser) level
+        readDepthDmb(folder + "/costs.dmb", coarse_cost);
+        const int sw = coarse_normal.cols, sh = coarse_normal.rows;
+        if (fine_depth.rows != H || fine_depth.cols != W) throw std::runtime_error("hierarchy stage: depths.dmb is not at this level's size");
+        const bool upsample = (sw != W || sh != H);
+        std::vector<float> coarse((size_t)4 * sw * sh);
+        for (size_t i = 0; i < (size_t)sw * sh; ++i) {
+            const cv::Vec3f &nr = coarse_normal.ptr()[i];
+            coarse[4 * i + 0] = nr[0]; coarse[4 * i + 1] = nr[1]; coarse[4 * i + 2] = nr[2];
+            coarse[4 * i + 3] = upsample ? coarse_cost.ptr()[i] : fine_depth.ptr()[i];     // ACMMP.cpp:823-828
+        }
+        check(acmmp_set_hierarchy_inputs(ctx_, coarse.data(), sw, sh, fine_depth.ptr()), "CudaSpaceInitialization (hierarchy)");
+    }
+}
+
+// reference ACMMP.cu:1506-1556
+void ACMMP::RunPatchMatch()
+{
+    check(acmmp_run_patch_match(ctx_), "RunPatchMatch");
+    check(acmmp_result_host(ctx_, &planes_host_, &costs_host_), "RunPatchMatch (result)");
+}
+
+void ACMMP::GetTimings(float out[8]) { check(acmmp_last_timings(ctx_, out), "GetTimings"); }
+
+int ACMMP::GetReferenceImageWidth() { return cameras_[0].width; }
+int ACMMP::GetReferenceImageHeight() { return cameras_[0].height; }
+cv::Mat_<float> ACMMP::GetReferenceImage() { return images_[0]; }
+float ACMMP::GetMinDepth() { return params_.depth_min; }
+float ACMMP::GetMaxDepth() { return params_.depth_max; }
+
+// reference ACMMP.cpp:884-892; index = row * width + col; (world normal xyz, depth w)
+float4 ACMMP::GetPlaneHypothesis(const int index)
+{
+    const float *p = planes_host_ + 4 * (size_t)index;
+    return make_float4(p[0], p[1], p[2], p[3]);
+}
+
+float ACMMP::GetCost(const int index) { return costs_host_[index]; }
+
+// reference ACMMP.cpp:904-930: per 5x5 cell the pixel of least cost, kept when that cost is below 0.1
+void ACMMP::GetSupportPoints(std::vector<cv::Point> &support2DPoints)
+{
+    support2DPoints.clear();
+    const int step = 5;
+    const int width = GetReferenceImageWidth(), height = GetReferenceImageHeight();
+    for (int col = 0; col < width; col += step) {
+        for (int row = 0; row < height; row += step) {
+            float best = 2.0f;
+            cv::Point where;
+            const int c_end = std::min(width, col + step), r_end = std::min(height, row + step);
+            for (int c = col; c < c_end; ++c) {
+                for (int r = row; r < r_end; ++r) {
+                    const float cst = costs_host_[(size_t)r * width + c];
+                    if (cst < 2.0f && best > cst) {
+                        where = cv::Point(c, r);
+                        best = cst;
+                    }
+                }
+            }
+            if (best < 0.1f) support2DPoints.push_back(where);
+        }
+    }
+}
+
+// reference ACMMP.cpp:932-954 (cv::Subdiv2D there)
+std::vector<Triangle> ACMMP::DelaunayTriangulation(const cv::Rect boundRC, const std::vector<cv::Point> &points)
+{
+    (void)boundRC;
+    std::vector<Triangle> results;
+    if (points.empty()) return results;
+    const std::vector<int> idx = DelaunayIndices(points);
+    results.reserve(idx.size() / 3);
+    for (size_t i = 0; i + 2 < idx.size(); i += 3) results.push_back(Triangle(points[idx[i]], points[idx[i + 1]], points[idx[i + 2]]));
+    return results;
+}
+
+// reference ACMMP.cpp:287-312 (the host twin of the device lifting: radial depth on the unit ray for SPHERE,
+// z-depth for PINHOLE)
+float3 Get3DPointonRefCam(const int x, const int y, const float depth, const Camera &camera)
+{
+    float3 X;
+    if (camera.model == SPHERE) {
+        const float lon = (static_cast<float>(x) - camera.params[1]) / static_cast<float>(camera.width) * 2.0f * (float)M_PI;
+        const float lat = -(static_cast<float>(y) - camera.params[2]) / static_cast<float>(camera.height) * (float)M_PI;
+        X.x = std::cos(lat) * std::sin(lon) * depth;
+        X.y = -std::sin(lat) * depth;
+        X.z = std::cos(lat) * std::cos(lon) * depth;
+    } else {
+        X.x = depth * (x - camera.K[2]) / camera.K[0];
+        X.y = depth * (y - camera.K[5]) / camera.K[4];
+        X.z = depth;
+    }
+    return X;
+}
+
+// reference ACMMP.cpp:956-989: the plane through the three lifted vertices.  The reference takes the null vector
+// of the 3x4 system [X 1] with cv::SVD::solveZ; the same 1-D null space in closed form: n = (X2-X1) x (X3-X1),
+// w = -n.X1, then normalised so that |n| = 1 and w >= 0.
+float4 ACMMP::GetPriorPlaneParams(const Triangle triangle, const cv::Mat_<float> &depths)
+{
+    const float3 a = Get3DPointonRefCam(triangle.pt1.x, triangle.pt1.y, depths(triangle.pt1.y, triangle.pt1.x), cameras_[0]);
+    const float3 b = Get3DPointonRefCam(triangle.pt2.x, triangle.pt2.y, depths(triangle.pt2.y, triangle.pt2.x), cameras_[0]);
+    const float3 c = Get3DPointonRefCam(triangle.pt3.x, triangle.pt3.y, depths(triangle.pt3.y, triangle.pt3.x), cameras_[0]);
+    const double ux = (double)b.x - a.x, uy = (double)b.y - a.y, uz = (double)b.z - a.z;
+    const double vx = (double)c.x - a.x, vy = (double)c.y - a.y, vz = (double)c.z - a.z;
+    double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    double w = -(nx * a.x + ny * a.y + nz * a.z);
+    double norm = std::sqrt(nx * nx + ny * ny + nz * nz);
+    if (w < 0) norm = -norm;
+    if (norm == 0.0) norm = 1.0;
+    return make_float4((float)(nx / norm), (float)(ny / norm), (float)(nz / norm), (float)(w / norm));
+}
+
+// reference ACMMP.cpp:991-1011
+float ACMMP::GetDepthFromPlaneParam(const float4 plane_hypothesis, const int x, const int y)
+{
+    const Camera &cam = cameras_[0];
+    if (cam.model == SPHERE) {
+        const float lon = (static_cast<float>(x) - cam.params[1]) / static_cast<float>(cam.width) * 2.0f * (float)M_PI;
+        const float lat = -(static_cast<float>(y) - cam.params[2]) / static_cast<float>(cam.height) * (float)M_PI;
+        const float dx = std::cos(lat) * std::sin(lon), dy = -std::sin(lat), dz = std::cos(lat) * std::cos(lon);
+        const float denom = plane_hypothesis.x * dx + plane_hypothesis.y * dy + plane_hypothesis.z * dz;
+        return (std::abs(denom) < 1e-6f) ? 1e6f : (-plane_hypothesis.w / denom);
+    }
+    return -plane_hypothesis.w * cam.K[0] /
+           ((x - cam.K[2]) * plane_hypothesis.x + (cam.K[0] / cam.K[4]) * (y - cam.K[5]) * plane_hypothesis.y + cam.K[0] * plane_hypothesis.z);
+}
+
+// reference ACMMP.cpp:847-867: masks(j, i) = 1-based triangle id as float (0 = none), PlaneParams[id - 1]
+void ACMMP::CudaPlanarPriorInitialization(const std::vector<float4> &PlaneParams, const cv::Mat_<float> &masks)
+{
+    static_assert(sizeof(float4) == 4 * sizeof(float), "float4 layout");
+    check(acmmp_set_planar_prior_inputs(ctx_, reinterpret_cast<const float *>(PlaneParams.data()), (int)PlaneParams.size(), masks.ptr()),
+          "CudaPlanarPriorInitialization");
+}
+
+// reference ACMMP.cpp:1071-1122
+void RunJBU(const cv::Mat_<float> &scaled_image_float, const cv::Mat_<float> &src_depthmap, const std::string &dense_folder,
+            const Problem &problem, int device)
+{
+    const int rows = scaled_image_float.rows, cols = scaled_image_float.cols;
+    const int Imagescale = std::max(rows / src_depthmap.rows, cols / src_depthmap.cols);
+    if (Imagescale == 1) {
+        std::cout << "Image.rows = Depthmap.rows" << std::endl;
+        return;
+    }
+    cv::Mat_<float> depthmap(rows, cols);
+    const int rc = acmmp_jbu(device, scaled_image_float.ptr(), cols, rows, src_depthmap.ptr(), src_depthmap.cols, src_depthmap.rows,
+                             depthmap.ptr());
+    if (rc != ACMMP_OK) throw std::runtime_error("acmmp_jbu failed");
+    for (size_t i = 0; i < depthmap.total(); ++i)
+        if (depthmap.ptr()[i] != depthmap.ptr()[i]) { std::cout << "wrong!" << std::endl; break; }     // the reference's NaN check
+    writeDepthDmb(result_folder_of(dense_folder, problem.ref_image_id) + "/depths.dmb", depthmap);
+}

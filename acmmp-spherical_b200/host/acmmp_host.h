@@ -1,0 +1,119 @@
+// acmmp_host.h -- C++ host side over the C ABI of libacmmp_b200.so.
+//
+// `class ACMMP` keeps the reference's host-class surface (reference ACMMP.h:57-81: same method names --
+// including the `Inuput` typo --, same argument meaning, same getters) so that the reference's pipeline
+// driver (main.cpp:73-238) compiles against it unchanged in spirit; acmmp_main.cpp is that driver.
+// Underneath, every device-side step is one call into include/acmmp_b200.h; there is no CPU fallback.
+//
+// Differences a caller can observe, all deliberate:
+//   * CUDA errors do not exit(): methods throw std::runtime_error with the library's message
+//     (the reference prints and exit(EXIT_FAILURE)s, ACMMP.cpp:64-97).
+//   * the cuRAND seed is explicit (SetSeed, default 0) instead of clock64() (ACMMP.cu:684).
+//   * images are read from images/%08d.jpg through nvJPEG (luma plane = what cv::imread(IMREAD_GRAYSCALE)
+//     returns up to the decoder's IDCT rounding), or from a lossless images/%08d.pgm twin when present.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <vector_types.h>      // float2, float3, float4 (CUDA toolkit headers, host-only use)
+#include <vector_functions.h>  // make_float4
+
+#ifdef ACMMP_HAVE_OPENCV
+#include <opencv2/core/core.hpp>
+#else
+#include "cvlite.h"
+#endif
+
+#include "../../include/acmmp_b200.h"
+
+// reference main.h:35-38, :40-54 -- the C ABI's acmmp_camera is byte-for-byte this struct
+enum CameraModel { PINHOLE = ACMMP_MODEL_PINHOLE, SPHERE = ACMMP_MODEL_SPHERE };
+typedef acmmp_camera Camera;
+typedef acmmp_params PatchMatchParams;
+
+// reference main.h:56-62
+struct Problem {
+    int ref_image_id = 0;
+    std::vector<int> src_image_ids;
+    int max_image_size = 3200;
+    int num_downscale = 0;
+    int cur_image_size = 3200;
+};
+
+// reference main.h:64-67
+struct Triangle {
+    cv::Point pt1, pt2, pt3;
+    Triangle(const cv::Point a, const cv::Point b, const cv::Point c) : pt1(a), pt2(b), pt3(c) {}
+};
+
+// ---- on-disk contract (reference ACMMP.cpp:146-209, :352-479, main.cpp:4-33) ---------------------------
+int readDepthDmb(const std::string file_path, cv::Mat_<float> &depth);
+int readNormalDmb(const std::string file_path, cv::Mat_<cv::Vec3f> &normal);
+int writeDepthDmb(const std::string file_path, const cv::Mat_<float> &depth);
+int writeNormalDmb(const std::string file_path, const cv::Mat_<cv::Vec3f> &normal);
+Camera ReadCamera(const std::string &cam_path);
+void GenerateSampleList(const std::string &dense_folder, std::vector<Problem> &problems);
+
+// ---- images ------------------------------------------------------------------------------------------------
+// Grey image of view `id` as float 0..255 (InuputInitialization, ACMMP.cpp:576-581).  Returns false when neither
+// images/%08d.pgm nor images/%08d.jpg can be read.
+bool LoadGreyImage(const std::string &dense_folder, int id, cv::Mat_<float> &image);
+// Only the size (ComputeMultiScaleSettings reads whole images just for that, main.cpp:46-50).
+bool ImageSize(const std::string &dense_folder, int id, int &cols, int &rows);
+// cv::resize(src, dst, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) on a float image
+void ResizeLinear(const cv::Mat_<float> &src, cv::Mat_<float> &dst, int new_cols, int new_rows);
+
+// ---- host twins of the camera math the CPU prior stage uses (ACMMP.cpp:287-312) -------------------------
+float3 Get3DPointonRefCam(const int x, const int y, const float depth, const Camera &camera);
+
+// Delaunay triangulation of integer points inside `bound` (stands in for cv::Subdiv2D, ACMMP.cpp:932-954):
+// exact integer predicates, incremental insertion with walking point location.  Returns vertex index triples.
+std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points);
+
+class ACMMP {
+public:
+    explicit ACMMP(int device = 0);      // the reference hard-codes device 0 (main.cpp:77)
+    ~ACMMP();
+    ACMMP(const ACMMP &) = delete;
+    ACMMP &operator=(const ACMMP &) = delete;
+
+    void InuputInitialization(const std::string &dense_folder, const std::vector<Problem> &problems, const int idx);
+    void CudaSpaceInitialization(const std::string &dense_folder, const Problem &problem);
+    void RunPatchMatch();
+    void SetGeomConsistencyParams(bool multi_geometry = false);
+    void SetPlanarPriorParams();
+    void SetHierarchyParams();
+    void SetSeed(uint64_t seed);
+
+    int GetReferenceImageWidth();
+    int GetReferenceImageHeight();
+    cv::Mat_<float> GetReferenceImage();
+    float4 GetPlaneHypothesis(const int index);
+    float GetCost(const int index);
+    void GetSupportPoints(std::vector<cv::Point> &support2DPoints);
+    std::vector<Triangle> DelaunayTriangulation(const cv::Rect boundRC, const std::vector<cv::Point> &points);
+    float4 GetPriorPlaneParams(const Triangle triangle, const cv::Mat_<float> &depths);
+    float GetDepthFromPlaneParam(const float4 plane_hypothesis, const int x, const int y);
+    float GetMinDepth();
+    float GetMaxDepth();
+    void CudaPlanarPriorInitialization(const std::vector<float4> &PlaneParams, const cv::Mat_<float> &masks);
+
+    // not in the reference: CUDA-event times of the last RunPatchMatch {init, passes, finalize, #passes, last pass}
+    void GetTimings(float out[8]);
+
+private:
+    void check(int rc, const char *what);
+    acmmp_ctx *ctx_ = nullptr;
+    int device_ = 0;
+    std::vector<cv::Mat_<float>> images_;
+    std::vector<cv::Mat_<float>> depths_;
+    std::vector<Camera> cameras_;
+    PatchMatchParams params_;
+    const float *planes_host_ = nullptr;      // pinned result buffers owned by the library
+    const float *costs_host_ = nullptr;
+};
+
+// RunJBU (ACMMP.cpp:1071-1122): joint-bilateral upsampling of depths_geom.dmb to the new level, written as depths.dmb
+void RunJBU(const cv::Mat_<float> &scaled_image_float, const cv::Mat_<float> &src_depthmap, const std::string &dense_folder,
+            const Problem &problem, int device = 0);

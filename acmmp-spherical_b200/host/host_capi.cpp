@@ -1,0 +1,87 @@
+// host_capi.cpp -- C entry points into the host-side helpers, for the CPU tests (ctypes); none touches the GPU.
+#include <cstring>
+#include "acmmp_host.h"
+
+extern "C" {
+
+int acmmp_host_read_camera(const char *path, acmmp_camera *out)
+{
+    if (!path || !out) return -1;
+    *out = ReadCamera(path);
+    return 0;
+}
+
+int acmmp_host_write_depth_dmb(const char *path, const float *data, int w, int h)
+{
+    cv::Mat_<float> m(h, w);
+    std::memcpy(m.ptr(), data, sizeof(float) * (size_t)w * h);
+    return writeDepthDmb(path, m);
+}
+
+int acmmp_host_read_depth_dmb(const char *path, float *data, int cap, int *w, int *h)
+{
+    cv::Mat_<float> m;
+    if (readDepthDmb(path, m)) return -1;
+    *w = m.cols; *h = m.rows;
+    if ((size_t)cap < m.total()) return -2;
+    std::memcpy(data, m.ptr(), sizeof(float) * m.total());
+    return 0;
+}
+
+int acmmp_host_write_normal_dmb(const char *path, const float *data, int w, int h)
+{
+    cv::Mat_<cv::Vec3f> m(h, w);
+    std::memcpy(static_cast<void *>(m.ptr()), data, sizeof(float) * 3 * (size_t)w * h);
+    return writeNormalDmb(path, m);
+}
+
+int acmmp_host_read_normal_dmb(const char *path, float *data, int cap, int *w, int *h)
+{
+    cv::Mat_<cv::Vec3f> m;
+    if (readNormalDmb(path, m)) return -1;
+    *w = m.cols; *h = m.rows;
+    if ((size_t)cap < 3 * m.total()) return -2;
+    std::memcpy(data, m.ptr(), sizeof(float) * 3 * m.total());
+    return 0;
+}
+
+int acmmp_host_resize_linear(const float *src, int w, int h, float *dst, int nw, int nh)
+{
+    cv::Mat_<float> s(h, w), d;
+    std::memcpy(s.ptr(), src, sizeof(float) * (size_t)w * h);
+    ResizeLinear(s, d, nw, nh);
+    std::memcpy(dst, d.ptr(), sizeof(float) * (size_t)nw * nh);
+    return 0;
+}
+
+// points: n x (x, y) int32; out: up to cap index triples; returns the number of triangles
+int acmmp_host_delaunay(const int32_t *points, int n, int32_t *out, int cap)
+{
+    std::vector<cv::Point> pts(n);
+    for (int i = 0; i < n; ++i) pts[i] = cv::Point(points[2 * i], points[2 * i + 1]);
+    const std::vector<int> idx = DelaunayIndices(pts);
+    const int nt = (int)(idx.size() / 3);
+    for (int i = 0; i < std::min(nt, cap) * 3; ++i) out[i] = idx[i];
+    return nt;
+}
+
+int acmmp_host_load_grey(const char *dense_folder, int id, float *dst, int cap, int *w, int *h)
+{
+    cv::Mat_<float> img;
+    if (!LoadGreyImage(dense_folder, id, img)) return -1;
+    *w = img.cols; *h = img.rows;
+    if ((size_t)cap < img.total()) return -2;
+    std::memcpy(dst, img.ptr(), sizeof(float) * img.total());
+    return 0;
+}
+
+int acmmp_host_pair_count(const char *dense_folder)
+{
+    std::vector<Problem> problems;
+    GenerateSampleList(dense_folder, problems);
+    int total = 0;
+    for (const auto &p : problems) total += 1000 + (int)p.src_image_ids.size();
+    return total;      // 1000 * views + kept source views
+}
+
+} // extern "C"

@@ -1,0 +1,154 @@
+"""CPU tests of the C++ host side (acmmp-spherical_b200/host): on-disk contract, image resampling,
+Delaunay stand-in.  No GPU work: the helpers are reached through the C hooks of libacmmp_host.so."""
+import ctypes as C
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HOST_LIB = ROOT / "acmmp-spherical_b200" / "lib" / "libacmmp_host.so"
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not HOST_LIB.exists():
+        pytest.fail(f"{HOST_LIB} is missing: run __graft_entry__.build()")
+    return C.CDLL(str(HOST_LIB))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def test_dmb_round_trip_and_layout(host, tmp_path):
+    """.dmb = int32 type(1), h, w, nb + float32 payload, row major (reference ACMMP.cpp:352-479)."""
+    rng = np.random.default_rng(0)
+    d = rng.uniform(1, 9, (7, 11)).astype(np.float32)
+    n = rng.standard_normal((7, 11, 3)).astype(np.float32)
+    pd, pn = str(tmp_path / "depths.dmb").encode(), str(tmp_path / "normals.dmb").encode()
+    assert host.acmmp_host_write_depth_dmb(pd, _fp(d), 11, 7) == 0
+    assert host.acmmp_host_write_normal_dmb(pn, _fp(n), 11, 7) == 0
+    raw = open(pd, "rb").read()
+    assert struct.unpack("<4i", raw[:16]) == (1, 7, 11, 1)
+    assert np.array_equal(np.frombuffer(raw[16:], np.float32).reshape(7, 11), d)
+    raw = open(pn, "rb").read()
+    assert struct.unpack("<4i", raw[:16]) == (1, 7, 11, 3)
+    assert np.array_equal(np.frombuffer(raw[16:], np.float32).reshape(7, 11, 3), n)
+    out = np.zeros((7, 11), np.float32)
+    w, h = C.c_int(), C.c_int()
+    assert host.acmmp_host_read_depth_dmb(pd, _fp(out), out.size, C.byref(w), C.byref(h)) == 0
+    assert (w.value, h.value) == (11, 7) and np.array_equal(out, d)
+    outn = np.zeros((7, 11, 3), np.float32)
+    assert host.acmmp_host_read_normal_dmb(pn, _fp(outn), outn.size, C.byref(w), C.byref(h)) == 0
+    assert np.array_equal(outn, n)
+    # a depth file is not a normal file
+    assert host.acmmp_host_read_normal_dmb(pd, _fp(outn), outn.size, C.byref(w), C.byref(h)) != 0
+    assert host.acmmp_host_read_depth_dmb(str(tmp_path / "missing.dmb").encode(), _fp(out), out.size, C.byref(w), C.byref(h)) != 0
+
+
+@pytest.mark.parametrize("model", ["pinhole", "sphere"])
+def test_camera_files_written_by_the_generator_parse_back(host, tmp_path, model):
+    """cams/%08d_cam.txt as the reference reads them (ACMMP.cpp:146-209), including the PINHOLE depth-line quirk."""
+    import acmmp_b200
+    from acmmp_b200 import synth
+    scene = (synth.make_pinhole_scene(n_views=3, width=64, height=48, focal=60.0, seed=1) if model == "pinhole"
+             else synth.make_sphere_scene(n_views=3, width=64, height=32, seed=4))
+    synth.write_dense_folder(scene, str(tmp_path), pgm=True)
+    for i, ref in enumerate(scene.cams):
+        cam = acmmp_b200.Camera()
+        assert host.acmmp_host_read_camera(str(tmp_path / "cams" / ("%08d_cam.txt" % i)).encode(), C.byref(cam)) == 0
+        assert cam.model == ref.model
+        np.testing.assert_allclose(list(cam.R), list(ref.R), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(list(cam.t), list(ref.t), rtol=1e-6, atol=1e-7)
+        if model == "pinhole":
+            np.testing.assert_allclose(list(cam.K), list(ref.K), rtol=1e-6)
+        else:
+            np.testing.assert_allclose(list(cam.params)[:3], list(ref.params)[:3], rtol=1e-6)
+        assert abs(cam.depth_min - ref.depth_min) <= 1e-5 * ref.depth_min
+        assert abs(cam.depth_max - ref.depth_max) <= 1e-5 * ref.depth_max
+    # pair.txt: every view listed with its kept sources
+    assert host.acmmp_host_pair_count(str(tmp_path).encode()) == sum(1000 + len(s) for _, s in scene.pairs)
+    # the lossless twin is what the loader returns
+    img = np.zeros(scene.images[0].shape, np.float32)
+    w, h = C.c_int(), C.c_int()
+    assert host.acmmp_host_load_grey(str(tmp_path).encode(), 0, _fp(img), img.size, C.byref(w), C.byref(h)) == 0
+    assert np.array_equal(img, scene.images[0].astype(np.uint8).astype(np.float32))
+
+
+@pytest.mark.parametrize("shape,new", [((96, 128), (48, 64)), ((97, 131), (41, 77)), ((50, 60), (50, 60)), ((64, 64), (23, 57))])
+def test_resize_matches_cv_inter_linear(host, shape, new):
+    """InuputInitialization resamples with cv::resize(..., INTER_LINEAR) (ACMMP.cpp:624); the C++ host restates it."""
+    import cv2
+    rng = np.random.default_rng(3)
+    src = rng.uniform(0, 255, shape).astype(np.float32)
+    dst = np.zeros(new, np.float32)
+    assert host.acmmp_host_resize_linear(_fp(src), shape[1], shape[0], _fp(dst), new[1], new[0]) == 0
+    ref = cv2.resize(src, (new[1], new[0]), interpolation=cv2.INTER_LINEAR)
+    assert np.abs(dst - ref).max() <= 2e-4 * 255
+
+
+def _circumcircle_empty(pts, tris):
+    """Delaunay property, exact in integers: no point strictly inside any triangle's circumcircle."""
+    P = pts.astype(object)
+    bad = 0
+    for a, b, c in tris[:: max(1, len(tris) // 150)]:
+        ax, ay = P[a]; bx, by = P[b]; cx, cy = P[c]
+        if (bx - ax) * (cy - ay) - (by - ay) * (cx - ax) < 0:
+            bx, by, cx, cy = cx, cy, bx, by
+        for d in range(len(P)):
+            if d in (a, b, c):
+                continue
+            dx, dy = P[d]
+            m = [[ax - dx, ay - dy], [bx - dx, by - dy], [cx - dx, cy - dy]]
+            r = [u * u + v * v for u, v in m]
+            det = (m[0][0] * (m[1][1] * r[2] - r[1] * m[2][1]) - m[0][1] * (m[1][0] * r[2] - r[1] * m[2][0])
+                   + r[0] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]))
+            bad += det > 0
+    return bad
+
+
+def test_delaunay_stand_in_is_a_delaunay_triangulation(host):
+    """DelaunayIndices replaces cv::Subdiv2D (ACMMP.cpp:932-954): same triangle count as scipy's Qhull on points in
+    general position and the empty-circumcircle property on near-grid support points (co-circular ties included)."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(5)
+    # (1) support-point-like input: one point per 5x5 cell, scan order col-major like GetSupportPoints
+    cells = [(cx, cy) for cx in range(40) for cy in range(30)]
+    pts = np.array([(5 * cx + rng.integers(0, 5), 5 * cy + rng.integers(0, 5)) for cx, cy in cells if rng.random() < 0.8], np.int32)
+    out = np.zeros((4 * len(pts), 3), np.int32)
+    nt = host.acmmp_host_delaunay(pts.ctypes.data_as(C.POINTER(C.c_int32)), len(pts), out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
+    tris = out[:nt]
+    assert nt > len(pts) and tris.min() >= 0 and tris.max() < len(pts)
+    assert _circumcircle_empty(pts, tris) == 0
+    # Qhull triangulates the convex hull completely; the big enclosing triangle may leave out a few thin hull triangles
+    ref = Delaunay(pts.astype(np.float64)).simplices
+    assert abs(nt - len(ref)) <= 0.02 * len(ref) + 8
+    def total_area(t):
+        u, v = (pts[t[:, 1]] - pts[t[:, 0]]).astype(np.float64), (pts[t[:, 2]] - pts[t[:, 0]]).astype(np.float64)
+        return 0.5 * np.abs(u[:, 0] * v[:, 1] - u[:, 1] * v[:, 0]).sum()
+    area, area_ref = total_area(tris), total_area(ref)
+    assert 0.99 * area_ref <= area <= area_ref * (1 + 1e-9)
+    # (2) exact grid (every quadruple co-circular) and duplicates must not break it
+    gx, gy = np.meshgrid(np.arange(0, 60, 5), np.arange(0, 40, 5))
+    grid = np.stack([gx.ravel(), gy.ravel()], 1).astype(np.int32)
+    grid = np.concatenate([grid, grid[:7]])
+    out = np.zeros((4 * len(grid), 3), np.int32)
+    nt = host.acmmp_host_delaunay(grid.ctypes.data_as(C.POINTER(C.c_int32)), len(grid), out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
+    assert nt == 2 * 11 * 7
+    assert _circumcircle_empty(grid, out[:nt]) == 0
+
+
+def test_delaunay_scales_to_full_resolution_point_counts(host):
+    """~270 k support points at 3200x2130: the walk-located insertion must stay near-linear."""
+    import time
+    rng = np.random.default_rng(9)
+    cx, cy = np.meshgrid(np.arange(640), np.arange(426), indexing="ij")
+    pts = np.stack([5 * cx.ravel() + rng.integers(0, 5, cx.size), 5 * cy.ravel() + rng.integers(0, 5, cx.size)], 1).astype(np.int32)
+    out = np.zeros((2 * len(pts) + 16, 3), np.int32)
+    t0 = time.perf_counter()
+    nt = host.acmmp_host_delaunay(pts.ctypes.data_as(C.POINTER(C.c_int32)), len(pts), out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
+    dt = time.perf_counter() - t0
+    assert 1.9 * len(pts) < nt < 2.0 * len(pts)
+    assert dt < 20.0, f"{dt:.1f} s for {len(pts)} points"

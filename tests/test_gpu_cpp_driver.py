@@ -1,0 +1,53 @@
+"""GPU test of the C++ host side: the `acmmp_b200` driver (reference: ./ACMMP dense_folder, main.cpp:392-482) on a
+synthetic dense folder, through the reference's own on-disk contract."""
+import json
+import struct
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import util
+
+ROOT = Path(__file__).resolve().parent.parent
+DRIVER = ROOT / "acmmp-spherical_b200" / "lib" / "acmmp_b200"
+
+
+def _read_dmb(path):
+    raw = open(path, "rb").read()
+    t, h, w, nb = struct.unpack("<4i", raw[:16])
+    assert t == 1
+    a = np.frombuffer(raw[16:], np.float32)
+    return a.reshape(h, w) if nb == 1 else a.reshape(h, w, nb)
+
+
+@pytest.mark.gpu
+def test_cpp_driver_runs_the_reference_schedule_on_a_dense_folder(tmp_path):
+    from acmmp_b200 import synth
+    assert DRIVER.exists(), "build the host side first (__graft_entry__.build())"
+    # 1100 px -> two pyramid levels (550 and 1100): JBU + hierarchy + prior + 2 geometric rounds per level
+    scene = synth.make_pinhole_scene(n_views=4, width=1100, height=820, focal=950.0, seed=3)
+    synth.write_dense_folder(scene, str(tmp_path), pgm=True)
+    r = subprocess.run([str(DRIVER), str(tmp_path), "--seed", "7"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    assert summary["views"] == 4 and summary["kernel_ms"] > 0
+    res = {}
+    for v in range(4):
+        folder = tmp_path / "ACMMP" / ("2333_%08d" % v)
+        for name in ("depths.dmb", "depths_geom.dmb", "normals.dmb", "costs.dmb"):
+            assert (folder / name).exists(), name
+        depth = _read_dmb(folder / "depths_geom.dmb")
+        normals = _read_dmb(folder / "normals.dmb")
+        costs = _read_dmb(folder / "costs.dmb")
+        gt = scene.depths_gt[v]
+        assert depth.shape == gt.shape and normals.shape == gt.shape + (3,) and costs.shape == gt.shape
+        ok = np.abs(depth - gt) / gt <= 0.01
+        res[f"view{v}_within_1pct_of_gt"] = float(ok[8:-8, 8:-8].mean())
+        res[f"view{v}_unit_normals"] = float((np.abs(np.linalg.norm(normals, axis=-1) - 1) < 1e-3).mean())
+    res.update(summary)
+    util.dump("cpp_driver", res)
+    for v in range(4):
+        assert res[f"view{v}_within_1pct_of_gt"] > 0.85, res
+        assert res[f"view{v}_unit_normals"] > 0.99, res
