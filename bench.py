@@ -145,29 +145,32 @@ class Exchange:
     def neighbour_depths(self, li, level, backend):
         if self.world == 1:
             return list(level.neighbour_depths), None
+        from acmmp_b200 import shard
         torch, dist = self.torch, self.dist
+        if not hasattr(self, "ex"):
+            self.ex = shard.DepthExchange(dist, self.world)
         H, W = level.images[0].shape
         mine = torch.empty((H, W), dtype=torch.float32, device=self.dev)
         backend.own_depth_to(mine.data_ptr())                      # device -> device, waits for the stage
-        gathered = torch.empty((self.world, H, W), dtype=torch.float32, device=self.dev)
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        dist.all_gather_into_tensor(gathered, mine)
+        gathered = self.ex.all_gather(mine)                        # NCCL over NVLink: the path's only collective
         t1.record()
-        standins = []
-        ptrs = []
-        for k, vid in enumerate(self.ids[1:]):
+        # rank r owns reference view r (one view per rank per step): round 0 of the plan
+        plan = shard.neighbour_sources(self.ids[1:], 0, self.world)
+        standins, ptrs = [], []
+        for k, (kind, who) in enumerate(plan):
             d = level.neighbour_depths[k]
-            if vid < self.world and d.shape == (H, W):
-                ptrs.append((gathered[vid].data_ptr(), W, H))
+            if kind == "gathered" and d.shape == (H, W):
+                ptrs.append((gathered[who].data_ptr(), W, H))
             else:
-                t = torch.from_numpy(d).to(self.dev, non_blocking=True)      # pinned host -> device
+                t = torch.from_numpy(d).to(self.dev, non_blocking=True)      # pinned host -> device (step input)
                 standins.append(t)
                 self.h2d += d.nbytes
                 ptrs.append((t.data_ptr(), d.shape[1], d.shape[0]))
         torch.cuda.synchronize()
         self.ms += t0.elapsed_time(t1)
-        self.bytes += mine.numel() * 4 * (self.world - 1)
+        self.bytes = self.ex.bytes
         self.keep = [mine, gathered, standins]                     # alive until the next exchange
         return None, ptrs
 
@@ -260,6 +263,8 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     exch.ms, exch.bytes, exch.h2d = 0.0, 0, 0
+    if hasattr(exch, "ex"):
+        exch.ex.bytes = 0
     barrier()
     t0 = time.perf_counter()
     tot = pipeline.StageTimes()
