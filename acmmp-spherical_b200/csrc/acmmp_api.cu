@@ -519,7 +519,8 @@ int configure_kernels(acmmp_ctx *ctx)
         const int big = 200 * 1024;
         cudaError_t e;
 #define SETATTR(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) result = e;
-        SETATTR(k_pass<kModelPinhole>) SETATTR(k_pass<kModelSphere>)
+        SETATTR((k_pass<kModelPinhole, kModePhoto>)) SETATTR((k_pass<kModelPinhole, kModePrior>)) SETATTR((k_pass<kModelPinhole, kModeGeom>))
+        SETATTR((k_pass<kModelSphere, kModePhoto>)) SETATTR((k_pass<kModelSphere, kModePrior>)) SETATTR((k_pass<kModelSphere, kModeGeom>))
         SETATTR(k_random_init<kModelPinhole>) SETATTR(k_random_init<kModelSphere>)
         SETATTR(k_probe<kModelPinhole>) SETATTR(k_probe<kModelSphere>)
 #undef SETATTR
@@ -769,7 +770,13 @@ int launch_pass(acmmp_ctx *ctx, int colour, int iter)
 {
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + kPassTW - 1) / kPassTW, (ctx->H + kPassTH - 1) / kPassTH);
-    k_pass<MODEL><<<grid, kPassNT, smem_pass<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
+    // the reference's flag combinations are exclusive per stage; should a caller set both, geometric wins for the
+    // cost terms and the prior term is dropped -- refuse instead
+    if (fc.geom && fc.prior) return fail(ctx, ACMMP_E_UNSUPPORTED, "geom_consistency and planar_prior in the same stage are not supported");
+    const size_t smem = smem_pass<MODEL>(fc.nsrc);
+    if (fc.geom) k_pass<MODEL, kModeGeom><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
+    else if (fc.prior) k_pass<MODEL, kModePrior><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
+    else k_pass<MODEL, kModePhoto><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
     ctx->launches++;
     CK(cudaGetLastError());
     std::swap(ctx->planes, ctx->planes_alt);

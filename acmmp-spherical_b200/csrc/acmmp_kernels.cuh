@@ -383,13 +383,19 @@ __device__ __forceinline__ float4 shfl_plane(const unsigned gmask, const float4 
     return r;
 }
 
-template <int MODEL>
+// MODE: which stage variant this instance serves -- the reference's flag combinations are exclusive
+// (main.cpp:427-473: prior stages have geom_consistency off, geometric stages have planar_prior off), and a
+// specialised instance carries only its own code (the instruction cache is a measured bottleneck of this kernel).
+constexpr int kModePhoto = 0, kModePrior = 1, kModeGeom = 2;
+
+template <int MODEL, int MODE>
 __global__ void __launch_bounds__(kPassNT, ACMMP_PASS_MIN_CTAS)
 k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap,
        const int colour, const int iter)
 {
     typedef TileGeom<kPassTW, kPassTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
+    constexpr bool kPrior = (MODE == kModePrior), kGeom = (MODE == kModeGeom);
     constexpr int WRS = kPassPix;
     constexpr int TQS = kPassNT;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -591,7 +597,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             cum_prob += prob;
             probs[i] = cum_prob;
         }
-#pragma unroll
+#pragma unroll 1
         for (int sample = 0; sample < 15; ++sample) tq[sample * TQS] = rng_uniform(rs) - FLT_EPSILON;     // ACMMP.cu:1188
     }
     __syncwarp(FULL);
@@ -628,7 +634,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     for (int j = 0; j < nsrc; ++j) {
         const float wj = vw[j];
         if (wj > 0) {
-            if (fc.geom) {
+            if (kGeom) {
                 if (flag) {
                     final_cost += wj * (costrow[j] + 0.2f * geom_cost<MODEL>(fc, s_vc[j], px, cand));
                 } else {
@@ -670,7 +676,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             quad_ncc<MODEL, 1, TG::RW, WRS, TQS>(
                 c, px, aux, wr, rr, tq, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
                 [&](const int, float cst) {
-                    if (fc.geom) cst += 0.2f * geom_cost<MODEL>(fc, s_vc[vsel], px, cur_plane);
+                    if (kGeom) cst += 0.2f * geom_cost<MODEL>(fc, s_vc[vsel], px, cur_plane);
                     row_now[vsel] = vw[vsel] * cst;
                 });
         }
@@ -692,34 +698,39 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     bool have_plane_now = false;                         // as-compiled semantics, see below
     float4 plane_intended = cur_plane;                   // "the plane the pixel currently holds"
 
-    const uint32_t mask_c = fc.prior ? fc.plane_masks[center] : 0u;
+    const uint32_t mask_c = kPrior ? fc.plane_masks[center] : 0u;
     float4 prior_plane = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (fc.prior && mask_c > 0) prior_plane = fc.prior_planes[center];
+    if (kPrior && mask_c > 0) prior_plane = fc.prior_planes[center];
     const float depth_sigma = (fc.depth_max - fc.depth_min) / 64.0f;
     const float two_depth_sigma_squared = 2 * depth_sigma * depth_sigma;
     const float beta = 0.18f;
     const float gamma = 0.5f;
+    const float angle_sigma_r = CUDART_PI_F * (5.0f / 180.0f);
+    const float two_angle_sigma_squared_r = 2 * angle_sigma_r * angle_sigma_r;
 
-    if (fc.prior) {                                      // ACMMP.cu:1247-1299
-        if (mask_c > 0) {
-            const float angle_sigma = (float)(3.14159265358979323846 * (double)(5.0f / 180.0f));
-            const float two_angle_sigma_squared = 2 * angle_sigma * angle_sigma;
-            const float depth_prior = plane_depth(prior_plane, px.dir);
-            float restricted = 0.0f;
-            if (flag) {
-                const float depth_c = plane_depth(cand, px.dir);
-                const float depth_diff = depth_c - depth_prior;
-                const float angle_cos = dot3(prior_plane, cand);
-                const float angle_diff = acosf(angle_cos);
-                const float prior = gamma + expf(-depth_diff * depth_diff / two_depth_sigma_squared) *
-                                                expf(-angle_diff * angle_diff / two_angle_sigma_squared);
-                restricted = expf(-final_cost * final_cost / beta) * prior;
-            }
-            float restricted_final_costs[8];
+    // All shuffles below run with the full-warp mask outside divergent code: a shuffle under a group mask costs
+    // a convergence barrier sequence each.  Values a group does not need are computed and dropped.
+    const float4 nb_min = shfl_plane(FULL, cand, gbase + min_cost_idx);
+    if (kPrior) {                                        // ACMMP.cu:1247-1299
+        const float angle_sigma = (float)(3.14159265358979323846 * (double)(5.0f / 180.0f));
+        const float two_angle_sigma_squared = 2 * angle_sigma * angle_sigma;
+        const float depth_prior = plane_depth(prior_plane, px.dir);
+        float restricted = 0.0f;
+        if (flag && mask_c > 0) {
+            const float depth_c = plane_depth(cand, px.dir);
+            const float depth_diff = depth_c - depth_prior;
+            const float angle_cos = dot3(prior_plane, cand);
+            const float angle_diff = acosf(angle_cos);
+            const float prior = gamma + expf(-depth_diff * depth_diff / two_depth_sigma_squared) *
+                                            expf(-angle_diff * angle_diff / two_angle_sigma_squared);
+            restricted = expf(-final_cost * final_cost / beta) * prior;
+        }
+        float restricted_final_costs[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) restricted_final_costs[k] = __shfl_sync(gmask, restricted, gbase + k);
-            const int max_cost_idx = find_max_idx(restricted_final_costs);
-
+        for (int k = 0; k < 8; ++k) restricted_final_costs[k] = __shfl_sync(FULL, restricted, gbase + k);
+        const int max_cost_idx = find_max_idx(restricted_final_costs);
+        const float4 nb_max = shfl_plane(FULL, cand, gbase + max_cost_idx);
+        if (mask_c > 0) {
             float restricted_cost_now;
             {
                 const float depth_diff = depth_now - depth_prior;
@@ -729,50 +740,43 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
                                                 expf(-angle_diff * angle_diff / two_angle_sigma_squared);
                 restricted_cost_now = expf(-cost_now * cost_now / beta) * prior;
             }
-            const float4 nb = shfl_plane(gmask, cand, gbase + max_cost_idx);
             if ((flagbits >> max_cost_idx) & 1u) {
-                plane_now = nb;
+                plane_now = nb_max;
                 have_plane_now = true;
-                const float depth_before = plane_depth(nb, px.dir);
+                const float depth_before = plane_depth(nb_max, px.dir);
                 if (depth_before >= fc.depth_min && depth_before <= fc.depth_max &&
                     restricted_final_costs[max_cost_idx] > restricted_cost_now) {
                     // note: the reference updates a SHADOWING depth_now here (ACMMP.cu:1271, :1282)
-                    plane_center = nb;
-                    plane_intended = nb;
+                    plane_center = nb_max;
+                    plane_intended = nb_max;
                     cost_center = final_costs[max_cost_idx];
                     restricted_cost = restricted_final_costs[max_cost_idx];
                     sel_center = temp_selected_views;
                     sel_dirty = true;
                 }
             }
-        } else {
-            const float4 nb = shfl_plane(gmask, cand, gbase + min_cost_idx);
-            if ((flagbits >> min_cost_idx) & 1u) {
-                plane_now = nb;
-                have_plane_now = true;
-                const float depth_before = plane_depth(nb, px.dir);
-                if (depth_before >= fc.depth_min && depth_before <= fc.depth_max && final_costs[min_cost_idx] < cost_now) {
-                    depth_now = depth_before;
-                    plane_center = nb;
-                    plane_intended = nb;
-                    cost_center = final_costs[min_cost_idx];
-                }
+        } else if ((flagbits >> min_cost_idx) & 1u) {
+            plane_now = nb_min;
+            have_plane_now = true;
+            const float depth_before = plane_depth(nb_min, px.dir);
+            if (depth_before >= fc.depth_min && depth_before <= fc.depth_max && final_costs[min_cost_idx] < cost_now) {
+                depth_now = depth_before;
+                plane_center = nb_min;
+                plane_intended = nb_min;
+                cost_center = final_costs[min_cost_idx];
             }
         }
-    } else {                                             // ACMMP.cu:1301-1311
-        const float4 nb = shfl_plane(gmask, cand, gbase + min_cost_idx);
-        if ((flagbits >> min_cost_idx) & 1u) {
-            const float depth_before = plane_depth(nb, px.dir);
-            const bool accept = depth_before >= fc.depth_min && depth_before <= fc.depth_max && final_costs[min_cost_idx] < cost_now;
-            plane_now = nb;
-            have_plane_now = true;
-            if (accept) {
-                depth_now = depth_before;
-                cost_now = final_costs[min_cost_idx];
-                sel_center = temp_selected_views;
-                sel_dirty = true;
-                plane_intended = nb;      // registers only: memory keeps the old plane (ACMMP.cu:1307)
-            }
+    } else if ((flagbits >> min_cost_idx) & 1u) {        // ACMMP.cu:1301-1311
+        const float depth_before = plane_depth(nb_min, px.dir);
+        const bool accept = depth_before >= fc.depth_min && depth_before <= fc.depth_max && final_costs[min_cost_idx] < cost_now;
+        plane_now = nb_min;
+        have_plane_now = true;
+        if (accept) {
+            depth_now = depth_before;
+            cost_now = final_costs[min_cost_idx];
+            sel_center = temp_selected_views;
+            sel_dirty = true;
+            plane_intended = nb_min;      // registers only: memory keeps the old plane (ACMMP.cu:1307)
         }
     }
     // `float4 plane_hypotheses_now;` is uninitialised in the reference (ACMMP.cu:1301).  The nvcc
@@ -783,21 +787,17 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
 
     // ---- PlaneHypothesisRefinement, ACMMP.cu:797-936 -----------------------------------------
     const bool do_refine = weight_norm > 0.0f;      // group-uniform
+    const bool use_prior = kPrior && do_refine && mask_c > 0;
     float cdepth = depth_now;
     float4 temp_plane = plane_now;
-    bool use_prior = false;
     float depth_prior = 0.f;
-    const float angle_sigma_r = CUDART_PI_F * (5.0f / 180.0f);
-    const float two_angle_sigma_squared_r = 2 * angle_sigma_r * angle_sigma_r;
-    if (do_refine) {
+    {
         const float perturbation = 0.02f;
         const float angle_sigma = angle_sigma_r;
-        use_prior = fc.prior && mask_c > 0;
         if (use_prior) depth_prior = plane_depth(prior_plane, px.dir);
-
         float depth_rand = 0.f, depth_perturbed = 0.f;
         float4 n_rand = make_float4(0.f, 0.f, 0.f, 0.f), n_pert = n_rand;
-        if (gl == 0) {
+        if (do_refine && gl == 0) {
             if (use_prior) {
                 depth_rand = sample_depth_inv(rs, fmaxf(depth_prior - 3 * depth_sigma, fc.depth_min),
                                               fminf(depth_prior + 3 * depth_sigma, fc.depth_max));
@@ -811,6 +811,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             if (!(hi > lo)) { lo = fc.depth_min; hi = fc.depth_max; }
             depth_perturbed = depth_now;
             bool ok = false;
+#pragma unroll 1
             for (int k = 0; k < 32; ++k) {
                 const float cnd = sample_depth_inv(rs, lo, hi);
                 if (cnd >= fc.depth_min && cnd <= fc.depth_max) {
@@ -822,17 +823,19 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             if (!ok) depth_perturbed = fminf(fmaxf(depth_now, fc.depth_min), fc.depth_max);
             n_pert = perturbed_normal(rs, px.dir, plane_now, perturbation * CUDART_PI_F);
         }
-        depth_rand = __shfl_sync(gmask, depth_rand, gbase);
-        depth_perturbed = __shfl_sync(gmask, depth_perturbed, gbase);
-        n_rand = shfl_plane(gmask, n_rand, gbase);
-        n_pert = shfl_plane(gmask, n_pert, gbase);
-
-        // candidate gl (0..4): depths {rand, now, rand, now, pert}, normals {now, rand, rand, pert, now}
-        if (gl == 0 || gl == 2) cdepth = depth_rand;
-        if (gl == 4) cdepth = depth_perturbed;
-        if (gl == 1 || gl == 2) temp_plane = n_rand;
-        if (gl == 3) temp_plane = n_pert;
-        temp_plane.w = plane_offset(temp_plane, px.dir, cdepth);
+        __syncwarp(FULL);
+        depth_rand = __shfl_sync(FULL, depth_rand, gbase);
+        depth_perturbed = __shfl_sync(FULL, depth_perturbed, gbase);
+        n_rand = shfl_plane(FULL, n_rand, gbase);
+        n_pert = shfl_plane(FULL, n_pert, gbase);
+        if (do_refine) {
+            // candidate gl (0..4): depths {rand, now, rand, now, pert}, normals {now, rand, rand, pert, now}
+            if (gl == 0 || gl == 2) cdepth = depth_rand;
+            if (gl == 4) cdepth = depth_perturbed;
+            if (gl == 1 || gl == 2) temp_plane = n_rand;
+            if (gl == 3) temp_plane = n_pert;
+            temp_plane.w = plane_offset(temp_plane, px.dir, cdepth);
+        }
     }
     __syncwarp(FULL);
     // The 5 refinement hypotheses are evaluated view by view, only for the selected views (the reference
@@ -867,19 +870,19 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
                 c, px, aux, wr, rr, tq, fetch, q, want ? 0x1Fu : 0u,
                 [&](const int h) { return (h < 3 ? h : h - 3) * kTqPerHyp * TQS + ((h < 3 ? 0 : 1) - Q) * 4; },
                 [&](const int h, float cst) {
-                    if (fc.geom) cst += 0.1f * geom_cost<MODEL>(fc, s_vc[vsel], px, h == 4 ? hp_4 : hp_q);
+                    if (kGeom) cst += 0.1f * geom_cost<MODEL>(fc, s_vc[vsel], px, h == 4 ? hp_4 : hp_q);
                     cost_grp[h * nvp + vsel] = cst;
                 });
         }
         __syncwarp(FULL);
     }
-    if (do_refine) {
+    {
         const float two_angle_sigma_squared = two_angle_sigma_squared_r;
         float temp_cost = 0.0f;
         float depth_before = 0.f;
         bool cand_ok = false;
         float restricted_temp_cost = 0.f;
-        if (gl < 5) {
+        if (do_refine && gl < 5) {
             for (int j = 0; j < nsrc; ++j) {
                 const float wj = vw[j];
                 if (wj > 0.0f) temp_cost += wj * costrow[j];
@@ -901,9 +904,9 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         int best = -1;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const float tc_i = __shfl_sync(gmask, temp_cost, gbase + i);
-            const float rc_i = __shfl_sync(gmask, restricted_temp_cost, gbase + i);
-            const int ok_i = __shfl_sync(gmask, (int)cand_ok, gbase + i);
+            const float tc_i = __shfl_sync(FULL, temp_cost, gbase + i);
+            const float rc_i = kPrior ? __shfl_sync(FULL, restricted_temp_cost, gbase + i) : 0.f;
+            const int ok_i = __shfl_sync(FULL, (int)cand_ok, gbase + i);
             if (ok_i) {
                 if (use_prior) {
                     if (rc_i > restricted_cost) { restricted_cost = rc_i; cost_now = tc_i; best = i; }
@@ -913,8 +916,8 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             }
         }
         const int src = gbase + (best < 0 ? 0 : best);
-        const float4 bp = shfl_plane(gmask, temp_plane, src);
-        const float bd = __shfl_sync(gmask, depth_before, src);
+        const float4 bp = shfl_plane(FULL, temp_plane, src);
+        const float bd = __shfl_sync(FULL, depth_before, src);
         if (best >= 0) {
             plane_now = bp;
             depth_now = bd;
