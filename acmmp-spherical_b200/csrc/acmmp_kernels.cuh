@@ -9,8 +9,8 @@
 //   k_jbu             : JBU_cu                                             (ACMMP.cu:1558-1616)
 //   k_pad_reference, k_rng_fill, k_export_depth : data-layout helpers
 //
-// Work decomposition of k_pass (the kernel that is >95 % of the time): a CTA owns an 8x8 pixel
-// tile = 32 pixels of the active colour; each pixel is served by a GROUP OF 8 LANES (4 pixels per
+// Work decomposition of k_pass (the kernel that is >95 % of the time): a CTA owns an 8x16 pixel
+// tile = 64 pixels of the active colour; each pixel is served by a GROUP OF 8 LANES (4 pixels per
 // warp).  Lane l evaluates candidate direction l of the adaptive checkerboard (8 neighbour
 // hypotheses in parallel, argmin by warp shuffles); the current plane's cost and the five refinement
 // hypotheses are evaluated as (hypothesis, selected view) pairs dealt out to the 8 lanes.  The
@@ -342,11 +342,15 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
 // ------------------------------------------------------------------------------------------
 // checkerboard pass
 // ------------------------------------------------------------------------------------------
+// Measured on B200 (C2, 6 photometric passes): 8x4 tiles / 128 threads x 4 CTAs 212 ms, 8x6 / 192 x 3 205 ms,
+// 8x8 / 256 x 2 176 ms, 8x16 / 512 x 1 168 ms -- larger tiles keep the warps of an SM on one image region
+// (texture L1 reuse) and in the same code region (instruction cache); register-capped variants with more
+// resident warps (96 / 80 registers) lose to their spills.
 #ifndef ACMMP_PASS_MIN_CTAS
-#define ACMMP_PASS_MIN_CTAS 2
+#define ACMMP_PASS_MIN_CTAS 1
 #endif
 #ifndef ACMMP_PASS_TH
-#define ACMMP_PASS_TH 8
+#define ACMMP_PASS_TH 16
 #endif
 constexpr int kPassTW = 8, kPassTH = ACMMP_PASS_TH, kPassPix = kPassTW * kPassTH / 2, kPassNT = 8 * kPassPix;
 constexpr int kPassTq = 5 * kTqPerHyp;      // tap-depth table entries per lane: up to 5 hypotheses x (9 taps + centre)

@@ -10,9 +10,10 @@ geometric consistency x 2) = 30 checkerboard iterations + 12 initialisations + 2
 
   value  : depth maps / s with inputs resident: (views per step over all ranks) / (sum of the
            CUDA-event times of every kernel of the step, max over ranks)
-  e2e    : the same metric through the host-buffer C ABI (H2D of images / neighbour depth maps /
-           stage hand-over state and D2H of every stage result inside the timed region), wall clock
-           bracketed by barrier + synchronize, max over ranks
+  e2e    : the same metric through the host-buffer C ABI, wall clock bracketed by barrier + synchronize, max over
+           ranks.  Inside the timed region: H2D (pinned) of every level's images, of the prior and of the stand-in
+           neighbour depth maps; D2H of the photometric result of every level (input of the CPU prior stage) and of
+           the view's final result; the stages in between hand their state over on the device
   N > 1  : one process per GPU (torchrun), rank r owns reference view r of a 16-view scene (weak
            scaling); after the prior stage and after the first geometric stage the ranks all-gather
            their depth maps over NCCL and use them as neighbour depth maps wherever a source view is
