@@ -635,18 +635,12 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
 
     // ---- weighted neighbour costs and arg-min over the 8 lanes (ACMMP.cu:1210-1230) ----------
     float final_cost = 0.0f;
-    for (int j = 0; j < nsrc; ++j) {
-        const float wj = vw[j];
-        if (wj > 0) {
-            if (kGeom) {
-                if (flag) {
-                    final_cost += wj * (costrow[j] + 0.2f * geom_cost<MODEL>(fc, s_vc[j], px, cand));
-                } else {
-                    final_cost += wj * (costrow[j] + 0.1f * 3.0f);
-                }
-            } else {
-                final_cost += wj * costrow[j];
-            }
+    if (kGeom && flag) {
+        final_cost = weighted_geom_sum<MODEL>(fc, s_vc, px, cand, vw, costrow, 0.2f, nsrc);
+    } else {
+        for (int j = 0; j < nsrc; ++j) {
+            const float wj = vw[j];
+            if (wj > 0) final_cost += kGeom ? wj * (costrow[j] + 0.1f * 3.0f) : wj * costrow[j];
         }
     }
     final_cost /= weight_norm;
@@ -679,10 +673,16 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             fetch.layer = vsel;
             quad_ncc<MODEL, 1, TG::RW, WRS, TQS>(
                 c, px, aux, wr, rr, tq, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
-                [&](const int, float cst) {
-                    if (kGeom) cst += 0.2f * geom_cost<MODEL>(fc, s_vc[vsel], px, cur_plane);
-                    row_now[vsel] = vw[vsel] * cst;
-                });
+                [&](const int, const float cst) { row_now[vsel] = cst; });
+        }
+        __syncwarp(FULL);
+        // weight (and, in geometric mode, add the geometric term): lane k of the group takes the k-th selected
+        // view, so that the group's neighbour-depth loads are in flight together instead of one after the other
+        for (int idx = gl; idx < n_sel; idx += 8) {
+            const int vsel = (int)__fns(temp_selected_views, 0, idx + 1);
+            float cst = row_now[vsel];
+            if (kGeom) cst += 0.2f * geom_cost<MODEL>(fc, s_vc[vsel], px, cur_plane);
+            row_now[vsel] = vw[vsel] * cst;
         }
         __syncwarp(FULL);
         for (int j = 0; j < nsrc; ++j) {
@@ -854,9 +854,6 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             const float4 hp = shfl_plane(FULL, temp_plane, gbase + min(h, 4));
             if (h < 5) quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, hp, q, tq + k * kTqPerHyp * TQS);
         }
-        // the plane of the hypothesis this lane finishes (lane q: hypothesis q; lane 0 also hypothesis 4)
-        const float4 hp_q = shfl_plane(FULL, temp_plane, gbase + q);
-        const float4 hp_4 = shfl_plane(FULL, temp_plane, gbase + 4);
         __syncwarp(FULL);
         const int n_sel = (do_refine && valid) ? __popc(temp_selected_views) : 0;
         int rounds = (n_sel + 1) >> 1;
@@ -873,12 +870,41 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             quad_ncc<MODEL, 5, TG::RW, WRS, TQS>(
                 c, px, aux, wr, rr, tq, fetch, q, want ? 0x1Fu : 0u,
                 [&](const int h) { return (h < 3 ? h : h - 3) * kTqPerHyp * TQS + ((h < 3 ? 0 : 1) - Q) * 4; },
-                [&](const int h, float cst) {
-                    if (kGeom) cst += 0.1f * geom_cost<MODEL>(fc, s_vc[vsel], px, h == 4 ? hp_4 : hp_q);
-                    cost_grp[h * nvp + vsel] = cst;
-                });
+                [&](const int h, const float cst) { cost_grp[h * nvp + vsel] = cst; });
         }
         __syncwarp(FULL);
+        if (kGeom) {
+            // geometric term of every (hypothesis, selected view) pair, dealt out to the 8 lanes of the group with
+            // four neighbour-depth loads in flight per lane; the five planes travel through the tap-depth table
+            if (gl < 5) {
+                tq[0 * TQS] = temp_plane.x; tq[1 * TQS] = temp_plane.y; tq[2 * TQS] = temp_plane.z; tq[3 * TQS] = temp_plane.w;
+            }
+            __syncwarp(FULL);
+            const float *planes5 = tq - gl;
+            const int n_pairs = 5 * n_sel;
+            for (int p0 = gl; p0 < n_pairs; p0 += 32) {
+                float sx[4], sy[4], sd[4];
+                int hh[4], vv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pidx = p0 + 8 * k;
+                    hh[k] = -1;
+                    sd[k] = 0.f;
+                    if (pidx < n_pairs) {
+                        hh[k] = pidx % 5;
+                        vv[k] = (int)__fns(temp_selected_views, 0, pidx / 5 + 1);
+                        const float4 hp = make_float4(planes5[hh[k]], planes5[hh[k] + TQS], planes5[hh[k] + 2 * TQS], planes5[hh[k] + 3 * TQS]);
+                        sd[k] = __ldg(geom_address<MODEL>(fc, s_vc[vv[k]], px, hp, sx[k], sy[k]));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (hh[k] >= 0)
+                        cost_grp[hh[k] * nvp + vv[k]] += 0.1f * geom_finish<MODEL>(fc, s_vc[vv[k]], px, sx[k], sy[k], sd[k]);
+                }
+            }
+            __syncwarp(FULL);
+        }
     }
     {
         const float two_angle_sigma_squared = two_angle_sigma_squared_r;
