@@ -516,7 +516,7 @@ int configure_kernels(acmmp_ctx *ctx)
     static std::once_flag once;
     static cudaError_t result = cudaSuccess;
     std::call_once(once, [] {
-        const int big = 200 * 1024;
+        const int big = 227 * 1024;      // the per-CTA maximum of sm_100
         cudaError_t e;
 #define SETATTR(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) result = e;
         SETATTR((k_pass<kModelPinhole, kModePhoto>)) SETATTR((k_pass<kModelPinhole, kModePrior>)) SETATTR((k_pass<kModelPinhole, kModeGeom>))
@@ -774,6 +774,7 @@ int launch_pass(acmmp_ctx *ctx, int colour, int iter)
     // cost terms and the prior term is dropped -- refuse instead
     if (fc.geom && fc.prior) return fail(ctx, ACMMP_E_UNSUPPORTED, "geom_consistency and planar_prior in the same stage are not supported");
     const size_t smem = smem_pass<MODEL>(fc.nsrc);
+    if (smem > 227 * 1024) return fail(ctx, ACMMP_E_UNSUPPORTED, "k_pass needs more shared memory than an SM has for this many source views");
     if (fc.geom) k_pass<MODEL, kModeGeom><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
     else if (fc.prior) k_pass<MODEL, kModePrior><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
     else k_pass<MODEL, kModePhoto><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);

@@ -353,7 +353,8 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
 #define ACMMP_PASS_TH 16
 #endif
 constexpr int kPassTW = 8, kPassTH = ACMMP_PASS_TH, kPassPix = kPassTW * kPassTH / 2, kPassNT = 8 * kPassPix;
-constexpr int kPassTq = 5 * kTqPerHyp;      // tap-depth table entries per lane: up to 5 hypotheses x (9 taps + centre)
+constexpr int kPassTq = 4 * kTqPerHyp;      // tap-depth table entries per lane: phase A holds 4 hypotheses x (9 taps + centre), the
+                                             // refinement 3 (five hypotheses spread over the two quads), view sampling 15 draws
 
 // FindMinCostIndex / FindMaxCostIndex, ACMMP.cu:62-86 (ties -> last index)
 __device__ __forceinline__ int find_min_idx(const float (&c)[8])

@@ -1,0 +1,167 @@
+"""GPU parity at the edges of the input space (through the C ABI, against the compiled reference): image sizes that
+are not multiples of any tile, a single source view, the maximum of 32 source views (reference ACMMP.cu:522),
+source views of different sizes (each view is scaled to its own size, ACMMP.cpp:606-610), argument errors."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from util import close_frac, dump
+
+pytestmark = pytest.mark.gpu
+SEED = 99
+
+
+def _pair(imgs, cams):
+    from acmmp_b200 import Context
+    from oracle.ref_driver import RefACMMP
+    ctx = Context(0)
+    ctx.set_views(imgs, cams)
+    ctx.set_seed(SEED)
+    return ctx, RefACMMP(imgs, cams, seed=SEED)
+
+
+def _stage_agreement(ctx, ref, gt):
+    """Whole stage on both sides.  The reference races and carries an uninitialised variable, so whole
+    maps agree statistically; what must hold at any size: the same quality against ground truth, the same share of
+    NaN costs (pixels whose 15 view draws all fail divide 0 by 0 in the reference too, ACMMP.cu:1243), no inf."""
+    ctx.run_patch_match()
+    pa, ca = ctx.get_result()
+    ref.run_patch_match()
+    pb, cb = ref.get_result()
+    rel = np.abs(pa[..., 3] - pb[..., 3]) / np.maximum(np.abs(pb[..., 3]), 1e-9)
+    return dict(depth_within_1pct=float((rel <= 0.01).mean()),
+                mine_vs_gt=float((np.abs(pa[..., 3] - gt) / gt <= 0.01).mean()),
+                ref_vs_gt=float((np.abs(pb[..., 3] - gt) / gt <= 0.01).mean()),
+                nan_mine=float(np.isnan(ca).mean()), nan_ref=float(np.isnan(cb).mean()),
+                no_inf=bool(not np.isinf(pa).any() and not np.isinf(ca).any()))
+
+
+def _one_pass(ctx, ref, H, W):
+    """Deterministic comparison: one black pass from the reference's own post-init state (test_gpu_parity._pass_compare)."""
+    from test_gpu_parity import _pass_compare
+    ref.launch_init()
+    r, _, _ = _pass_compare(ctx, ref, 0, 0, H, W, border=min(4, H // 8))
+    return max(r["mode0"]["plane_match"], r["mode1"]["plane_match"]), r["mode1"]["untouched_ok"], max(r["mode0"]["rng_match"], r["mode1"]["rng_match"])
+
+
+def _quality_ok(res, slack=0.06, nan_slack=0.03):
+    """(whole-stage figures are statistical, see _stage_agreement; on a 40 x 24 image 1 % is ten pixels)"""
+    return res["no_inf"] and abs(res["mine_vs_gt"] - res["ref_vs_gt"]) <= slack and abs(res["nan_mine"] - res["nan_ref"]) <= nan_slack
+
+
+@pytest.mark.parametrize("size", [(333, 251), (97, 61), (40, 24)])
+def test_ragged_image_sizes(size):
+    """Sizes that no tile divides (8x16 pass tiles, 16x8 init tiles, odd widths for the checkerboard)."""
+    from acmmp_b200 import synth
+    w, h = size
+    scene = synth.make_pinhole_scene(n_views=4, width=w, height=h, focal=0.8 * w, seed=11)
+    imgs, cams, ids = scene.problem(0)
+    ctx, ref = _pair(imgs, cams)
+    planes = util.random_planes(scene, 0, seed=3, perturb=0.05)
+    a, b = ctx.probe_ncc(planes, 1), ref.probe_ncc(planes, 1)
+    res = dict(ncc_1e4=close_frac(a, b, atol=1e-4, rtol=1e-4), ncc_1e3=close_frac(a, b, atol=1e-3, rtol=1e-3))
+    # identical initial hypotheses (same XORWOW stream per pixel) everywhere, borders included
+    ctx.random_init(); ctx.synchronize()
+    ref.launch_init()
+    sa, sb = ctx.download_state(), ref.download_state()
+    res["init_planes"] = close_frac(sa["planes"], sb["planes"], 1e-5, 1e-5)
+    res["init_views"] = float((sa["views"] == sb["views"]).mean())
+    res["pass_plane_match"], res["pass_untouched"], res["pass_rng"] = _one_pass(ctx, ref, h, w)
+    res.update(_stage_agreement(ctx, ref, scene.depths_gt[0]))
+    dump(f"edge_size_{w}x{h}", res)
+    assert res["ncc_1e4"] >= 0.97 and res["ncc_1e3"] >= 0.999, res
+    assert res["init_planes"] >= 0.999 and res["init_views"] >= 0.99, res
+    assert res["pass_plane_match"] >= 0.90 and res["pass_untouched"] == 1.0 and res["pass_rng"] >= 0.97, res
+    assert _quality_ok(res), res
+
+
+def test_single_source_view():
+    from acmmp_b200 import synth
+    scene = synth.make_pinhole_scene(n_views=2, width=160, height=120, focal=130.0, seed=5)
+    imgs, cams, ids = scene.problem(0)
+    assert len(imgs) == 2
+    ctx, ref = _pair(imgs, cams)
+    res = {}
+    res["pass_plane_match"], res["pass_untouched"], res["pass_rng"] = _one_pass(ctx, ref, 120, 160)
+    res.update(_stage_agreement(ctx, ref, scene.depths_gt[0]))
+    dump("edge_single_source", res)
+    assert res["pass_plane_match"] >= 0.90 and res["pass_untouched"] == 1.0, res
+    assert _quality_ok(res), res
+
+
+def test_thirty_two_source_views():
+    """The reference's arrays and view bitmask hold at most 32 source views (ACMMP.cu:522, :88-96)."""
+    from acmmp_b200 import synth, AcmmpError, Context
+    scene = synth.make_pinhole_scene(n_views=34, width=128, height=96, focal=110.0, seed=6, baseline_ratio=0.012, n_src=33)
+    imgs, cams, ids = scene.problem(16)
+    imgs, cams = imgs[:33], cams[:33]            # reference view + 32 sources
+    ctx, ref = _pair(imgs, cams)
+    planes = util.random_planes(scene, 16, seed=3, perturb=0.02)
+    a, va = ctx.probe_initcost(planes)
+    b, vb = ref.probe_initcost(planes)
+    res = dict(initcost=close_frac(a, b, atol=1e-3, rtol=1e-3), views=float((va == vb).mean()), bit31_used=bool((va >> 31).any()))
+    res["pass_plane_match"], res["pass_untouched"], res["pass_rng"] = _one_pass(ctx, ref, 96, 128)
+    res.update(_stage_agreement(ctx, ref, scene.depths_gt[16]))
+    dump("edge_32_sources", res)
+    assert res["initcost"] >= 0.995 and res["views"] >= 0.98, res
+    assert res["pass_plane_match"] >= 0.90 and res["pass_untouched"] == 1.0, res
+    assert _quality_ok(res), res
+    # 33 source views are refused, not truncated
+    imgs34, cams34, _ = scene.problem(16)
+    with pytest.raises(AcmmpError):
+        Context(0).set_views(imgs34[:34], cams34[:34])
+
+
+def test_source_views_of_different_sizes():
+    """Every view is scaled to its own size upstream; sources smaller than the layered texture are edge-replicated."""
+    import cv2
+    from acmmp_b200 import synth, make_camera, MODEL_PINHOLE
+    scene = synth.make_pinhole_scene(n_views=4, width=200, height=150, focal=170.0, seed=8)
+    imgs, cams, ids = scene.problem(0)
+    imgs, cams = list(imgs), list(cams)
+    # halve source view 2 (image + intrinsics), as RescaleImageAndCamera would (ACMMP.cpp:225-246)
+    small = cv2.resize(imgs[2], (100, 75), interpolation=cv2.INTER_LINEAR)
+    K = np.array(list(cams[2].K), np.float32).reshape(3, 3).copy()
+    K[0, 0] *= 0.5; K[0, 2] *= 0.5; K[1, 1] *= 0.5; K[1, 2] *= 0.5
+    cams[2] = make_camera(MODEL_PINHOLE, list(cams[2].R), list(cams[2].t), K=K, width=100, height=75,
+                          depth_min=cams[2].depth_min, depth_max=cams[2].depth_max)
+    imgs[2] = small
+    ctx, ref = _pair(imgs, cams)
+    planes = util.random_planes(scene, 0, seed=3, perturb=0.03)
+    res = {}
+    for view in (1, 2, 3):
+        a, b = ctx.probe_ncc(planes, view), ref.probe_ncc(planes, view)
+        res[f"ncc_v{view}_1e4"] = close_frac(a, b, atol=1e-4, rtol=1e-4)
+        res[f"ncc_v{view}_1e3"] = close_frac(a, b, atol=1e-3, rtol=1e-3)
+    res["pass_plane_match"], res["pass_untouched"], res["pass_rng"] = _one_pass(ctx, ref, 150, 200)
+    res.update(_stage_agreement(ctx, ref, scene.depths_gt[0]))
+    dump("edge_mixed_sizes", res)
+    for view in (1, 2, 3):
+        assert res[f"ncc_v{view}_1e4"] >= 0.97 and res[f"ncc_v{view}_1e3"] >= 0.999, res
+    assert res["pass_plane_match"] >= 0.90 and res["pass_untouched"] == 1.0, res
+    assert _quality_ok(res), res
+
+
+def test_argument_errors_are_reported_not_fatal():
+    """The reference exit()s on failure (ACMMP.cpp:64-97); the library returns codes."""
+    from acmmp_b200 import Context, AcmmpError, lib, synth
+    ctx = Context(0)
+    with pytest.raises(AcmmpError):
+        ctx.run_patch_match()                      # no views yet
+    scene = synth.make_pinhole_scene(n_views=3, width=64, height=48, focal=60.0, seed=1)
+    imgs, cams, ids = scene.problem(0)
+    with pytest.raises(AcmmpError):
+        ctx.set_views(imgs[:1], cams[:1])          # a reference view without sources
+    ctx.set_views(imgs, cams)
+    ctx.set_geom_consistency(False)
+    with pytest.raises(AcmmpError):
+        ctx.run_patch_match()                      # geometric mode without depth maps
+    ctx.reset_modes()
+    ctx.set_planar_prior()
+    with pytest.raises(AcmmpError):
+        ctx.run_patch_match()                      # prior mode without prior inputs
+    ctx.reset_modes()
+    ctx.run_patch_match()                          # and the context is still usable
+    assert lib().acmmp_create(C.byref(C.c_void_p()), C.c_int(4096)) != 0      # no such device
