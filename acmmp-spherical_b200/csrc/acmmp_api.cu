@@ -791,9 +791,9 @@ int launch_finalize(acmmp_ctx *ctx)
     const FrameConst fc = frame_const(ctx);
     const int npx = ctx->W * ctx->H;
     k_depth_normal<MODEL><<<(npx + 255) / 256, 256, 0, ctx->stream>>>(fc);
-    const int half = ((ctx->W + 1) / 2) * ctx->H;
-    k_median_filter<<<(half + 255) / 256, 256, 0, ctx->stream>>>(fc, 0);
-    k_median_filter<<<(half + 255) / 256, 256, 0, ctx->stream>>>(fc, 1);
+    const dim3 mgrid((ctx->W + kMedTW - 1) / kMedTW, (ctx->H + kMedTH - 1) / kMedTH);
+    k_median_filter<<<mgrid, 256, 0, ctx->stream>>>(fc, 0);
+    k_median_filter<<<mgrid, 256, 0, ctx->stream>>>(fc, 1);
     ctx->launches += 3;
     CK(cudaGetLastError());
     return ACMMP_OK;

@@ -989,47 +989,60 @@ k_depth_normal(const __grid_constant__ FrameConst fc)
 
 // CheckerboardFilter, ACMMP.cu:1366-1480: median of up to 21 depths, in place, one colour per
 // launch.  All 20 neighbour offsets have odd Manhattan distance, i.e. the other colour, so a
-// launch never reads what it writes.
+// launch never reads what it writes.  A CTA owns a 32x16 pixel tile (256 pixels of the active colour, one per
+// thread) and first stages the depths of the tile + 5 px halo in shared memory with coalesced float4 loads: the
+// 21 scattered .w reads per pixel from the float4 map made the direct form L1-bound (0.42 ms per launch at
+// 3200x2130, 0.55 TB/s effective).
+constexpr int kMedTW = 32, kMedTH = 16, kMedHalo = 5, kMedPW = kMedTW + 2 * kMedHalo, kMedPH = kMedTH + 2 * kMedHalo;
+
 __global__ void __launch_bounds__(256)
 k_median_filter(const __grid_constant__ FrameConst fc, const int colour)
 {
+    __shared__ float sd[kMedPH][kMedPW + 1];
     const int W = fc.W, H = fc.H;
-    const int half = (W + 1) / 2;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= half * H) return;
-    const int y = idx / half;
-    const int x = 2 * (idx % half) + ((y + colour) & 1);
-    if (x >= W) return;
-    const int center = y * W + x;
+    const int x0 = blockIdx.x * kMedTW, y0 = blockIdx.y * kMedTH;
     float4 *ph = fc.planes;
+    for (int i = threadIdx.x; i < kMedPW * kMedPH; i += 256) {
+        const int lx = i % kMedPW, ly = i / kMedPW;
+        const int gx = x0 + lx - kMedHalo, gy = y0 + ly - kMedHalo;
+        float d = 0.f;
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) d = ph[(size_t)gy * W + gx].w;
+        sd[ly][lx] = d;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4;                                  // 16 rows x 16 colour pixels
+    const int y = y0 + ty;
+    const int x = x0 + 2 * (threadIdx.x & 15) + ((y + colour) & 1);
+    if (x >= W || y >= H) return;
+    const int center = y * W + x;
+    if (fc.costs[center] < 0.001f) return;
+    const int cx = x - x0 + kMedHalo, cy = y - y0 + kMedHalo;
+#define ACMMP_D(dx, dy) sd[cy + (dy)][cx + (dx)]
     float filter[21];
     int index = 0;
-    filter[index++] = ph[center].w;
-    if (fc.costs[center] < 0.001f) return;
-    const int left = center - 1, leftleft = center - 3;
-    const int up = center - W, upup = center - 3 * W;
-    const int down = center + W, downdown = center + 3 * W;
-    const int right = center + 1, rightright = center + 3;
-    if (y > 0) filter[index++] = ph[up].w;
-    if (y > 2) filter[index++] = ph[upup].w;
-    if (y > 4) filter[index++] = ph[upup - W * 2].w;
-    if (y < H - 1) filter[index++] = ph[down].w;
-    if (y < H - 3) filter[index++] = ph[downdown].w;
-    if (y < H - 5) filter[index++] = ph[downdown + W * 2].w;
-    if (x > 0) filter[index++] = ph[left].w;
-    if (x > 2) filter[index++] = ph[leftleft].w;
-    if (x > 4) filter[index++] = ph[leftleft - 2].w;
-    if (x < W - 1) filter[index++] = ph[right].w;
-    if (x < W - 3) filter[index++] = ph[rightright].w;
-    if (x < W - 5) filter[index++] = ph[rightright + 2].w;
-    if (y > 0 && x < W - 2) filter[index++] = ph[up + 2].w;
-    if (y < H - 1 && x < W - 2) filter[index++] = ph[down + 2].w;
-    if (y > 0 && x > 1) filter[index++] = ph[up - 2].w;
-    if (y < H - 1 && x > 1) filter[index++] = ph[down - 2].w;
-    if (x > 0 && y > 2) filter[index++] = ph[left - W * 2].w;
-    if (x < W - 1 && y > 2) filter[index++] = ph[right - W * 2].w;
-    if (x > 0 && y < H - 2) filter[index++] = ph[left + W * 2].w;
-    if (x < W - 1 && y < H - 2) filter[index++] = ph[right + W * 2].w;
+    filter[index++] = ACMMP_D(0, 0);
+    // same order as the reference (ACMMP.cu:1393-1455); the order does not change the median
+    if (y > 0) filter[index++] = ACMMP_D(0, -1);
+    if (y > 2) filter[index++] = ACMMP_D(0, -3);
+    if (y > 4) filter[index++] = ACMMP_D(0, -5);
+    if (y < H - 1) filter[index++] = ACMMP_D(0, 1);
+    if (y < H - 3) filter[index++] = ACMMP_D(0, 3);
+    if (y < H - 5) filter[index++] = ACMMP_D(0, 5);
+    if (x > 0) filter[index++] = ACMMP_D(-1, 0);
+    if (x > 2) filter[index++] = ACMMP_D(-3, 0);
+    if (x > 4) filter[index++] = ACMMP_D(-5, 0);
+    if (x < W - 1) filter[index++] = ACMMP_D(1, 0);
+    if (x < W - 3) filter[index++] = ACMMP_D(3, 0);
+    if (x < W - 5) filter[index++] = ACMMP_D(5, 0);
+    if (y > 0 && x < W - 2) filter[index++] = ACMMP_D(2, -1);
+    if (y < H - 1 && x < W - 2) filter[index++] = ACMMP_D(2, 1);
+    if (y > 0 && x > 1) filter[index++] = ACMMP_D(-2, -1);
+    if (y < H - 1 && x > 1) filter[index++] = ACMMP_D(-2, 1);
+    if (x > 0 && y > 2) filter[index++] = ACMMP_D(-1, -2);
+    if (x < W - 1 && y > 2) filter[index++] = ACMMP_D(1, -2);
+    if (x > 0 && y < H - 2) filter[index++] = ACMMP_D(-1, 2);
+    if (x < W - 1 && y < H - 2) filter[index++] = ACMMP_D(1, 2);
+#undef ACMMP_D
     // sort_small, ACMMP.cu:36-45
     for (int i = 1; i < index; i++) {
         const float tmp = filter[i];
