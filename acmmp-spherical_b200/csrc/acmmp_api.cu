@@ -509,7 +509,7 @@ NccTable ncc_table(const acmmp_ctx *ctx)
 }
 
 template <int MODEL> size_t smem_tp(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT>(nsrc, kTpNT, 0).total; }
-template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT>(nsrc, kPassNT, kPassPix, kPassTq).total; }
+template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassWRS, kPassNT>(nsrc, kPassNT, kPassPix, kPassTq).total; }
 
 int configure_kernels(acmmp_ctx *ctx)
 {

@@ -353,6 +353,13 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
 #define ACMMP_PASS_TH 16
 #endif
 constexpr int kPassTW = 8, kPassTH = ACMMP_PASS_TH, kPassPix = kPassTW * kPassTH / 2, kPassNT = 8 * kPassPix;
+// Tap stride of the weight tables in elements.  The four lanes of a quad read taps {0, 1, 6, 7} + const of four
+// neighbouring pixels in one LDS.64: with a stride = 4 (mod 16) float2 the four taps land in four different bank
+// groups (one wavefront per load; the unpadded power-of-two stride cost 8 -- ncu r1f: 42 % of all shared wavefronts).
+#ifndef ACMMP_PASS_WPAD
+#define ACMMP_PASS_WPAD 4
+#endif
+constexpr int kPassWRS = kPassPix + ACMMP_PASS_WPAD;
 constexpr int kPassTq = 4 * kTqPerHyp;      // tap-depth table entries per lane: phase A holds 4 hypotheses x (9 taps + centre), the
                                              // refinement 3 (five hypotheses spread over the two quads), view sampling 15 draws
 
@@ -401,10 +408,10 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     typedef TileGeom<kPassTW, kPassTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     constexpr bool kPrior = (MODE == kModePrior), kGeom = (MODE == kModeGeom);
-    constexpr int WRS = kPassPix;
+    constexpr int WRS = kPassWRS;
     constexpr int TQS = kPassNT;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kPassTW, kPassTH, kPassPix, kPassNT> L(fc.nsrc, kPassNT, kPassPix, kPassTq);
+    const SmemLayout<MODEL, kPassTW, kPassTH, kPassWRS, kPassNT> L(fc.nsrc, kPassNT, kPassPix, kPassTq);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
     float2 *wr_all = reinterpret_cast<float2 *>(smem + L.off_wr);
