@@ -72,40 +72,14 @@ void ACMMP::InuputInitialization(const std::string &dense_folder, const std::vec
     std::vector<int> ids;
     ids.push_back(problem.ref_image_id);
     ids.insert(ids.end(), problem.src_image_ids.begin(), problem.src_image_ids.end());
-    for (int id : ids) {
-        cv::Mat_<float> img;
-        if (!LoadGreyImage(dense_folder, id, img)) std::cerr << "Error: could not read image " << id << std::endl;
-        std::stringstream cam_path;
-        cam_path << dense_folder << "/cams/" << std::setw(8) << std::setfill('0') << id << "_cam.txt";
-        Camera cam = ReadCamera(cam_path.str());
-        cam.height = img.rows;
-        cam.width = img.cols;
-        images_.push_back(img);
-        cameras_.push_back(cam);
-    }
-    for (size_t i = 0; i < images_.size(); ++i) {
+    for (size_t i = 0; i < ids.size(); ++i) {
         // note: the reference indexes the problem vector BY IMAGE ID here (ACMMP.cpp:609)
         const int max_image_size = (i == 0) ? problems[idx].cur_image_size : problems[problem.src_image_ids[i - 1]].cur_image_size;
-        if (images_[i].cols <= max_image_size && images_[i].rows <= max_image_size) continue;
-        const float factor_x = static_cast<float>(max_image_size) / images_[i].cols;
-        const float factor_y = static_cast<float>(max_image_size) / images_[i].rows;
-        const float factor = std::min(factor_x, factor_y);
-        const int new_cols = (int)std::round(images_[i].cols * factor);
-        const int new_rows = (int)std::round(images_[i].rows * factor);
-        const float scale_x = new_cols / static_cast<float>(images_[i].cols);
-        const float scale_y = new_rows / static_cast<float>(images_[i].rows);
-        cv::Mat_<float> scaled;
-        ResizeLinear(images_[i], scaled, new_cols, new_rows);
-        images_[i] = scaled;
-        if (cameras_[i].model == SPHERE) {
-            cameras_[i].params[1] *= scale_x;
-            cameras_[i].params[2] *= scale_y;
-        } else {
-            cameras_[i].K[0] *= scale_x; cameras_[i].K[2] *= scale_x;
-            cameras_[i].K[4] *= scale_y; cameras_[i].K[5] *= scale_y;
-        }
-        cameras_[i].height = new_rows;
-        cameras_[i].width = new_cols;
+        cv::Mat_<float> img;
+        Camera cam;
+        LoadScaledView(dense_folder, ids[i], max_image_size, img, cam);
+        images_.push_back(img);
+        cameras_.push_back(cam);
     }
     params_.depth_min = cameras_[0].depth_min * 0.6f;
     params_.depth_max = cameras_[0].depth_max * 1.2f;
@@ -122,6 +96,108 @@ void ACMMP::InuputInitialization(const std::string &dense_folder, const std::vec
             depths_.push_back(d);
         }
     }
+}
+
+// One view of InuputInitialization (ACMMP.cpp:576-643): grey image as float, camera file, both scaled so that the
+// longer side is at most max_image_size (bilinear resampling, intrinsics scaled by the achieved ratios).
+bool LoadScaledView(const std::string &dense_folder, int id, int max_image_size, cv::Mat_<float> &image, Camera &cam)
+{
+    bool ok = LoadGreyImage(dense_folder, id, image);
+    if (!ok) std::cerr << "Error: could not read image " << id << std::endl;
+    std::stringstream cam_path;
+    cam_path << dense_folder << "/cams/" << std::setw(8) << std::setfill('0') << id << "_cam.txt";
+    cam = ReadCamera(cam_path.str());
+    cam.height = image.rows;
+    cam.width = image.cols;
+    if (image.cols <= max_image_size && image.rows <= max_image_size) return ok;
+    const float factor_x = static_cast<float>(max_image_size) / image.cols;
+    const float factor_y = static_cast<float>(max_image_size) / image.rows;
+    const float factor = std::min(factor_x, factor_y);
+    const int new_cols = (int)std::round(image.cols * factor);
+    const int new_rows = (int)std::round(image.rows * factor);
+    const float scale_x = new_cols / static_cast<float>(image.cols);
+    const float scale_y = new_rows / static_cast<float>(image.rows);
+    cv::Mat_<float> scaled;
+    ResizeLinear(image, scaled, new_cols, new_rows);
+    image = scaled;
+    if (cam.model == SPHERE) {
+        cam.params[1] *= scale_x;
+        cam.params[2] *= scale_y;
+    } else {
+        cam.K[0] *= scale_x; cam.K[2] *= scale_x;
+        cam.K[4] *= scale_y; cam.K[5] *= scale_y;
+    }
+    cam.height = new_rows;
+    cam.width = new_cols;
+    return ok;
+}
+
+// ---- GPU-resident stage chaining (see acmmp_host.h) ------------------------------------------------------------
+void ACMMP::SetViewsHost(const std::vector<cv::Mat_<float>> &images, const std::vector<Camera> &cameras, bool next_level)
+{
+    images_ = images;
+    cameras_ = cameras;
+    const int n = (int)images_.size();
+    std::vector<const float *> ptrs(n);
+    std::vector<int32_t> ws(n), hs(n);
+    for (int i = 0; i < n; ++i) {
+        ptrs[i] = images_[i].ptr();
+        ws[i] = images_[i].cols;
+        hs[i] = images_[i].rows;
+    }
+    params_.depth_min = cameras_[0].depth_min * 0.6f;
+    params_.depth_max = cameras_[0].depth_max * 1.2f;
+    params_.num_images = n;
+    if (next_level) {
+        check(acmmp_next_level(ctx_, n, ptrs.data(), ws.data(), hs.data(), cameras_.data()), "SetViewsHost (next level)");
+        params_.geom_consistency = params_.multi_geometry = params_.planar_prior = 0;
+        params_.max_iterations = 3;
+        params_.hierarchy = 1;
+    } else {
+        check(acmmp_set_views(ctx_, n, ptrs.data(), ws.data(), hs.data(), cameras_.data()), "SetViewsHost");
+    }
+}
+
+void ACMMP::ResetModes()
+{
+    check(acmmp_reset_modes(ctx_), "ResetModes");
+    params_.geom_consistency = params_.multi_geometry = params_.planar_prior = params_.hierarchy = 0;
+    params_.max_iterations = 3;
+}
+
+void ACMMP::SetNeighbourDepthMapsDevice(const std::vector<const float *> &maps_dev, const std::vector<int> &widths,
+                                        const std::vector<int> &heights)
+{
+    const int n = (int)maps_dev.size() + 1;
+    std::vector<const float *> p(n);
+    std::vector<int32_t> w(n), h(n);
+    p[0] = nullptr;
+    w[0] = cameras_[0].width;
+    h[0] = cameras_[0].height;
+    for (int i = 1; i < n; ++i) {
+        p[i] = maps_dev[i - 1];
+        w[i] = widths[i - 1];
+        h[i] = heights[i - 1];
+    }
+    check(acmmp_set_depth_maps_device(ctx_, n, p.data(), w.data(), h.data()), "SetNeighbourDepthMapsDevice");
+}
+
+void ACMMP::RunPatchMatchResident(bool download)
+{
+    check(acmmp_run_patch_match_resident(ctx_), "RunPatchMatchResident");
+    if (download) {
+        check(acmmp_download_result(ctx_), "RunPatchMatchResident (download)");
+        check(acmmp_result_host(ctx_, &planes_host_, &costs_host_), "RunPatchMatchResident (result)");
+    } else {
+        check(acmmp_synchronize(ctx_), "RunPatchMatchResident (synchronize)");
+        planes_host_ = costs_host_ = nullptr;
+    }
+}
+
+void ACMMP::ExportDepthDevice(float *depth_dev)
+{
+    check(acmmp_export_depth_device(ctx_, depth_dev), "ExportDepthDevice");
+    check(acmmp_synchronize(ctx_), "ExportDepthDevice (synchronize)");
 }
 
 // reference ACMMP.cpp:681-845: host -> device, plus the reload of the previous stage's state from .dmb files

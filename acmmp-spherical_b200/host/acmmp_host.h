@@ -61,6 +61,8 @@ void GenerateSampleList(const std::string &dense_folder, std::vector<Problem> &p
 bool LoadGreyImage(const std::string &dense_folder, int id, cv::Mat_<float> &image);
 // Only the size (ComputeMultiScaleSettings reads whole images just for that, main.cpp:46-50).
 bool ImageSize(const std::string &dense_folder, int id, int &cols, int &rows);
+// Image `id` and its camera scaled to max_image_size the way InuputInitialization does (ACMMP.cpp:576-643)
+bool LoadScaledView(const std::string &dense_folder, int id, int max_image_size, cv::Mat_<float> &image, Camera &camera);
 // cv::resize(src, dst, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) on a float image
 void ResizeLinear(const cv::Mat_<float> &src, cv::Mat_<float> &dst, int new_cols, int new_rows);
 
@@ -101,6 +103,23 @@ public:
 
     // not in the reference: CUDA-event times of the last RunPatchMatch {init, passes, finalize, #passes, last pass}
     void GetTimings(float out[8]);
+
+    // ---- GPU-resident stage chaining (not in the reference) --------------------------
+    // What the reference hands from stage to stage through .dmb files and a new object per stage stays on the device
+    // of ONE object per view: the driver keeps the object, feeds it the next level's views / the neighbours' depth
+    // maps (device pointers) and downloads a result only where the host needs it.  Same kernels, same inputs, same
+    // order => the same maps as the file-chained schedule.
+    //   SetViewsHost(next_level = false): what InuputInitialization + CudaSpaceInitialization do, from host arrays
+    //   SetViewsHost(next_level = true) : move to the next finer level: JBU of the current result on the device,
+    //                                     hierarchy inputs, SetHierarchyParams (acmmp_next_level)
+    void SetViewsHost(const std::vector<cv::Mat_<float>> &images, const std::vector<Camera> &cameras, bool next_level);
+    void ResetModes();                                   // flags of a freshly constructed object, views kept
+    // depth maps of the SOURCE views for the geometric term (device pointers); the reference view's own map is the
+    // state on the device (acmmp_set_depth_maps_device with maps[0] == NULL)
+    void SetNeighbourDepthMapsDevice(const std::vector<const float *> &maps_dev, const std::vector<int> &widths,
+                                     const std::vector<int> &heights);
+    void RunPatchMatchResident(bool download);           // download: fill what GetPlaneHypothesis / GetCost read
+    void ExportDepthDevice(float *depth_dev);            // W*H float32, what depths*.dmb would hold
 
 private:
     void check(int rc, const char *what);

@@ -1,9 +1,11 @@
-// acmmp_main.cpp -- `acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N]`: the reference's pipeline
+// acmmp_main.cpp -- `acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N] [--resident 1]`: the reference's pipeline
 // schedule (main.cpp:392-482) on top of the B200 library, stage by stage through the same .dmb files:
 //   per pyramid level (coarsest first):
 //     [level > 0] JBU of depths_geom.dmb -> depths.dmb, then photometric stage with hierarchy
 //     photometric stage -> CPU planar prior -> prior stage (same object)            -> depths.dmb
 //     2 x geometric-consistency stage (the second one with multi_geometry)          -> depths_geom.dmb
+// `--resident 1` runs the same stages GPU-resident (RunResident below): no .dmb round trips between stages, every
+// image read once per level; it writes the same final maps.
 // Fusion (RunFusionCuda, main.cpp:478-479) is not part of this path.
 #include <chrono>
 #include <cmath>
@@ -11,9 +13,14 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <map>
+#include <memory>
 #include <sstream>
+#include <stdexcept>
 #include <sys/stat.h>
 #include <sys/types.h>
+
+#include <cuda_runtime.h>
 
 #include "acmmp_host.h"
 
@@ -73,6 +80,50 @@ void collect(ACMMP &acmmp, cv::Mat_<float> &depths, cv::Mat_<cv::Vec3f> &normals
     g_gpu_ms += t[0] + t[1] + t[2];
 }
 
+// The CPU planar-prior stage, main.cpp:113-185: support points -> Delaunay triangles -> triangle-id mask
+// (the reference's barycentric stepping rasteriser) + one plane per triangle -> pixels whose prior depth leaves the
+// depth range dropped.  `depths` is the photometric stage's depth map.
+void PlanarPriorStage(ACMMP &acmmp, const cv::Mat_<float> &depths, cv::Mat_<float> &mask_tri, std::vector<float4> &planeParams_tri)
+{
+    const double t0 = now_s();
+    const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
+    acmmp.SetPlanarPriorParams();
+    const cv::Rect imageRC(0, 0, width, height);
+    std::vector<cv::Point> support2DPoints;
+    acmmp.GetSupportPoints(support2DPoints);
+    const auto triangles = acmmp.DelaunayTriangulation(imageRC, support2DPoints);
+    mask_tri = cv::Mat_<float>::zeros(height, width);
+    planeParams_tri.clear();
+    uint32_t tri_idx = 0;
+    for (const auto &triangle : triangles) {
+        if (!(imageRC.contains(triangle.pt1) && imageRC.contains(triangle.pt2) && imageRC.contains(triangle.pt3))) continue;
+        const float L01 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt2.x, 2) + std::pow(triangle.pt1.y - triangle.pt2.y, 2));
+        const float L02 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt3.x, 2) + std::pow(triangle.pt1.y - triangle.pt3.y, 2));
+        const float L12 = std::sqrt(std::pow(triangle.pt2.x - triangle.pt3.x, 2) + std::pow(triangle.pt2.y - triangle.pt3.y, 2));
+        const float max_edge_length = std::max(L01, std::max(L02, L12));
+        const float step = 1.0 / max_edge_length;
+        // barycentric stepping rasteriser of the reference (main.cpp:153-159)
+        for (float p = 0; p < 1.0; p += step) {
+            for (float q = 0; q < 1.0 - p; q += step) {
+                const int x = p * triangle.pt1.x + q * triangle.pt2.x + (1.0 - p - q) * triangle.pt3.x;
+                const int y = p * triangle.pt1.y + q * triangle.pt2.y + (1.0 - p - q) * triangle.pt3.y;
+                mask_tri(y, x) = tri_idx + 1.0;
+            }
+        }
+        planeParams_tri.push_back(acmmp.GetPriorPlaneParams(triangle, depths));
+        tri_idx++;
+    }
+    for (int i = 0; i < width; ++i) {
+        for (int j = 0; j < height; ++j) {
+            if (mask_tri(j, i) > 0) {
+                const float d = acmmp.GetDepthFromPlaneParam(planeParams_tri[(size_t)(mask_tri(j, i) - 1)], i, j);
+                if (!(d <= acmmp.GetMaxDepth() && d >= acmmp.GetMinDepth())) mask_tri(j, i) = 0;
+            }
+        }
+    }
+    g_prior_s += now_s() - t0;
+}
+
 // main.cpp:73-210
 void ProcessProblem(const std::string &dense_folder, const std::vector<Problem> &problems, const int idx, bool geom_consistency,
                     bool planar_prior, bool hierarchy, bool multi_geometry = false)
@@ -98,42 +149,9 @@ void ProcessProblem(const std::string &dense_folder, const std::vector<Problem> 
 
     if (planar_prior) {                                     // main.cpp:113-197
         std::cout << "Run Planar Prior Assisted PatchMatch MVS ..." << std::endl;
-        const double t0 = now_s();
-        acmmp.SetPlanarPriorParams();
-        const cv::Rect imageRC(0, 0, width, height);
-        std::vector<cv::Point> support2DPoints;
-        acmmp.GetSupportPoints(support2DPoints);
-        const auto triangles = acmmp.DelaunayTriangulation(imageRC, support2DPoints);
-        cv::Mat_<float> mask_tri = cv::Mat_<float>::zeros(height, width);
+        cv::Mat_<float> mask_tri;
         std::vector<float4> planeParams_tri;
-        uint32_t tri_idx = 0;
-        for (const auto &triangle : triangles) {
-            if (!(imageRC.contains(triangle.pt1) && imageRC.contains(triangle.pt2) && imageRC.contains(triangle.pt3))) continue;
-            const float L01 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt2.x, 2) + std::pow(triangle.pt1.y - triangle.pt2.y, 2));
-            const float L02 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt3.x, 2) + std::pow(triangle.pt1.y - triangle.pt3.y, 2));
-            const float L12 = std::sqrt(std::pow(triangle.pt2.x - triangle.pt3.x, 2) + std::pow(triangle.pt2.y - triangle.pt3.y, 2));
-            const float max_edge_length = std::max(L01, std::max(L02, L12));
-            const float step = 1.0 / max_edge_length;
-            // barycentric stepping rasteriser of the reference (main.cpp:153-159)
-            for (float p = 0; p < 1.0; p += step) {
-                for (float q = 0; q < 1.0 - p; q += step) {
-                    const int x = p * triangle.pt1.x + q * triangle.pt2.x + (1.0 - p - q) * triangle.pt3.x;
-                    const int y = p * triangle.pt1.y + q * triangle.pt2.y + (1.0 - p - q) * triangle.pt3.y;
-                    mask_tri(y, x) = tri_idx + 1.0;
-                }
-            }
-            planeParams_tri.push_back(acmmp.GetPriorPlaneParams(triangle, depths));
-            tri_idx++;
-        }
-        for (int i = 0; i < width; ++i) {
-            for (int j = 0; j < height; ++j) {
-                if (mask_tri(j, i) > 0) {
-                    const float d = acmmp.GetDepthFromPlaneParam(planeParams_tri[(size_t)(mask_tri(j, i) - 1)], i, j);
-                    if (!(d <= acmmp.GetMaxDepth() && d >= acmmp.GetMinDepth())) mask_tri(j, i) = 0;
-                }
-            }
-        }
-        g_prior_s += now_s() - t0;
+        PlanarPriorStage(acmmp, depths, mask_tri, planeParams_tri);
         acmmp.CudaPlanarPriorInitialization(planeParams_tri, mask_tri);
         acmmp.RunPatchMatch();
         collect(acmmp, depths, normals, costs);
@@ -164,17 +182,164 @@ void JointBilateralUpsampling(const std::string &dense_folder, const Problem &pr
     RunJBU(scaled, ref_depth, dense_folder, problem, g_device);
 }
 
+// ---- GPU-resident schedule ---------------------------------------------------------
+// The same stages in the same order as the file-chained loop in main() -- per level: photometric (+ hierarchy) and
+// prior stage for every view, then two geometric sweeps over the views -- but one ACMMP object per view lives through
+// the whole run: a stage finds the previous stage's planes / costs on the device, the next level is reached through
+// the on-device JBU, the neighbours' depth maps are device buffers (`dmap` = what depths.dmb would hold, `gmap` =
+// depths_geom.dmb, overwritten view by view exactly like the file: the second geometric sweep is Gauss-Seidel across
+// views in the reference, main.cpp:443-445, and here).  Every image is read and scaled once per level instead of
+// once per (view that uses it, stage).  Only the finest level's maps are written, at the end.
+// Returns false (nothing done) when the scene does not fit the scheme; the caller then runs the file-chained schedule.
+struct DeviceMap {
+    float *ptr = nullptr;
+    int w = 0, h = 0;
+    size_t cap = 0;
+    void fit(int nw, int nh)
+    {
+        const size_t need = (size_t)nw * nh;
+        if (need > cap) {
+            if (ptr) cudaFree(ptr);
+            if (cudaMalloc(&ptr, need * sizeof(float)) != cudaSuccess) throw std::runtime_error("cudaMalloc of a depth map failed");
+            cap = need;
+        }
+        w = nw;
+        h = nh;
+    }
+};
+
+bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems, const size_t num_images, int max_num_downscale)
+{
+    std::map<int, int> index_of;                      // image id -> position in `problems`
+    for (size_t i = 0; i < problems.size(); ++i) index_of[problems[i].ref_image_id] = (int)i;
+    for (size_t i = 0; i < num_images; ++i) {
+        if (problems[i].num_downscale != max_num_downscale) return false;       // views with fewer levels: JBU no-op case
+        for (int id : problems[i].src_image_ids) {
+            const auto it = index_of.find(id);
+            if (it == index_of.end() || (size_t)it->second >= num_images) return false;    // a neighbour that is not processed
+        }
+    }
+    cudaSetDevice(g_device);
+    std::vector<std::unique_ptr<ACMMP>> objs(num_images);
+    std::vector<DeviceMap> dmap(num_images), gmap(num_images);
+    std::vector<cv::Mat_<float>> final_prior_depth(num_images);
+    bool first_level = true;
+    while (max_num_downscale >= 0) {
+        std::cout << "Scale: " << max_num_downscale << std::endl;
+        for (auto &problem : problems) {
+            if (problem.num_downscale >= 0) {
+                problem.cur_image_size = problem.max_image_size / (int)std::pow(2, problem.num_downscale);
+                problem.num_downscale--;
+            }
+        }
+        const bool finest = max_num_downscale == 0;
+        // every view of this level, read and scaled once
+        std::vector<cv::Mat_<float>> level_image(num_images);
+        std::vector<Camera> level_camera(num_images);
+        for (size_t i = 0; i < num_images; ++i)
+            LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].cur_image_size, level_image[i], level_camera[i]);
+
+        for (size_t i = 0; i < num_images; ++i) {                                // photometric + prior stage
+            const Problem &problem = problems[i];
+            std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << "..." << std::endl;
+            std::vector<cv::Mat_<float>> images{level_image[i]};
+            std::vector<Camera> cameras{level_camera[i]};
+            for (int id : problem.src_image_ids) {
+                images.push_back(level_image[index_of[id]]);
+                cameras.push_back(level_camera[index_of[id]]);
+            }
+            if (first_level) {
+                objs[i].reset(new ACMMP(g_device));
+                objs[i]->SetSeed(g_seed);
+            }
+            ACMMP &acmmp = *objs[i];
+            acmmp.SetViewsHost(images, cameras, !first_level);
+            acmmp.RunPatchMatchResident(true);                                   // the CPU prior stage reads the result
+            float t[8];
+            acmmp.GetTimings(t);
+            g_gpu_ms += t[0] + t[1] + t[2];
+            const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
+            cv::Mat_<float> depths(height, width);
+            for (int k = 0; k < width * height; ++k) depths.ptr()[k] = acmmp.GetPlaneHypothesis(k).w;
+            cv::Mat_<float> mask_tri;
+            std::vector<float4> planeParams_tri;
+            PlanarPriorStage(acmmp, depths, mask_tri, planeParams_tri);
+            acmmp.CudaPlanarPriorInitialization(planeParams_tri, mask_tri);
+            acmmp.RunPatchMatchResident(finest);                                 // finest level: depths.dmb is an output
+            acmmp.GetTimings(t);
+            g_gpu_ms += t[0] + t[1] + t[2];
+            if (finest) {
+                final_prior_depth[i] = cv::Mat_<float>(height, width);
+                for (int k = 0; k < width * height; ++k) final_prior_depth[i].ptr()[k] = acmmp.GetPlaneHypothesis(k).w;
+            }
+            dmap[i].fit(width, height);
+            acmmp.ExportDepthDevice(dmap[i].ptr);
+        }
+        for (int geom_iter = 0; geom_iter < 2; ++geom_iter) {                    // geometric sweeps
+            const bool multi_geometry = geom_iter > 0;
+            for (size_t i = 0; i < num_images; ++i) {
+                const Problem &problem = problems[i];
+                ACMMP &acmmp = *objs[i];
+                acmmp.ResetModes();
+                acmmp.SetGeomConsistencyParams(multi_geometry);
+                std::vector<const float *> maps;
+                std::vector<int> ws, hs;
+                for (int id : problem.src_image_ids) {
+                    const DeviceMap &m = multi_geometry ? gmap[index_of[id]] : dmap[index_of[id]];
+                    maps.push_back(m.ptr);
+                    ws.push_back(m.w);
+                    hs.push_back(m.h);
+                }
+                acmmp.SetNeighbourDepthMapsDevice(maps, ws, hs);
+                const bool last = finest && multi_geometry;
+                acmmp.RunPatchMatchResident(last);
+                float t[8];
+                acmmp.GetTimings(t);
+                g_gpu_ms += t[0] + t[1] + t[2];
+                gmap[i].fit(acmmp.GetReferenceImageWidth(), acmmp.GetReferenceImageHeight());
+                acmmp.ExportDepthDevice(gmap[i].ptr);
+                if (last) {
+                    const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
+                    cv::Mat_<float> depths = cv::Mat_<float>::zeros(height, width), costs = cv::Mat_<float>::zeros(height, width);
+                    cv::Mat_<cv::Vec3f> normals = cv::Mat_<cv::Vec3f>::zeros(height, width);
+                    for (int k = 0; k < width * height; ++k) {
+                        const float4 ph = acmmp.GetPlaneHypothesis(k);
+                        depths.ptr()[k] = ph.w;
+                        normals.ptr()[k] = cv::Vec3f(ph.x, ph.y, ph.z);
+                        costs.ptr()[k] = acmmp.GetCost(k);
+                    }
+                    const std::string result_folder = result_folder_of(dense_folder, problem.ref_image_id);
+                    mkdir(result_folder.c_str(), 0777);
+                    writeDepthDmb(result_folder + "/depths.dmb", final_prior_depth[i]);
+                    writeDepthDmb(result_folder + "/depths_geom.dmb", depths);
+                    writeNormalDmb(result_folder + "/normals.dmb", normals);
+                    writeDepthDmb(result_folder + "/costs.dmb", costs);
+                    std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << " done!" << std::endl;
+                }
+            }
+        }
+        first_level = false;
+        max_num_downscale--;
+    }
+    objs.clear();
+    for (auto &m : dmap) if (m.ptr) cudaFree(m.ptr);
+    for (auto &m : gmap) if (m.ptr) cudaFree(m.ptr);
+    return true;
+}
+
 } // namespace
 
 int main(int argc, char **argv)
 {
     if (argc < 2) {
-        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N]" << std::endl;
+        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N] [--resident 0|1]" << std::endl;
         return -1;
     }
     const std::string dense_folder = argv[1];
     size_t max_views = 0;
+    int resident = 0;
     for (int i = 2; i + 1 < argc; i += 2) {
+        if (!std::strcmp(argv[i], "--resident")) resident = std::atoi(argv[i + 1]);
         if (!std::strcmp(argv[i], "--seed")) g_seed = std::strtoull(argv[i + 1], nullptr, 10);
         else if (!std::strcmp(argv[i], "--device")) g_device = std::atoi(argv[i + 1]);
         else if (!std::strcmp(argv[i], "--max-views")) max_views = (size_t)std::atoi(argv[i + 1]);
@@ -187,6 +352,11 @@ int main(int argc, char **argv)
     const double t_start = now_s();
     try {
         int max_num_downscale = ComputeMultiScaleSettings(dense_folder, problems);
+        if (resident) {
+            std::vector<Problem> work = problems;
+            if (RunResident(dense_folder, work, num_images, max_num_downscale)) max_num_downscale = -1;     // done
+            else { std::cout << "resident schedule not applicable to this scene; running the file-chained schedule" << std::endl; resident = 0; }
+        }
         int flag = 0;
         const int geom_iterations = 2;
         while (max_num_downscale >= 0) {                       // main.cpp:417-476
@@ -214,7 +384,7 @@ int main(int argc, char **argv)
         std::cerr << "acmmp_b200: " << e.what() << std::endl;
         return 1;
     }
-    std::cout << "{\"views\": " << num_images << ", \"wall_s\": " << now_s() - t_start << ", \"kernel_ms\": " << g_gpu_ms
+    std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"views\": " << num_images << ", \"wall_s\": " << now_s() - t_start << ", \"kernel_ms\": " << g_gpu_ms
               << ", \"prior_cpu_s\": " << g_prior_s << "}" << std::endl;
     return 0;
 }
