@@ -482,37 +482,48 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         const int b = vertical ? x : y, B = vertical ? W : H;
         const int sa = vertical ? W : 1, sb = vertical ? 1 : W;
 #define ACMMP_INB(s) (du < 0 ? (a - (s) >= 0) : (a + (s) <= A - 1))
+        // All cost reads of a direction are issued before the first comparison (positions that fall outside read
+        // nothing and count as +inf): at the start of a tile the 16 warps of the CTA are all here at once, nobody hides
+        // a chain of dependent L2 round trips (the scan took 2.6 % of the warp time as load -> compare -> load).
+        constexpr float kInf = 3.0e38f;
         if (far_dir) {
             flag = ACMMP_INB(3);
             if (flag) {
-                pos = center + du * 3 * sa;
-                float cmin = costs_in[pos];
+                float cv[11];
+                int pt[11];
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const bool ok = ACMMP_INB(3 + 2 * i);
+                    pt[i] = center + du * (3 + 2 * i) * sa;
+                    cv[i] = ok ? __ldg(costs_in + pt[i]) : kInf;
+                }
+                pos = pt[0];
+                float cmin = cv[0];
+#pragma unroll
                 for (int i = 1; i < 11; ++i) {
-                    if (ACMMP_INB(3 + 2 * i)) {
-                        const int pt = center + du * (3 + 2 * i) * sa;
-                        const float cv = costs_in[pt];
-                        if (cv < cmin) { cmin = cv; pos = pt; }
-                    }
+                    if (cv[i] < cmin) { cmin = cv[i]; pos = pt[i]; }
                 }
             }
         } else {
             flag = ACMMP_INB(1);
             if (flag) {
-                pos = center + du * sa;
-                float cmin = costs_in[pos];
+                float cv[7];
+                int pt[7];
+                pt[0] = center + du * sa;
+                cv[0] = __ldg(costs_in + pt[0]);
+#pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    if (ACMMP_INB(2 + i)) {
-                        if (b > i) {
-                            const int pt = center + du * (2 + i) * sa - i * sb;
-                            const float cv = costs_in[pt];
-                            if (cv < cmin) { cmin = cv; pos = pt; }
-                        }
-                        if (b < B - 1 - i) {
-                            const int pt = center + du * (2 + i) * sa + i * sb;
-                            const float cv = costs_in[pt];
-                            if (cv < cmin) { cmin = cv; pos = pt; }
-                        }
-                    }
+                    const bool row_ok = ACMMP_INB(2 + i);
+                    pt[1 + 2 * i] = center + du * (2 + i) * sa - i * sb;
+                    pt[2 + 2 * i] = center + du * (2 + i) * sa + i * sb;
+                    cv[1 + 2 * i] = (row_ok && b > i) ? __ldg(costs_in + pt[1 + 2 * i]) : kInf;
+                    cv[2 + 2 * i] = (row_ok && b < B - 1 - i) ? __ldg(costs_in + pt[2 + 2 * i]) : kInf;
+                }
+                pos = pt[0];
+                float cmin = cv[0];
+#pragma unroll
+                for (int i = 1; i < 7; ++i) {
+                    if (cv[i] < cmin) { cmin = cv[i]; pos = pt[i]; }
                 }
             }
         }
