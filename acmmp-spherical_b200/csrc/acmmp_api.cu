@@ -4,6 +4,7 @@
 // (ACMMP.cpp:681-845), ACMMP::CudaPlanarPriorInitialization (:847-867), ACMMP::RunPatchMatch
 // (ACMMP.cu:1506-1556), RunJBU / JBU::CudaRun (ACMMP.cpp:1071-1122, ACMMP.cu:1617-1649).
 // No CPU fallback exists: without a usable CUDA device every compute entry point fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -229,6 +230,7 @@ struct acmmp_ctx {
     acmmp_params params;
     int as_compiled = 1;
     int use_tma = 1;
+    int num_sms = 148;
     uint64_t seed = 0;
     bool have_seeded = false;
     std::map<std::tuple<uint64_t, int, int>, uint2 *> seeded_cache;   // curand_init states per (seed, W, H), kept across levels
@@ -509,7 +511,7 @@ NccTable ncc_table(const acmmp_ctx *ctx)
 }
 
 template <int MODEL> size_t smem_tp(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT>(nsrc, kTpNT, 0).total; }
-template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassWRS, kPassNT>(nsrc, kPassNT, kPassPix, kPassTq).total; }
+template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassWRS, kPassNT>(nsrc, kPassNT, kPassPix, kPassTq, 2).total; }
 
 int configure_kernels(acmmp_ctx *ctx)
 {
@@ -769,15 +771,17 @@ template <int MODEL>
 int launch_pass(acmmp_ctx *ctx, int colour, int iter)
 {
     const FrameConst fc = frame_const(ctx);
-    dim3 grid((ctx->W + kPassTW - 1) / kPassTW, (ctx->H + kPassTH - 1) / kPassTH);
+    // persistent kernel: one CTA per SM walks the tile grid (row-major) with stride gridDim.x
+    const int tiles_x = (ctx->W + kPassTW - 1) / kPassTW, ntiles = tiles_x * ((ctx->H + kPassTH - 1) / kPassTH);
+    const dim3 grid(std::min(ntiles, ctx->num_sms * ACMMP_PASS_MIN_CTAS));
     // the reference's flag combinations are exclusive per stage; should a caller set both, geometric wins for the
     // cost terms and the prior term is dropped -- refuse instead
     if (fc.geom && fc.prior) return fail(ctx, ACMMP_E_UNSUPPORTED, "geom_consistency and planar_prior in the same stage are not supported");
     const size_t smem = smem_pass<MODEL>(fc.nsrc);
     if (smem > 227 * 1024) return fail(ctx, ACMMP_E_UNSUPPORTED, "k_pass needs more shared memory than an SM has for this many source views");
-    if (fc.geom) k_pass<MODEL, kModeGeom><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
-    else if (fc.prior) k_pass<MODEL, kModePrior><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
-    else k_pass<MODEL, kModePhoto><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter);
+    if (fc.geom) k_pass<MODEL, kModeGeom><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter, tiles_x, ntiles);
+    else if (fc.prior) k_pass<MODEL, kModePrior><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter, tiles_x, ntiles);
+    else k_pass<MODEL, kModePhoto><<<grid, kPassNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_pass, colour, iter, tiles_x, ntiles);
     ctx->launches++;
     CK(cudaGetLastError());
     std::swap(ctx->planes, ctx->planes_alt);
@@ -940,6 +944,7 @@ int acmmp_create(acmmp_ctx **out, int device)
     if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
     acmmp_ctx *ctx = new acmmp_ctx();
     ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
     acmmp_default_params(&ctx->params);
     if (const char *e = std::getenv("ACMMP_NO_TMA")) ctx->use_tma = (e[0] == '1') ? 0 : 1;   // debug aid
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {

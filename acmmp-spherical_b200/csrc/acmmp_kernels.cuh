@@ -33,12 +33,15 @@ struct SmemLayout {
     typedef TileGeom<TW, TH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     size_t off_tile, off_aux, off_wr, off_rr, off_tq, off_vc, off_ncc, off_bar, off_cost, off_vw, off_probs, total;
-    __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows, int tq_entries = kTaps)
+    size_t tile_stride, aux_stride;     // between the buffers of a multi-buffered tile (k_pass: 2)
+    __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows, int tq_entries = kTaps, int nbuf = 1)
     {
         const int nvp = nsrc | 1;
         size_t o = 0;
-        off_tile = o; o += align_up(TG::kTileBytes, 128);
-        off_aux = o; o += align_up(sizeof(AuxT) * TG::RW * TG::RH, 16);
+        tile_stride = align_up(TG::kTileBytes, 128);
+        aux_stride = align_up(sizeof(AuxT) * TG::RW * TG::RH, 16);
+        off_tile = o; o += tile_stride * nbuf;
+        off_aux = o; o += aux_stride * nbuf;
         off_wr = o; o += sizeof(float2) * kTaps * NPIX;
         off_rr = o; o += sizeof(float) * kTaps * NPIX;
         off_tq = o; o += sizeof(float) * (size_t)tq_entries * NT;
@@ -400,64 +403,44 @@ __device__ __forceinline__ float4 shfl_plane(const unsigned gmask, const float4 
 // specialised instance carries only its own code (the instruction cache is a measured bottleneck of this kernel).
 constexpr int kModePhoto = 0, kModePrior = 1, kModeGeom = 2;
 
+// Persistent form: the grid is one CTA per SM; CTA b walks the tiles b, b + gridDim.x, ... (tile index = row-major
+// over the tile grid) and its 16 warps meet at a __syncthreads() after every tile -- exactly the lock step separate
+// CTAs per tile have (the instruction cache needs it: warps left to drift across tiles ran 1.75x slower, 46 % of the
+// warp time waiting for instructions).  What the loop saves is everything between two tiles: the CTA launch gap, the
+// per-view constants (staged once per CTA), and the latency of the reference tile -- tile and ray table are
+// double-buffered, the tile after next is requested (TMA) and its ray table computed right after the barrier.
 template <int MODEL, int MODE>
 __global__ void __launch_bounds__(kPassNT, ACMMP_PASS_MIN_CTAS)
 k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap,
-       const int colour, const int iter)
+       const int colour, const int iter, const int tiles_x, const int ntiles)
 {
     typedef TileGeom<kPassTW, kPassTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     constexpr bool kPrior = (MODE == kModePrior), kGeom = (MODE == kModeGeom);
     constexpr int WRS = kPassWRS;
     constexpr int TQS = kPassNT;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kPassTW, kPassTH, kPassWRS, kPassNT> L(fc.nsrc, kPassNT, kPassPix, kPassTq);
-    float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
-    AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
+    const SmemLayout<MODEL, kPassTW, kPassTH, kPassWRS, kPassNT> L(fc.nsrc, kPassNT, kPassPix, kPassTq, 2);
     float2 *wr_all = reinterpret_cast<float2 *>(smem + L.off_wr);
     float *rr_all = reinterpret_cast<float *>(smem + L.off_rr);
     float *tq_all = reinterpret_cast<float *>(smem + L.off_tq);
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
     NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + L.off_bar);        // full[2]
     float *cost_all = reinterpret_cast<float *>(smem + L.off_cost);
     float *vw_all = reinterpret_cast<float *>(smem + L.off_vw);
     float *probs_all = reinterpret_cast<float *>(smem + L.off_probs);
 
     const int W = fc.W, H = fc.H;
-    const int x0 = blockIdx.x * kPassTW, y0 = blockIdx.y * kPassTH;
     const int tid = threadIdx.x;
-
-    // pixels of the other colour are carried over to the output buffers unchanged
-    if (tid < kPassPix) {
-        const int yy = y0 + (tid >> 2);
-        const int xx = x0 + 2 * (tid & 3) + ((yy + colour + 1) & 1);
-        if (xx < W && yy < H) {
-            const int cc = yy * W + xx;
-            fc.planes_alt[cc] = fc.planes[cc];
-            fc.costs_alt[cc] = fc.costs[cc];
-        }
-    }
-
-    stage_tile<MODEL, kPassTW, kPassTH, kPassNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
-
+    const int G = gridDim.x;
     const int g = tid >> 3;            // pixel slot in the CTA
     const int gl = tid & 7;            // lane in the pixel group == candidate direction
     const int lane = tid & 31;
     const int gbase = lane & ~7;       // first lane of the group inside the warp
-    const unsigned gmask = 0xFFu << gbase;
-    const int yy_ = y0 + (g >> 2);
-    const int xx_ = x0 + 2 * (g & 3) + ((yy_ + colour) & 1);
-    // Groups that fall outside the image stay alive (clamped coordinates, nothing stored) so that the
-    // warp walks the view loops in lock step; see ncc_views.
-    const bool valid = xx_ < W && yy_ < H;
-    const int x = min(xx_, W - 1), y = min(yy_, H - 1);
-    constexpr unsigned FULL = 0xffffffffu;
-
-    const int center = y * W + x;
     const int nsrc = fc.nsrc;
     const int nvp = nsrc | 1;
-    PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
     float2 *wr = wr_all + g;
     float *rr = rr_all + g;
     float *tq = tq_all + tid;                  // this lane's column of the tap-depth table
@@ -467,6 +450,75 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     float *probs = probs_all + g * nvp;
     const float4 *planes_in = fc.planes;
     const float *costs_in = fc.costs;
+
+    // buffer `buf` for tile t: ray table by all threads, reference tile by one TMA copy (or plain loads, debug aid)
+    auto fill_buffer = [&](const int buf, const int t) {
+        AuxT *a = reinterpret_cast<AuxT *>(smem + L.off_aux + buf * L.aux_stride);
+        float *dst = reinterpret_cast<float *>(smem + L.off_tile + buf * L.tile_stride);
+        const int tx0 = (t % tiles_x) * kPassTW - kHalo, ty0 = (t / tiles_x) * kPassTH - kHalo;
+        for (int idx = tid; idx < TG::RW * TG::RH; idx += kPassNT) a[idx] = make_aux<MODEL>(fc, tx0 + idx % TG::RW, ty0 + idx / TG::RW);
+        if (fc.use_tma) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tma_load_tile_2d(dst, &tmap, tx0 + kRefPad, ty0 + kRefPad, bars + buf, TG::kTileBytes);
+            }
+        } else {
+            for (int idx = tid; idx < TG::RW * TG::RH; idx += kPassNT) {
+                const int cx = idx % TG::RW, cy = idx / TG::RW;
+                const int gy = min(ty0 + kRefPad + cy, fc.H + 2 * kRefPad - 1);
+                const int gx = min(tx0 + kRefPad + cx, fc.ref_pitch - 1);
+                dst[cy * TG::PW + cx] = __ldg(fc.ref_padded + (size_t)gy * fc.ref_pitch + gx);
+            }
+        }
+    };
+
+    // ---- prologue: per-view constants, barriers, the first two tiles -------------------------------------------
+    for (int i = tid; i < nsrc * 16; i += kPassNT) s_ncc[i >> 4].a[i & 15] = nt.c[i >> 4].a[i & 15];
+    {   // view constants: nsrc * 72 words
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(fc.views);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_vc);
+        const int nwords = nsrc * (int)(sizeof(ViewConst) / 4);
+        for (int i = tid; i < nwords; i += kPassNT) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+    }
+    __syncthreads();
+    for (int k = 0; k < 2; ++k)
+        if ((int)blockIdx.x + k * G < ntiles) fill_buffer(k, blockIdx.x + k * G);
+    __syncthreads();
+
+#pragma unroll 1
+    for (int it = 0, tile = blockIdx.x; tile < ntiles; ++it, tile += G) {
+    const int buf = it & 1;
+    const float *tile_r = reinterpret_cast<const float *>(smem + L.off_tile + buf * L.tile_stride);
+    const AuxT *aux = reinterpret_cast<const AuxT *>(smem + L.off_aux + buf * L.aux_stride);
+    if (fc.use_tma) {
+        if (lane == 0) mbar_wait(bars + buf, (unsigned)((it >> 1) & 1));
+        __syncwarp(FULL);
+    }
+    const int x0 = (tile % tiles_x) * kPassTW, y0 = (tile / tiles_x) * kPassTH;
+
+    // pixels of the other colour are carried over to the output buffers unchanged (each warp: its own row)
+    if (lane < 4) {
+        const int yy = y0 + (tid >> 5);
+        const int xx = x0 + 2 * lane + ((yy + colour + 1) & 1);
+        if (xx < W && yy < H) {
+            const int cc = yy * W + xx;
+            fc.planes_alt[cc] = fc.planes[cc];
+            fc.costs_alt[cc] = fc.costs[cc];
+        }
+    }
+
+    const int yy_ = y0 + (g >> 2);
+    const int xx_ = x0 + 2 * (g & 3) + ((yy_ + colour) & 1);
+    // Groups that fall outside the image stay alive (clamped coordinates, nothing stored) so that the
+    // warp walks the view loops in lock step; see ncc_views.
+    const bool valid = xx_ < W && yy_ < H;
+    const int x = min(xx_, W - 1), y = min(yy_, H - 1);
+    const int center = y * W + x;
+    PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
 
     fill_weights<MODEL, TG::PW, WRS>(fc, tile_r, px, wr, rr, gl, 8);
 
@@ -639,16 +691,41 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
                 }
             }
         }
-        __syncwarp(FULL);
-        for (int i = 0; i < nsrc; ++i) {
-            const unsigned ba = __ballot_sync(FULL, id_a == i), bb = __ballot_sync(FULL, id_b == i);
-            const int cnt = __popc(ba & gmask) + __popc(bb & gmask);
-            if (gl == 0) vw[i] = (float)cnt;
-            if (cnt > 0) {
-                temp_selected_views |= 1u << i;
-                weight_norm += (float)cnt;          // small integers: exact in any order
+        // Per-view draw counts of the group without votes (a vote loop here costs the persistent tile loop its
+        // warp-uniform texture handles, see the kernel header): every lane adds its one or two draws into 4-bit
+        // counters (15 draws at most; 8 views per word), three xor-shuffles sum the words over the group's 8 lanes.
+        unsigned cw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (id_a >= 0 && (id_a >> 3) == k) cw[k] += 1u << (4 * (id_a & 7));
+            if (id_b >= 0 && (id_b >> 3) == k) cw[k] += 1u << (4 * (id_b & 7));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (8 * k < nsrc) {          // warp-uniform
+                cw[k] += __shfl_xor_sync(FULL, cw[k], 1);
+                cw[k] += __shfl_xor_sync(FULL, cw[k], 2);
+                cw[k] += __shfl_xor_sync(FULL, cw[k], 4);
             }
         }
+        unsigned sel_part = 0u, cnt_part = 0u;           // lane gl: views gl, gl + 8, ...
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = gl + 8 * k;
+            const unsigned cnt = (cw[k] >> (4 * gl)) & 15u;
+            if (i < nsrc) {
+                vw[i] = (float)cnt;
+                if (cnt > 0u) sel_part |= 1u << i;
+                cnt_part += cnt;
+            }
+        }
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+            sel_part |= __shfl_xor_sync(FULL, sel_part, off);
+            cnt_part += __shfl_xor_sync(FULL, cnt_part, off);
+        }
+        temp_selected_views = sel_part;
+        weight_norm = (float)cnt_part;                   // small integers: exact in any order
     }
     __syncwarp(FULL);
 
@@ -988,6 +1065,11 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         if (sel_dirty) fc.selected_views[center] = sel_center;
         rng_store(fc.rng + 3 * (size_t)center, rs);
     }
+
+    // ---- every warp is through the tile: its buffer is free for the tile after next ---------------------------
+    __syncthreads();
+    if (tile + 2 * G < ntiles) fill_buffer(buf, tile + 2 * G);
+    }   // tile loop
 }
 
 // ------------------------------------------------------------------------------------------
