@@ -258,6 +258,8 @@ def run_view(levels, backend, prior_cache=None, exchange=None):
                 host_maps, dev = exchange.neighbour_depths(li, L, backend)
             planes, costs = backend.geom(L, multi, host_maps, finest, last=(finest and multi), device_ptrs=dev)
         if planes is not None:
-            out = (np.array(planes), np.array(costs))
+            # no copy: for the B200 backend these are views of the library's pinned result buffers, valid until the
+            # context runs again (the caller copies if it needs them longer); the reference backend returns fresh arrays
+            out = (planes, costs)
         state = True if out is None else out        # the reference backend hands the host arrays to the next level
     return out

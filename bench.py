@@ -261,6 +261,11 @@ def main():
         b.end()
         prior_cpu_s += b.t.prior_cpu_s          # only the first warm-up step computes it
 
+    # the prior (computed once in warm-up) is a step input like the images: pinned host memory
+    for k, (pp, mm) in list(prior_cache.items()):
+        prior_cache[k] = (torch.from_numpy(np.ascontiguousarray(pp)).pin_memory().numpy(),
+                          torch.from_numpy(np.ascontiguousarray(mm)).pin_memory().numpy())
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     exch.ms, exch.bytes, exch.h2d = 0.0, 0, 0
