@@ -78,7 +78,8 @@ _EXPORTS = [
     "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
     "acmmp_get_params", "acmmp_reset_modes", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
-    "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_set_seed",
+    "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_support_points",
+    "acmmp_planar_prior_from_triangles", "acmmp_set_seed",
     "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_download_state", "acmmp_upload_state",
@@ -249,6 +250,22 @@ class Context:
         mk = _f32(masks)
         self._ck(self._l.acmmp_set_planar_prior_inputs(self._h, _fp(pp), C.c_int(pp.shape[0]), _fp(mk)),
                  "acmmp_set_planar_prior_inputs")
+
+    def support_points(self):
+        """GetSupportPoints on the device (costs of the current state) -> int32 array [n, 2] of (x, y), reference order."""
+        cap = ((self.W + 4) // 5) * ((self.H + 4) // 5)
+        xy = np.zeros((cap, 2), np.int32)
+        n = C.c_int(0)
+        self._ck(self._l.acmmp_support_points(self._h, xy.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(cap), C.byref(n)),
+                 "acmmp_support_points")
+        return xy[: n.value].copy()
+
+    def planar_prior_from_triangles(self, tri_xy):
+        """tri_xy: int32 [n, 3, 2] triangle vertices (x, y) inside the image, ids 1..n in this order: plane fit,
+        rasteriser, depth-range test and prior upload on the device."""
+        t = np.ascontiguousarray(tri_xy, np.int32).reshape(-1, 6)
+        self._ck(self._l.acmmp_planar_prior_from_triangles(self._h, t.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(t.shape[0])),
+                 "acmmp_planar_prior_from_triangles")
 
     def set_seed(self, seed):
         self._ck(self._l.acmmp_set_seed(self._h, C.c_uint64(seed)), "acmmp_set_seed")

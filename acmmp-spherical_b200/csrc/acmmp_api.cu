@@ -1106,6 +1106,88 @@ int acmmp_set_planar_prior_inputs(acmmp_ctx *ctx, const float *plane_params4, in
     return ACMMP_OK;
 }
 
+namespace {
+PriorCam prior_cam(const acmmp_ctx *ctx)
+{
+    PriorCam c;
+    const acmmp_camera &cam = ctx->cams[0];
+    c.model = cam.model;
+    c.W = ctx->W;
+    c.H = ctx->H;
+    c.K0 = cam.K[0]; c.K2 = cam.K[2]; c.K4 = cam.K[4]; c.K5 = cam.K[5];
+    c.cx = cam.params[1]; c.cy = cam.params[2];
+    c.depth_min = ctx->params.depth_min;
+    c.depth_max = ctx->params.depth_max;
+    return c;
+}
+} // namespace
+
+int acmmp_support_points(acmmp_ctx *ctx, int32_t *xy, int capacity, int *n)
+{
+    if (!ctx || !ctx->planes || !xy || !n) return fail(ctx, ACMMP_E_ARG, "acmmp_support_points: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int cells_x = (ctx->W + 4) / 5, cells_y = (ctx->H + 4) / 5, ncell = cells_x * cells_y;
+    int2 *cells_dev = nullptr, *cells_host = nullptr;
+    CK(pmalloc(ctx, &cells_dev, sizeof(int2) * (size_t)ncell));
+    CK(phmalloc(ctx, &cells_host, sizeof(int2) * (size_t)ncell));
+    k_support_cells<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->costs, ctx->W, ctx->H, cells_x, cells_y, cells_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cells_host, cells_dev, sizeof(int2) * (size_t)ncell, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int count = 0;
+    for (int i = 0; i < ncell; ++i) {
+        if (cells_host[i].x < 0) continue;
+        if (count < capacity) {
+            xy[2 * count] = cells_host[i].x;
+            xy[2 * count + 1] = cells_host[i].y;
+        }
+        ++count;
+    }
+    ctx->pool.dfree(cells_dev);
+    ctx->pool.hfree(cells_host);
+    *n = count;
+    if (count > capacity) return fail(ctx, ACMMP_E_ARG, "acmmp_support_points: output array too small");
+    return ACMMP_OK;
+}
+
+int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int n_tri)
+{
+    if (!ctx || !ctx->planes || n_tri < 0 || (n_tri > 0 && !tri_xy))
+        return fail(ctx, ACMMP_E_ARG, "acmmp_planar_prior_from_triangles: bad arguments");
+    for (int i = 0; i < 6 * n_tri; i += 2) {
+        if (tri_xy[i] < 0 || tri_xy[i] >= ctx->W || tri_xy[i + 1] < 0 || tri_xy[i + 1] >= ctx->H)
+            return fail(ctx, ACMMP_E_ARG, "acmmp_planar_prior_from_triangles: triangle vertex outside the image");
+    }
+    CK(cudaSetDevice(ctx->device));
+    const int npx = ctx->W * ctx->H;
+    const PriorCam cam = prior_cam(ctx);
+    int *tri_dev = nullptr;
+    float4 *params_dev = nullptr;
+    uint32_t *mask_dev = nullptr;
+    CK(pmalloc(ctx, &tri_dev, sizeof(int) * 6 * (size_t)std::max(n_tri, 1)));
+    CK(pmalloc(ctx, &params_dev, sizeof(float4) * (size_t)std::max(n_tri, 1)));
+    CK(pmalloc(ctx, &mask_dev, sizeof(uint32_t) * (size_t)npx));
+    if (!ctx->prior_planes) CK(pmalloc(ctx, &ctx->prior_planes, sizeof(float4) * (size_t)npx));
+    if (!ctx->plane_masks) CK(pmalloc(ctx, &ctx->plane_masks, sizeof(uint32_t) * (size_t)npx));
+    CK(cudaMemsetAsync(mask_dev, 0, sizeof(uint32_t) * (size_t)npx, ctx->stream));
+    if (n_tri > 0) {
+        CK(cudaMemcpyAsync(tri_dev, tri_xy, sizeof(int) * 6 * (size_t)n_tri, cudaMemcpyHostToDevice, ctx->stream));
+        k_tri_planes<<<(n_tri + 255) / 256, 256, 0, ctx->stream>>>(tri_dev, n_tri, ctx->planes, cam, params_dev);
+        k_tri_raster<<<(n_tri + 127) / 128, 128, 0, ctx->stream>>>(tri_dev, n_tri, ctx->W, mask_dev);
+        ctx->launches += 2;
+    }
+    k_prior_finish<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(mask_dev, params_dev, cam, ctx->prior_planes, ctx->plane_masks);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pool.dfree(tri_dev);
+    ctx->pool.dfree(params_dev);
+    ctx->pool.dfree(mask_dev);
+    ctx->params.planar_prior = 1;
+    return ACMMP_OK;
+}
+
 int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const int32_t *widths, const int32_t *heights,
                      const acmmp_camera *cams)
 {

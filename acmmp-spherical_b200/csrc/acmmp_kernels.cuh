@@ -1269,6 +1269,149 @@ k_expand_prior(const float *__restrict__ masks, const float4 *__restrict__ param
     prior_planes[idx] = p;
 }
 
+// ------------------------------------------------------------------------------------------
+// Planar-prior stage on the device.  The reference runs it on the CPU between the photometric
+// and the prior stage (ACMMP.cpp:904-1011, main.cpp:113-185); here only the Delaunay triangulation stays on the
+// host (host/delaunay.cpp).  Every floating-point step is written with round-to-nearest intrinsics in the order the
+// host code (host/acmmp_host.cpp, acmmp_main.cpp: PlanarPriorStage) evaluates it: no contraction, no fast-math
+// substitution, so that PINHOLE results are bit-identical to the CPU stage (SPHERE differs in the last bit of sin/cos).
+// ------------------------------------------------------------------------------------------
+struct PriorCam {
+    int model, W, H;
+    float K0, K2, K4, K5;      // PINHOLE fx, cx, fy, cy
+    float cx, cy;              // SPHERE params[1], params[2]
+    float depth_min, depth_max;
+};
+
+// GetSupportPoints, ACMMP.cpp:904-930: per 5x5 cell (columns outer, rows inner) the first pixel of least cost, kept
+// when that cost is below 0.1.  cells[cx * cells_y + cy] = (x, y) or (-1, -1); the host compacts in that order.
+__global__ void __launch_bounds__(256)
+k_support_cells(const float *__restrict__ costs, const int W, const int H, const int cells_x, const int cells_y, int2 *__restrict__ cells)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cells_x * cells_y) return;
+    const int col = (idx / cells_y) * 5, row = (idx % cells_y) * 5;
+    float best = 2.0f;
+    int2 where = make_int2(-1, -1);
+    const int c_end = min(W, col + 5), r_end = min(H, row + 5);
+    for (int c = col; c < c_end; ++c)
+        for (int r = row; r < r_end; ++r) {
+            const float cst = costs[(size_t)r * W + c];
+            if (cst < 2.0f && best > cst) {
+                where = make_int2(c, r);
+                best = cst;
+            }
+        }
+    cells[idx] = (best < 0.1f) ? where : make_int2(-1, -1);
+}
+
+// Get3DPointonRefCam, ACMMP.cpp:287-312 (host twin: acmmp_host.cpp)
+__device__ __forceinline__ void prior_lift(const PriorCam &cam, const int x, const int y, const float depth, float &X, float &Y, float &Z)
+{
+    if (cam.model == kModelSphere) {
+        const float lon = __fmul_rn(__fmul_rn(__fdiv_rn(__fsub_rn((float)x, cam.cx), (float)cam.W), 2.0f), (float)M_PI);
+        const float lat = __fmul_rn(__fdiv_rn(-__fsub_rn((float)y, cam.cy), (float)cam.H), (float)M_PI);
+        const float cl = (float)cos((double)lat), sl = (float)sin((double)lat);
+        const float co = (float)cos((double)lon), so = (float)sin((double)lon);
+        X = __fmul_rn(__fmul_rn(cl, so), depth);
+        Y = __fmul_rn(-sl, depth);
+        Z = __fmul_rn(__fmul_rn(cl, co), depth);
+    } else {
+        X = __fdiv_rn(__fmul_rn(depth, __fsub_rn((float)x, cam.K2)), cam.K0);
+        Y = __fdiv_rn(__fmul_rn(depth, __fsub_rn((float)y, cam.K5)), cam.K4);
+        Z = depth;
+    }
+}
+
+// GetPriorPlaneParams, ACMMP.cpp:956-989, in the closed form of acmmp_host.cpp: n = (b - a) x (c - a), w = -n.a,
+// normalised to |n| = 1 and w >= 0; double precision, one triangle per thread.  tri = 6 ints (x1 y1 x2 y2 x3 y3).
+__global__ void __launch_bounds__(256)
+k_tri_planes(const int *__restrict__ tri, const int n_tri, const float4 *__restrict__ planes, const PriorCam cam, float4 *__restrict__ params)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tri) return;
+    float P[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int x = tri[6 * t + 2 * k], y = tri[6 * t + 2 * k + 1];
+        prior_lift(cam, x, y, planes[(size_t)y * cam.W + x].w, P[k][0], P[k][1], P[k][2]);
+    }
+    const double ux = __dsub_rn((double)P[1][0], (double)P[0][0]), uy = __dsub_rn((double)P[1][1], (double)P[0][1]), uz = __dsub_rn((double)P[1][2], (double)P[0][2]);
+    const double vx = __dsub_rn((double)P[2][0], (double)P[0][0]), vy = __dsub_rn((double)P[2][1], (double)P[0][1]), vz = __dsub_rn((double)P[2][2], (double)P[0][2]);
+    const double nx = __dsub_rn(__dmul_rn(uy, vz), __dmul_rn(uz, vy));
+    const double ny = __dsub_rn(__dmul_rn(uz, vx), __dmul_rn(ux, vz));
+    const double nz = __dsub_rn(__dmul_rn(ux, vy), __dmul_rn(uy, vx));
+    const double w = -__dadd_rn(__dadd_rn(__dmul_rn(nx, (double)P[0][0]), __dmul_rn(ny, (double)P[0][1])), __dmul_rn(nz, (double)P[0][2]));
+    double norm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
+    if (w < 0) norm = -norm;
+    if (norm == 0.0) norm = 1.0;
+    params[t] = make_float4((float)__ddiv_rn(nx, norm), (float)__ddiv_rn(ny, norm), (float)__ddiv_rn(nz, norm), (float)__ddiv_rn(w, norm));
+}
+
+// The reference's barycentric stepping rasteriser (main.cpp:153-159), one triangle per thread; the sequential loop
+// lets a later triangle overwrite an earlier one, i.e. the largest id wins: atomicMax.
+__global__ void __launch_bounds__(128)
+k_tri_raster(const int *__restrict__ tri, const int n_tri, const int W, uint32_t *__restrict__ mask)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tri) return;
+    const int x1 = tri[6 * t], y1 = tri[6 * t + 1], x2 = tri[6 * t + 2], y2 = tri[6 * t + 3], x3 = tri[6 * t + 4], y3 = tri[6 * t + 5];
+    // std::sqrt(std::pow(int, 2) + std::pow(int, 2)) in double, stored to float
+    const float L01 = (float)__dsqrt_rn((double)((long long)(x1 - x2) * (x1 - x2) + (long long)(y1 - y2) * (y1 - y2)));
+    const float L02 = (float)__dsqrt_rn((double)((long long)(x1 - x3) * (x1 - x3) + (long long)(y1 - y3) * (y1 - y3)));
+    const float L12 = (float)__dsqrt_rn((double)((long long)(x2 - x3) * (x2 - x3) + (long long)(y2 - y3) * (y2 - y3)));
+    const float max_edge_length = fmaxf(L01, fmaxf(L02, L12));
+    const float step = (float)__ddiv_rn(1.0, (double)max_edge_length);
+    const float fx1 = (float)x1, fx2 = (float)x2, fy1 = (float)y1, fy2 = (float)y2;
+    const double dx3 = (double)x3, dy3 = (double)y3;
+    for (float p = 0; (double)p < 1.0; p = __fadd_rn(p, step)) {
+        const double one_minus_p = __dsub_rn(1.0, (double)p);
+        for (float q = 0; (double)q < one_minus_p; q = __fadd_rn(q, step)) {
+            // p * x1 + q * x2: float;  (1.0 - p - q) * x3: double;  sum in double, truncated
+            const double r = __dsub_rn(one_minus_p, (double)q);
+            const int x = __double2int_rz(__dadd_rn((double)__fadd_rn(__fmul_rn(p, fx1), __fmul_rn(q, fx2)), __dmul_rn(r, dx3)));
+            const int y = __double2int_rz(__dadd_rn((double)__fadd_rn(__fmul_rn(p, fy1), __fmul_rn(q, fy2)), __dmul_rn(r, dy3)));
+            atomicMax(mask + (size_t)y * W + x, (uint32_t)(t + 1));
+        }
+    }
+}
+
+// main.cpp:168-181 + CudaPlanarPriorInitialization (ACMMP.cpp:847-867): drop the pixels whose prior depth
+// (GetDepthFromPlaneParam, ACMMP.cpp:991-1011) leaves the depth range, then mask + per-pixel prior plane
+__global__ void __launch_bounds__(256)
+k_prior_finish(const uint32_t *__restrict__ mask, const float4 *__restrict__ params, const PriorCam cam, float4 *__restrict__ prior_planes,
+               uint32_t *__restrict__ plane_masks)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cam.W * cam.H) return;
+    uint32_t m = mask[idx];
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m > 0) {
+        p = params[m - 1];
+        const int x = idx % cam.W, y = idx / cam.W;
+        float d;
+        if (cam.model == kModelSphere) {
+            const float lon = __fmul_rn(__fmul_rn(__fdiv_rn(__fsub_rn((float)x, cam.cx), (float)cam.W), 2.0f), (float)M_PI);
+            const float lat = __fmul_rn(__fdiv_rn(-__fsub_rn((float)y, cam.cy), (float)cam.H), (float)M_PI);
+            const float cl = (float)cos((double)lat), sl = (float)sin((double)lat);
+            const float dx = __fmul_rn(cl, (float)sin((double)lon)), dy = -sl, dz = __fmul_rn(cl, (float)cos((double)lon));
+            const float denom = __fadd_rn(__fadd_rn(__fmul_rn(p.x, dx), __fmul_rn(p.y, dy)), __fmul_rn(p.z, dz));
+            d = (fabsf(denom) < 1e-6f) ? 1e6f : __fdiv_rn(-p.w, denom);
+        } else {
+            const float t0 = __fmul_rn(__fsub_rn((float)x, cam.K2), p.x);
+            const float t1 = __fmul_rn(__fmul_rn(__fdiv_rn(cam.K0, cam.K4), __fsub_rn((float)y, cam.K5)), p.y);
+            const float t2 = __fmul_rn(cam.K0, p.z);
+            d = __fdiv_rn(__fmul_rn(-p.w, cam.K0), __fadd_rn(__fadd_rn(t0, t1), t2));
+        }
+        if (!(d <= cam.depth_max && d >= cam.depth_min)) {
+            m = 0;
+            p = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    plane_masks[idx] = m;
+    prior_planes[idx] = p;
+}
+
 // hierarchy hand-over between pyramid levels, all on the device (ACMMP.cpp:816-840):
 // coarse (normal, cost) from the previous level's (n_world, depth) planes + costs
 __global__ void __launch_bounds__(256)

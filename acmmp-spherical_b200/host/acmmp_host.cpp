@@ -200,6 +200,31 @@ void ACMMP::ExportDepthDevice(float *depth_dev)
     check(acmmp_synchronize(ctx_), "ExportDepthDevice (synchronize)");
 }
 
+// ---- planar-prior stage on the device (see acmmp_host.h) ------------------------------------------------------
+void ACMMP::GetSupportPointsDevice(std::vector<cv::Point> &support2DPoints)
+{
+    const int width = GetReferenceImageWidth(), height = GetReferenceImageHeight();
+    const int capacity = ((width + 4) / 5) * ((height + 4) / 5);
+    std::vector<int32_t> xy(2 * (size_t)capacity);
+    int n = 0;
+    check(acmmp_support_points(ctx_, xy.data(), capacity, &n), "GetSupportPointsDevice");
+    support2DPoints.clear();
+    support2DPoints.reserve(n);
+    for (int i = 0; i < n; ++i) support2DPoints.push_back(cv::Point(xy[2 * i], xy[2 * i + 1]));
+}
+
+void ACMMP::CudaPlanarPriorFromTriangles(const std::vector<Triangle> &triangles)
+{
+    std::vector<int32_t> tri(6 * triangles.size());
+    for (size_t i = 0; i < triangles.size(); ++i) {
+        tri[6 * i + 0] = triangles[i].pt1.x; tri[6 * i + 1] = triangles[i].pt1.y;
+        tri[6 * i + 2] = triangles[i].pt2.x; tri[6 * i + 3] = triangles[i].pt2.y;
+        tri[6 * i + 4] = triangles[i].pt3.x; tri[6 * i + 5] = triangles[i].pt3.y;
+    }
+    params_.planar_prior = 1;
+    check(acmmp_planar_prior_from_triangles(ctx_, tri.data(), (int)triangles.size()), "CudaPlanarPriorFromTriangles");
+}
+
 // reference ACMMP.cpp:681-845: host -> device, plus the reload of the previous stage's state from .dmb files
 void ACMMP::CudaSpaceInitialization(const std::string &dense_folder, const Problem &problem)
 {

@@ -121,6 +121,13 @@ public:
     void RunPatchMatchResident(bool download);           // download: fill what GetPlaneHypothesis / GetCost read
     void ExportDepthDevice(float *depth_dev);            // W*H float32, what depths*.dmb would hold
 
+    // ---- planar-prior stage on the device: only the triangulation stays on the host ----
+    // GetSupportPoints on the costs of the state on the device (no result download needed)
+    void GetSupportPointsDevice(std::vector<cv::Point> &support2DPoints);
+    // plane per triangle + rasteriser + depth-range test + CudaPlanarPriorInitialization, all on the device; the
+    // triangles must lie inside the image and get the ids 1..n in the given order (main.cpp:140-166)
+    void CudaPlanarPriorFromTriangles(const std::vector<Triangle> &triangles);
+
 private:
     void check(int rc, const char *what);
     acmmp_ctx *ctx_ = nullptr;

@@ -28,6 +28,7 @@ namespace {
 
 uint64_t g_seed = 0;
 int g_device = 0;
+int g_gpu_prior = 0;
 double g_gpu_ms = 0.0, g_prior_s = 0.0;
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -124,6 +125,26 @@ void PlanarPriorStage(ACMMP &acmmp, const cv::Mat_<float> &depths, cv::Mat_<floa
     g_prior_s += now_s() - t0;
 }
 
+// The same stage with everything but the triangulation on the device: support points
+// from the costs on the device, Delaunay on the host, then plane fit / rasteriser / depth-range test / prior upload in
+// one library call.  Ends where PlanarPriorStage + CudaPlanarPriorInitialization end.
+void PlanarPriorStageGpu(ACMMP &acmmp)
+{
+    const double t0 = now_s();
+    const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
+    acmmp.SetPlanarPriorParams();
+    const cv::Rect imageRC(0, 0, width, height);
+    std::vector<cv::Point> support2DPoints;
+    acmmp.GetSupportPointsDevice(support2DPoints);
+    const auto triangles = acmmp.DelaunayTriangulation(imageRC, support2DPoints);
+    std::vector<Triangle> inside;
+    inside.reserve(triangles.size());
+    for (const auto &triangle : triangles)
+        if (imageRC.contains(triangle.pt1) && imageRC.contains(triangle.pt2) && imageRC.contains(triangle.pt3)) inside.push_back(triangle);
+    acmmp.CudaPlanarPriorFromTriangles(inside);
+    g_prior_s += now_s() - t0;
+}
+
 // main.cpp:73-210
 void ProcessProblem(const std::string &dense_folder, const std::vector<Problem> &problems, const int idx, bool geom_consistency,
                     bool planar_prior, bool hierarchy, bool multi_geometry = false)
@@ -149,10 +170,14 @@ void ProcessProblem(const std::string &dense_folder, const std::vector<Problem> 
 
     if (planar_prior) {                                     // main.cpp:113-197
         std::cout << "Run Planar Prior Assisted PatchMatch MVS ..." << std::endl;
-        cv::Mat_<float> mask_tri;
-        std::vector<float4> planeParams_tri;
-        PlanarPriorStage(acmmp, depths, mask_tri, planeParams_tri);
-        acmmp.CudaPlanarPriorInitialization(planeParams_tri, mask_tri);
+        if (g_gpu_prior) {
+            PlanarPriorStageGpu(acmmp);
+        } else {
+            cv::Mat_<float> mask_tri;
+            std::vector<float4> planeParams_tri;
+            PlanarPriorStage(acmmp, depths, mask_tri, planeParams_tri);
+            acmmp.CudaPlanarPriorInitialization(planeParams_tri, mask_tri);
+        }
         acmmp.RunPatchMatch();
         collect(acmmp, depths, normals, costs);
     }
@@ -254,17 +279,21 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             }
             ACMMP &acmmp = *objs[i];
             acmmp.SetViewsHost(images, cameras, !first_level);
-            acmmp.RunPatchMatchResident(true);                                   // the CPU prior stage reads the result
+            acmmp.RunPatchMatchResident(!g_gpu_prior);                           // the CPU prior stage reads the result
             float t[8];
             acmmp.GetTimings(t);
             g_gpu_ms += t[0] + t[1] + t[2];
             const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
-            cv::Mat_<float> depths(height, width);
-            for (int k = 0; k < width * height; ++k) depths.ptr()[k] = acmmp.GetPlaneHypothesis(k).w;
-            cv::Mat_<float> mask_tri;
-            std::vector<float4> planeParams_tri;
-            PlanarPriorStage(acmmp, depths, mask_tri, planeParams_tri);
-            acmmp.CudaPlanarPriorInitialization(planeParams_tri, mask_tri);
+            if (g_gpu_prior) {
+                PlanarPriorStageGpu(acmmp);
+            } else {
+                cv::Mat_<float> depths(height, width);
+                for (int k = 0; k < width * height; ++k) depths.ptr()[k] = acmmp.GetPlaneHypothesis(k).w;
+                cv::Mat_<float> mask_tri;
+                std::vector<float4> planeParams_tri;
+                PlanarPriorStage(acmmp, depths, mask_tri, planeParams_tri);
+                acmmp.CudaPlanarPriorInitialization(planeParams_tri, mask_tri);
+            }
             acmmp.RunPatchMatchResident(finest);                                 // finest level: depths.dmb is an output
             acmmp.GetTimings(t);
             g_gpu_ms += t[0] + t[1] + t[2];
@@ -332,7 +361,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
 int main(int argc, char **argv)
 {
     if (argc < 2) {
-        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N] [--resident 0|1]" << std::endl;
+        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N] [--resident 0|1] [--gpu-prior 0|1]" << std::endl;
         return -1;
     }
     const std::string dense_folder = argv[1];
@@ -340,6 +369,7 @@ int main(int argc, char **argv)
     int resident = 0;
     for (int i = 2; i + 1 < argc; i += 2) {
         if (!std::strcmp(argv[i], "--resident")) resident = std::atoi(argv[i + 1]);
+        else if (!std::strcmp(argv[i], "--gpu-prior")) g_gpu_prior = std::atoi(argv[i + 1]);
         if (!std::strcmp(argv[i], "--seed")) g_seed = std::strtoull(argv[i + 1], nullptr, 10);
         else if (!std::strcmp(argv[i], "--device")) g_device = std::atoi(argv[i + 1]);
         else if (!std::strcmp(argv[i], "--max-views")) max_views = (size_t)std::atoi(argv[i + 1]);
@@ -384,7 +414,7 @@ int main(int argc, char **argv)
         std::cerr << "acmmp_b200: " << e.what() << std::endl;
         return 1;
     }
-    std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"views\": " << num_images << ", \"wall_s\": " << now_s() - t_start << ", \"kernel_ms\": " << g_gpu_ms
+    std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << now_s() - t_start << ", \"kernel_ms\": " << g_gpu_ms
               << ", \"prior_cpu_s\": " << g_prior_s << "}" << std::endl;
     return 0;
 }

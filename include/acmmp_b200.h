@@ -151,6 +151,24 @@ int acmmp_result_host(acmmp_ctx *ctx, const float **planes4, const float **costs
  * planar_prior like SetPlanarPriorParams. */
 int acmmp_set_planar_prior_inputs(acmmp_ctx *ctx, const float *plane_params4, int n_planes, const float *masks);
 
+/* The planar-prior stage on the device.  The reference runs it on the CPU between the
+ * photometric and the prior stage; with these two calls only the Delaunay triangulation stays on the host.
+ *
+ * acmmp_support_points replaces ACMMP::GetSupportPoints (ACMMP.cpp:904-930) on the costs of the state on the device
+ * (after acmmp_run_patch_match[_resident]): per 5x5 cell the pixel of least cost if that cost is below 0.1.  xy
+ * receives (x, y) int32 pairs in the reference's order (cell columns outer, rows inner), *n their number;
+ * capacity is in points.
+ *
+ * acmmp_planar_prior_from_triangles replaces the rest of main.cpp:113-185 + CudaPlanarPriorInitialization
+ * (ACMMP.cpp:847-867): tri_xy holds n_tri triangles, six int32 each (x1 y1 x2 y2 x3 y3, every vertex inside the
+ * image), in the order their 1-based ids are assigned.  Per triangle the plane through the three lifted vertices
+ * (GetPriorPlaneParams, ACMMP.cpp:956-989; depths = the state on the device) and the reference's barycentric
+ * stepping rasteriser (main.cpp:153-159; a later triangle overwrites an earlier one); per pixel the depth-range
+ * test of main.cpp:168-181 (GetDepthFromPlaneParam, ACMMP.cpp:991-1011).  Leaves the prior inputs on the device and
+ * sets planar_prior like SetPlanarPriorParams.  PINHOLE results are bit-identical to the CPU stage. */
+int acmmp_support_points(acmmp_ctx *ctx, int32_t *xy, int capacity, int *n);
+int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int n_tri);
+
 /* The reference seeds cuRAND XORWOW with clock64() per thread (ACMMP.cu:684); here the seed is
  * explicit: state(pixel) = curand_init(seed, subsequence = y, offset = x). */
 int acmmp_set_seed(acmmp_ctx *ctx, uint64_t seed);

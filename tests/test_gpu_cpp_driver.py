@@ -54,35 +54,44 @@ def test_cpp_driver_runs_the_reference_schedule_on_a_dense_folder(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cpp_driver_resident_schedule_writes_the_same_maps_as_the_file_chained_one(tmp_path):
+def test_cpp_driver_resident_schedule_and_gpu_prior_write_the_same_maps_as_the_file_chained_one(tmp_path):
     """`--resident 1` (stage state, JBU hand-over and neighbour depth maps stay on the device, images
-    are read once per level) runs the same kernels on the same inputs in the same order as the reference's file-chained
-    schedule, so the final maps must be IDENTICAL bit for bit -- a size-independent property, no tolerance."""
+    are read once per level) and `--gpu-prior 1` (N2: support points, plane fit, rasteriser and depth-range test of the
+    planar-prior stage on the device, written with round-to-nearest intrinsics in the host code's evaluation order)
+    run the same arithmetic on the same inputs in the same order as the reference's file-chained schedule with its CPU
+    prior stage, so the final maps must be IDENTICAL bit for bit -- a size-independent property, no tolerance."""
     import shutil
     from acmmp_b200 import synth
     assert DRIVER.exists(), "build the host side first (__graft_entry__.build())"
     scene = synth.make_pinhole_scene(n_views=4, width=1100, height=820, focal=950.0, seed=5)
-    a, b = tmp_path / "files", tmp_path / "resident"
-    a.mkdir()
-    synth.write_dense_folder(scene, str(a), pgm=True)
-    shutil.copytree(a, b)
-    out = {}
-    for folder, flag in ((a, "0"), (b, "1")):
-        r = subprocess.run([str(DRIVER), str(folder), "--seed", "11", "--resident", flag], capture_output=True, text=True, timeout=900)
+    base = tmp_path / "files"
+    base.mkdir()
+    synth.write_dense_folder(scene, str(base), pgm=True)
+    variants = {"files": ("0", "0"), "resident": ("1", "0"), "files_gpu_prior": ("0", "1"), "resident_gpu_prior": ("1", "1")}
+    folders, out = {}, {}
+    for name in variants:
+        folders[name] = base if name == "files" else tmp_path / name
+        if name != "files":
+            shutil.copytree(base, folders[name])
+    for name, (resident, gpu_prior) in variants.items():
+        r = subprocess.run([str(DRIVER), str(folders[name]), "--seed", "11", "--resident", resident, "--gpu-prior", gpu_prior],
+                           capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-        out[flag] = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out["0"]["mode"] == "files" and out["1"]["mode"] == "resident", out
-    res = {"files": out["0"], "resident": out["1"]}
-    for v in range(4):
-        for name in ("depths.dmb", "depths_geom.dmb", "normals.dmb", "costs.dmb"):
-            x = _read_dmb(a / "ACMMP" / ("2333_%08d" % v) / name)
-            y = _read_dmb(b / "ACMMP" / ("2333_%08d" % v) / name)
-            assert x.shape == y.shape, (v, name)
-            # bit patterns: costs hold NaN where no view was selected (0 / 0, as in the reference), and NaN != NaN
-            res[f"view{v}_{name}_identical"] = bool(np.array_equal(x.view(np.uint32), y.view(np.uint32)))
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+        assert out[name]["mode"] == ("resident" if resident == "1" else "files") and out[name]["gpu_prior"] == int(gpu_prior), out[name]
+    res = dict(out)
+    for name in variants:
+        if name == "files":
+            continue
+        for v in range(4):
+            for dmb in ("depths.dmb", "depths_geom.dmb", "normals.dmb", "costs.dmb"):
+                x = _read_dmb(folders["files"] / "ACMMP" / ("2333_%08d" % v) / dmb)
+                y = _read_dmb(folders[name] / "ACMMP" / ("2333_%08d" % v) / dmb)
+                assert x.shape == y.shape, (name, v, dmb)
+                # bit patterns: costs hold NaN where no view was selected (0 / 0, as in the reference), and NaN != NaN
+                res[f"{name}_view{v}_{dmb}_identical"] = bool(np.array_equal(x.view(np.uint32), y.view(np.uint32)))
     util.dump("cpp_driver_resident", res)
-    for v in range(4):
-        for name in ("depths.dmb", "depths_geom.dmb", "normals.dmb", "costs.dmb"):
-            assert res[f"view{v}_{name}_identical"], res
-    # wall times of both schedules are in the metrics dump (process start-up and the page cache dominate at this size:
-    # not asserted)
+    bad = [k for k, v in res.items() if k.endswith("_identical") and not v]
+    assert not bad, bad
+    # wall times and CPU-side prior times of the four schedules are in the metrics dump (process start-up and the page
+    # cache dominate the wall time at this size: not asserted)
