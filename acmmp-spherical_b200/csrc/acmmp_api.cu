@@ -645,8 +645,8 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
         CK(cudaMemsetAsync(ctx->costs, 0, sizeof(float) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->pre_costs, 0, sizeof(float) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->selected_views, 0, sizeof(uint32_t) * npx, ctx->stream));
-        CK(phmalloc(ctx, &ctx->planes_host, sizeof(float4) * npx));
-        CK(phmalloc(ctx, &ctx->costs_host, sizeof(float) * npx));
+        // the pinned result buffers are allocated on the first download (ensure_host_result): a resident chain that
+        // never brings a level's result to the host does not pay 136 MB of cudaMallocHost per level
         typedef TileGeom<kPassTW, kPassTH> TGp;
         typedef TileGeom<kTpTW, kTpTH> TGt;
         int rc = make_tmap(ctx, &ctx->tmap_pass, TGp::PW, TGp::RH);
@@ -1282,6 +1282,14 @@ int acmmp_synchronize(acmmp_ctx *ctx)
     return collect_timings(ctx);
 }
 
+static int ensure_host_result(acmmp_ctx *ctx)
+{
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    if (!ctx->planes_host) CK(phmalloc(ctx, &ctx->planes_host, sizeof(float4) * npx));
+    if (!ctx->costs_host) CK(phmalloc(ctx, &ctx->costs_host, sizeof(float) * npx));
+    return ACMMP_OK;
+}
+
 static int run_stage(acmmp_ctx *ctx, bool download)
 {
     int rc = do_init(ctx);
@@ -1294,6 +1302,7 @@ static int run_stage(acmmp_ctx *ctx, bool download)
     ctx->have_result = false;
     if (download) {
         const size_t npx = (size_t)ctx->W * ctx->H;
+        { const int rc_h = ensure_host_result(ctx); if (rc_h) return rc_h; }
         CK(cudaMemcpyAsync(ctx->planes_host, ctx->planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->costs_host, ctx->costs, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -1313,6 +1322,7 @@ int acmmp_download_result(acmmp_ctx *ctx)
     if (!ctx || !ctx->planes) return ACMMP_E_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)ctx->W * ctx->H;
+    { const int rc_h = ensure_host_result(ctx); if (rc_h) return rc_h; }
     CK(cudaMemcpyAsync(ctx->planes_host, ctx->planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->costs_host, ctx->costs, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
