@@ -1175,7 +1175,8 @@ int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int
         CK(cudaMemcpyAsync(tri_dev, tri_xy, sizeof(int) * 6 * (size_t)n_tri, cudaMemcpyHostToDevice, ctx->stream));
         k_tri_planes<<<(n_tri + 255) / 256, 256, 0, ctx->stream>>>(tri_dev, n_tri, ctx->planes, cam, params_dev);
         k_tri_raster<<<(n_tri + 127) / 128, 128, 0, ctx->stream>>>(tri_dev, n_tri, ctx->W, mask_dev);
-        ctx->launches += 2;
+        k_tri_raster_long<<<(n_tri + 3) / 4, 128, 0, ctx->stream>>>(tri_dev, n_tri, ctx->W, mask_dev);
+        ctx->launches += 3;
     }
     k_prior_finish<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(mask_dev, params_dev, cam, ctx->prior_planes, ctx->plane_masks);
     ctx->launches++;

@@ -1348,31 +1348,67 @@ k_tri_planes(const int *__restrict__ tri, const int n_tri, const float4 *__restr
     params[t] = make_float4((float)__ddiv_rn(nx, norm), (float)__ddiv_rn(ny, norm), (float)__ddiv_rn(nz, norm), (float)__ddiv_rn(w, norm));
 }
 
-// The reference's barycentric stepping rasteriser (main.cpp:153-159), one triangle per thread; the sequential loop
-// lets a later triangle overwrite an earlier one, i.e. the largest id wins: atomicMax.
-__global__ void __launch_bounds__(128)
-k_tri_raster(const int *__restrict__ tri, const int n_tri, const int W, uint32_t *__restrict__ mask)
+// The reference's barycentric stepping rasteriser (main.cpp:153-159); the sequential loop lets a later triangle
+// overwrite an earlier one, i.e. the largest id wins: atomicMax.  Triangles up to kRasterSmall pixels of longest edge
+// (the bulk: support points sit on a 5-pixel grid) take one thread each; the few long ones along image borders and
+// across texture-less regions (10^5 .. 10^6 steps each -- on one thread they dominated the stage) take a warp each:
+// lane l walks the outer-loop iterations l, l + 32, ...  The outer variable is the reference's running float sum
+// (p += step), so a lane reaches its iteration by the same sequence of additions.
+constexpr float kRasterSmall = 48.0f;
+
+struct RasterTri {
+    float fx1, fx2, fy1, fy2, step, max_edge;
+    double dx3, dy3;
+};
+__device__ __forceinline__ RasterTri raster_setup(const int *__restrict__ tri, const int t)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tri) return;
     const int x1 = tri[6 * t], y1 = tri[6 * t + 1], x2 = tri[6 * t + 2], y2 = tri[6 * t + 3], x3 = tri[6 * t + 4], y3 = tri[6 * t + 5];
     // std::sqrt(std::pow(int, 2) + std::pow(int, 2)) in double, stored to float
     const float L01 = (float)__dsqrt_rn((double)((long long)(x1 - x2) * (x1 - x2) + (long long)(y1 - y2) * (y1 - y2)));
     const float L02 = (float)__dsqrt_rn((double)((long long)(x1 - x3) * (x1 - x3) + (long long)(y1 - y3) * (y1 - y3)));
     const float L12 = (float)__dsqrt_rn((double)((long long)(x2 - x3) * (x2 - x3) + (long long)(y2 - y3) * (y2 - y3)));
-    const float max_edge_length = fmaxf(L01, fmaxf(L02, L12));
-    const float step = (float)__ddiv_rn(1.0, (double)max_edge_length);
-    const float fx1 = (float)x1, fx2 = (float)x2, fy1 = (float)y1, fy2 = (float)y2;
-    const double dx3 = (double)x3, dy3 = (double)y3;
-    for (float p = 0; (double)p < 1.0; p = __fadd_rn(p, step)) {
-        const double one_minus_p = __dsub_rn(1.0, (double)p);
-        for (float q = 0; (double)q < one_minus_p; q = __fadd_rn(q, step)) {
-            // p * x1 + q * x2: float;  (1.0 - p - q) * x3: double;  sum in double, truncated
-            const double r = __dsub_rn(one_minus_p, (double)q);
-            const int x = __double2int_rz(__dadd_rn((double)__fadd_rn(__fmul_rn(p, fx1), __fmul_rn(q, fx2)), __dmul_rn(r, dx3)));
-            const int y = __double2int_rz(__dadd_rn((double)__fadd_rn(__fmul_rn(p, fy1), __fmul_rn(q, fy2)), __dmul_rn(r, dy3)));
-            atomicMax(mask + (size_t)y * W + x, (uint32_t)(t + 1));
-        }
+    RasterTri r;
+    r.max_edge = fmaxf(L01, fmaxf(L02, L12));
+    r.step = (float)__ddiv_rn(1.0, (double)r.max_edge);
+    r.fx1 = (float)x1; r.fx2 = (float)x2; r.fy1 = (float)y1; r.fy2 = (float)y2;
+    r.dx3 = (double)x3; r.dy3 = (double)y3;
+    return r;
+}
+// the inner loop of one outer iteration
+__device__ __forceinline__ void raster_row(const RasterTri &r, const float p, const int W, const uint32_t id, uint32_t *__restrict__ mask)
+{
+    const double one_minus_p = __dsub_rn(1.0, (double)p);
+    for (float q = 0; (double)q < one_minus_p; q = __fadd_rn(q, r.step)) {
+        // p * x1 + q * x2: float;  (1.0 - p - q) * x3: double;  sum in double, truncated
+        const double w3 = __dsub_rn(one_minus_p, (double)q);
+        const int x = __double2int_rz(__dadd_rn((double)__fadd_rn(__fmul_rn(p, r.fx1), __fmul_rn(q, r.fx2)), __dmul_rn(w3, r.dx3)));
+        const int y = __double2int_rz(__dadd_rn((double)__fadd_rn(__fmul_rn(p, r.fy1), __fmul_rn(q, r.fy2)), __dmul_rn(w3, r.dy3)));
+        atomicMax(mask + (size_t)y * W + x, id);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_tri_raster(const int *__restrict__ tri, const int n_tri, const int W, uint32_t *__restrict__ mask)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tri) return;
+    const RasterTri r = raster_setup(tri, t);
+    if (r.max_edge > kRasterSmall) return;               // k_tri_raster_long
+    for (float p = 0; (double)p < 1.0; p = __fadd_rn(p, r.step)) raster_row(r, p, W, (uint32_t)(t + 1), mask);
+}
+
+__global__ void __launch_bounds__(128)
+k_tri_raster_long(const int *__restrict__ tri, const int n_tri, const int W, uint32_t *__restrict__ mask)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= n_tri) return;
+    const RasterTri r = raster_setup(tri, t);
+    if (!(r.max_edge > kRasterSmall)) return;
+    float p = 0;
+    for (int i = 0; i < lane && (double)p < 1.0; ++i) p = __fadd_rn(p, r.step);
+    while ((double)p < 1.0) {
+        raster_row(r, p, W, (uint32_t)(t + 1), mask);
+        for (int i = 0; i < 32 && (double)p < 1.0; ++i) p = __fadd_rn(p, r.step);
     }
 }
 

@@ -17,6 +17,7 @@
 #include <iostream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <sys/stat.h>
@@ -35,7 +36,14 @@ double g_gpu_ms = 0.0, g_prior_s = 0.0;
 // wall-clock attribution of the resident schedule (printed in the summary): image load + scaling, view upload / level
 // change (incl. context creation), stage runs (kernels + waits + downloads), depth-map export, result output
 double g_t_load = 0.0, g_t_views = 0.0, g_t_run = 0.0, g_t_export = 0.0, g_t_output = 0.0, g_t_join = 0.0;
-double g_t_run_worker = 0.0, g_gpu_ms_worker = 0.0;       // written by the worker thread only (one at a time)
+double g_t_sweep1 = 0.0, g_t_geom = 0.0;   // totals: first sweep, geometric sweeps
+
+std::mutex g_prior_mutex;
+void add_prior_s(double dt)      // the CPU prior stages of two views may overlap on worker threads
+{
+    std::lock_guard<std::mutex> lock(g_prior_mutex);
+    g_prior_s += dt;
+}
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -128,7 +136,7 @@ void PlanarPriorStage(ACMMP &acmmp, const cv::Mat_<float> &depths, cv::Mat_<floa
             }
         }
     }
-    g_prior_s += now_s() - t0;
+    add_prior_s(now_s() - t0);
 }
 
 // The same stage with everything but the triangulation on the device: support points
@@ -148,7 +156,7 @@ void PlanarPriorStageGpu(ACMMP &acmmp)
     for (const auto &triangle : triangles)
         if (imageRC.contains(triangle.pt1) && imageRC.contains(triangle.pt2) && imageRC.contains(triangle.pt3)) inside.push_back(triangle);
     acmmp.CudaPlanarPriorFromTriangles(inside);
-    g_prior_s += now_s() - t0;
+    add_prior_s(now_s() - t0);
 }
 
 // main.cpp:73-210
@@ -262,7 +270,6 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         if (ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) full_px[i] = (size_t)cols * rows;
     }
     bool first_level = true;
-    std::shared_future<void> tail;                      // the worker chain of the current sweep
     while (max_num_downscale >= 0) {
         std::cout << "Scale: " << max_num_downscale << std::endl;
         for (auto &problem : problems) {
@@ -280,6 +287,47 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].cur_image_size, level_image[i], level_camera[i]);
         g_t_load += now_s() - tp;
 
+        struct PriorJob {
+            std::future<void> done;
+            std::vector<cv::Point> support;
+            std::vector<Triangle> inside;                  // --gpu-prior 1: triangles inside the image, id order
+            cv::Mat_<float> mask_tri;                      // --gpu-prior 0: the CPU stage's outputs
+            std::vector<float4> planeParams_tri;
+            double host_s = 0.0;
+        };
+        std::vector<std::unique_ptr<PriorJob>> pending(num_images);
+        auto finish_view = [&](const size_t v) {
+            ACMMP &a = *objs[v];
+            double tw = now_s();
+            pending[v]->done.get();                        // rethrows a worker exception
+            g_t_join += now_s() - tw;
+            tw = now_s();
+            if (g_gpu_prior) {
+                a.CudaPlanarPriorFromTriangles(pending[v]->inside);
+                add_prior_s(pending[v]->host_s + (now_s() - tw));
+            } else {
+                a.CudaPlanarPriorInitialization(pending[v]->planeParams_tri, pending[v]->mask_tri);
+            }
+            pending[v].reset();
+            const int width = a.GetReferenceImageWidth(), height = a.GetReferenceImageHeight();
+            tw = now_s();
+            a.RunPatchMatchResident(finest);                                     // finest level: depths.dmb is an output
+            g_t_run += now_s() - tw;
+            float tt[8];
+            a.GetTimings(tt);
+            g_gpu_ms += tt[0] + tt[1] + tt[2];
+            tw = now_s();
+            if (finest) {
+                final_prior_depth[v] = cv::Mat_<float>(height, width);
+                for (int k = 0; k < width * height; ++k) final_prior_depth[v].ptr()[k] = a.GetPlaneHypothesis(k).w;
+            }
+            g_t_output += now_s() - tw;
+            tw = now_s();
+            dmap[v].fit(width, height, full_px[v]);
+            a.ExportDepthDevice(dmap[v].ptr);
+            g_t_export += now_s() - tw;
+        };
+        const double t_sweep1 = now_s();
         for (size_t i = 0; i < num_images; ++i) {                                // photometric + prior stage
             const Problem &problem = problems[i];
             std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << "..." << std::endl;
@@ -303,47 +351,42 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             float t[8];
             acmmp.GetTimings(t);
             g_gpu_ms += t[0] + t[1] + t[2];
-            // Second half of the view's sweep -- prior stage (its triangulation is host work), prior-stage PatchMatch,
-            // depth-map export -- on a worker thread, one view at a time and in view order, while this thread goes on
-            // with the next view's photometric stage: the host triangulation of view i hides behind the kernels of
-            // view i + 1.  Each view has its own object / context / stream; the geometric sweeps start after the join.
+            // The host part of the planar-prior stage of view i (the Delaunay triangulation; with --gpu-prior 0 the whole
+            // CPU stage) runs on a worker thread while this thread -- which issues ALL device work, in a fixed order --
+            // goes on with the photometric stage of view i + 1; view i is finished (prior upload, prior-stage
+            // PatchMatch, depth export) one iteration later.  (Device work from two threads would queue behind each
+            // other's persistent kernels: a k_pass launch holds every SM for its ~20 ms.)
+            pending[i].reset(new PriorJob());
+            PriorJob *job = pending[i].get();
             ACMMP *obj = objs[i].get();
-            DeviceMap *dm = &dmap[i];
-            cv::Mat_<float> *fpd = &final_prior_depth[i];
-            const size_t reserve_px = full_px[i];
-            std::shared_future<void> prev = tail;
-            tail = std::async(std::launch::async, [obj, dm, fpd, reserve_px, finest, prev]() {
-                if (prev.valid()) prev.get();
-                cudaSetDevice(g_device);
-                ACMMP &a = *obj;
-                const int width = a.GetReferenceImageWidth(), height = a.GetReferenceImageHeight();
-                if (g_gpu_prior) {
-                    PlanarPriorStageGpu(a);
-                } else {
+            if (g_gpu_prior) {
+                const double t0 = now_s();
+                acmmp.SetPlanarPriorParams();
+                acmmp.GetSupportPointsDevice(job->support);
+                add_prior_s(now_s() - t0);
+                job->done = std::async(std::launch::async, [job, obj]() {
+                    const double t1 = now_s();
+                    const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
+                    const cv::Rect imageRC(0, 0, width, height);
+                    const auto triangles = obj->DelaunayTriangulation(imageRC, job->support);
+                    job->inside.reserve(triangles.size());
+                    for (const auto &tr : triangles)
+                        if (imageRC.contains(tr.pt1) && imageRC.contains(tr.pt2) && imageRC.contains(tr.pt3)) job->inside.push_back(tr);
+                    job->host_s = now_s() - t1;
+                });
+            } else {
+                job->done = std::async(std::launch::async, [job, obj]() {
+                    const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
                     cv::Mat_<float> depths(height, width);
-                    for (int k = 0; k < width * height; ++k) depths.ptr()[k] = a.GetPlaneHypothesis(k).w;
-                    cv::Mat_<float> mask_tri;
-                    std::vector<float4> planeParams_tri;
-                    PlanarPriorStage(a, depths, mask_tri, planeParams_tri);
-                    a.CudaPlanarPriorInitialization(planeParams_tri, mask_tri);
-                }
-                double tw = now_s();
-                a.RunPatchMatchResident(finest);                                 // finest level: depths.dmb is an output
-                g_t_run_worker += now_s() - tw;
-                float tt[8];
-                a.GetTimings(tt);
-                g_gpu_ms_worker += tt[0] + tt[1] + tt[2];
-                if (finest) {
-                    *fpd = cv::Mat_<float>(height, width);
-                    for (int k = 0; k < width * height; ++k) fpd->ptr()[k] = a.GetPlaneHypothesis(k).w;
-                }
-                dm->fit(width, height, reserve_px);
-                a.ExportDepthDevice(dm->ptr);
-            }).share();
+                    for (int k = 0; k < width * height; ++k) depths.ptr()[k] = obj->GetPlaneHypothesis(k).w;
+                    PlanarPriorStage(*obj, depths, job->mask_tri, job->planeParams_tri);        // adds its time to g_prior_s
+                });
+            }
+            if (i > 0) finish_view(i - 1);
         }
-        tp = now_s();
-        if (tail.valid()) tail.get();                  // rethrows a worker exception
-        g_t_join += now_s() - tp;
+        if (num_images > 0) finish_view(num_images - 1);
+        g_t_sweep1 += now_s() - t_sweep1;
+        const double t_geom = now_s();
         for (int geom_iter = 0; geom_iter < 2; ++geom_iter) {                    // geometric sweeps
             const bool multi_geometry = geom_iter > 0;
             for (size_t i = 0; i < num_images; ++i) {
@@ -393,6 +436,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 g_t_output += now_s() - tg;
             }
         }
+        g_t_geom += now_s() - t_geom;
         first_level = false;
         max_num_downscale--;
     }
@@ -461,9 +505,8 @@ int main(int argc, char **argv)
         std::cerr << "acmmp_b200: " << e.what() << std::endl;
         return 1;
     }
-    std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << now_s() - t_start << ", \"kernel_ms\": " << g_gpu_ms + g_gpu_ms_worker
+    std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << now_s() - t_start << ", \"kernel_ms\": " << g_gpu_ms
               << ", \"prior_cpu_s\": " << g_prior_s << ", \"load_s\": " << g_t_load << ", \"views_s\": " << g_t_views << ", \"run_s\": " << g_t_run
-              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"worker_run_s\": " << g_t_run_worker
-              << ", \"join_s\": " << g_t_join << "}" << std::endl;
+              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"sweep1_s\": " << g_t_sweep1 << ", \"geom_s\": " << g_t_geom << "}" << std::endl;
     return 0;
 }

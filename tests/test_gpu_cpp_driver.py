@@ -95,3 +95,45 @@ def test_cpp_driver_resident_schedule_and_gpu_prior_write_the_same_maps_as_the_f
     assert not bad, bad
     # wall times and CPU-side prior times of the four schedules are in the metrics dump (process start-up and the page
     # cache dominate the wall time at this size: not asserted)
+
+
+@pytest.mark.gpu
+def test_cpp_driver_on_an_equirectangular_dense_folder(tmp_path):
+    """The fork's SPHERE camera model through the on-disk contract (`intrinsic / SPHERE / f cx cy` cam files,
+    reference ACMMP.cpp:172-192; BASELINE config 4 at a small size, two pyramid levels): the file-chained and the
+    GPU-resident schedule write bit-identical maps; the device prior stage (its sin / cos differ from the host's in the
+    last bit) agrees with them within the full-map tolerance; depths match the ground truth."""
+    import shutil
+    from acmmp_b200 import synth
+    assert DRIVER.exists(), "build the host side first (__graft_entry__.build())"
+    scene = synth.make_sphere_scene(n_views=4, width=1200, height=600, seed=4)
+    base = tmp_path / "files"
+    base.mkdir()
+    synth.write_dense_folder(scene, str(base), pgm=True)
+    variants = {"files": ("0", "0"), "resident": ("1", "0"), "resident_gpu_prior": ("1", "1")}
+    folders, res = {}, {}
+    for name, (resident, gpu_prior) in variants.items():
+        folders[name] = base if name == "files" else tmp_path / name
+        if name != "files":
+            shutil.copytree(base, folders[name])
+        r = subprocess.run([str(DRIVER), str(folders[name]), "--seed", "3", "--resident", resident, "--gpu-prior", gpu_prior],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    for v in range(4):
+        ref = {d: _read_dmb(folders["files"] / "ACMMP" / ("2333_%08d" % v) / d) for d in ("depths_geom.dmb", "normals.dmb", "costs.dmb")}
+        for d, x in ref.items():
+            y = _read_dmb(folders["resident"] / "ACMMP" / ("2333_%08d" % v) / d)
+            res[f"resident_view{v}_{d}_identical"] = bool(x.shape == y.shape and np.array_equal(x.view(np.uint32), y.view(np.uint32)))
+        z = _read_dmb(folders["resident_gpu_prior"] / "ACMMP" / ("2333_%08d" % v) / "depths_geom.dmb")
+        x = ref["depths_geom.dmb"]
+        res[f"gpu_prior_view{v}_within_1pct_of_files"] = float((np.abs(z - x) <= 0.01 * np.abs(x)).mean())
+        gt = scene.depths_gt[v]
+        assert x.shape == gt.shape
+        res[f"view{v}_within_1pct_of_gt"] = float((np.abs(x - gt) / gt <= 0.01)[8:-8, 8:-8].mean())
+    util.dump("cpp_driver_sphere", res)
+    for v in range(4):
+        for d in ("depths_geom.dmb", "normals.dmb", "costs.dmb"):
+            assert res[f"resident_view{v}_{d}_identical"], res
+        assert res[f"gpu_prior_view{v}_within_1pct_of_files"] > 0.99, res
+        assert res[f"view{v}_within_1pct_of_gt"] > 0.85, res

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--height", type=int, default=2130)
     ap.add_argument("--focal", type=float, default=2800.0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--skip-files", action="store_true", help="only the resident schedules (no bit comparison)")
     a = ap.parse_args()
     from acmmp_b200 import synth
     scene = synth.make_pinhole_scene(n_views=a.views, width=a.width, height=a.height, focal=a.focal, seed=2)
@@ -42,6 +43,8 @@ def main():
     variants = {"files": ("0", "0"), "resident": ("1", "0"), "resident_gpu_prior": ("1", "1")}
     res = {"views": a.views, "width": a.width, "height": a.height, "src_views": len(scene.pairs[0][1])}
     folders = {}
+    if a.skip_files:
+        variants.pop("files")
     for name, (resident, gpu_prior) in variants.items():
         folders[name] = base if name == "files" else tmp / name
         if name != "files":
@@ -54,6 +57,8 @@ def main():
         res[name]["process_wall_s"] = time.time() - t0
         res[name]["s_per_view"] = res[name]["wall_s"] / a.views
     for name in ("resident", "resident_gpu_prior"):
+        if a.skip_files:
+            break
         same = True
         for v in range(a.views):
             for dmb in ("depths.dmb", "depths_geom.dmb", "normals.dmb", "costs.dmb"):
