@@ -32,7 +32,7 @@ template <int MODEL, int TW, int TH, int NPIX, int NT>
 struct SmemLayout {
     typedef TileGeom<TW, TH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
-    size_t off_tile, off_aux, off_wr, off_rr, off_tq, off_vc, off_ncc, off_bar, off_cost, off_vw, off_probs, total;
+    size_t off_tile, off_aux, off_wr, off_rr, off_tq, off_vc, off_ncc, off_bar, off_cost, off_vw, off_probs, off_sums, total;
     size_t tile_stride, aux_stride;     // between the buffers of a multi-buffered tile (k_pass: 2)
     __host__ __device__ SmemLayout(int nsrc, int cost_rows, int group_rows, int tq_entries = kTaps, int nbuf = 1)
     {
@@ -51,6 +51,8 @@ struct SmemLayout {
         off_cost = o; o += sizeof(float) * (size_t)cost_rows * nvp;
         off_vw = o; o += sizeof(float) * (size_t)group_rows * nvp;
         off_probs = o; o += sizeof(float) * (size_t)group_rows * nvp;
+        o = align_up(o, 16);
+        off_sums = o; o += sizeof(float4) * (size_t)group_rows;
         total = align_up(o, 16);
     }
 };
@@ -398,6 +400,35 @@ __device__ __forceinline__ float4 shfl_plane(const unsigned gmask, const float4 
     return r;
 }
 
+// The (pixel, selected view) pairs of the four pixels of a warp, dealt to its eight quads: pair j = 8 r + (lane >> 2)
+// in round r.  With each pixel group working through its own selected views two at a time (one per quad) the warp ran
+// max_i ceil(n_i / 2) rounds with idle quads wherever a pixel has fewer views than its busiest neighbour; dealt across
+// the warp it runs ceil(sum_i n_i / 8).  A quad that serves another group's pixel takes that pixel's weight tables,
+// tap-depth columns, reference-side sums and cost rows from shared memory (all four pixels sit in one tile row).
+struct WarpPairs {
+    uint32_t m[4];         // selected-view masks of the warp's four pixel groups (0 = group takes no part)
+    int pre[5];            // prefix sums of their pair counts
+    __device__ __forceinline__ void build(const uint32_t my_mask)
+    {
+        pre[0] = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            m[g] = __shfl_sync(0xffffffffu, my_mask, 8 * g);
+            pre[g + 1] = pre[g] + __popc(m[g]);
+        }
+    }
+    // pair j -> owner group and source view; false when j is past the end
+    __device__ __forceinline__ bool get(const int j, int &g, int &vsel) const
+    {
+        if (j >= pre[4]) return false;
+        g = (j >= pre[1]) + (j >= pre[2]) + (j >= pre[3]);
+        const uint32_t mg = g == 0 ? m[0] : (g == 1 ? m[1] : (g == 2 ? m[2] : m[3]));
+        const int base = g == 0 ? pre[0] : (g == 1 ? pre[1] : (g == 2 ? pre[2] : pre[3]));
+        vsel = (int)__fns(mg, 0, j - base + 1);
+        return true;
+    }
+};
+
 // MODE: which stage variant this instance serves -- the reference's flag combinations are exclusive
 // (main.cpp:427-473: prior stages have geom_consistency off, geometric stages have planar_prior off), and a
 // specialised instance carries only its own code (the instruction cache is a measured bottleneck of this kernel).
@@ -431,6 +462,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     float *cost_all = reinterpret_cast<float *>(smem + L.off_cost);
     float *vw_all = reinterpret_cast<float *>(smem + L.off_vw);
     float *probs_all = reinterpret_cast<float *>(smem + L.off_probs);
+    float4 *sums_all = reinterpret_cast<float4 *>(smem + L.off_sums);      // per pixel slot: (Sw, Swr, Swrr, -)
 
     const int W = fc.W, H = fc.H;
     const int tid = threadIdx.x;
@@ -512,7 +544,8 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     }
 
     const int yy_ = y0 + (g >> 2);
-    const int xx_ = x0 + 2 * (g & 3) + ((yy_ + colour) & 1);
+    const int xpar = (yy_ + colour) & 1;               // x offset of the active colour in this tile row
+    const int xx_ = x0 + 2 * (g & 3) + xpar;
     // Groups that fall outside the image stay alive (clamped coordinates, nothing stored) so that the
     // warp walks the view loops in lock step; see ncc_views.
     const bool valid = xx_ < W && yy_ < H;
@@ -593,6 +626,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
 
     __syncwarp(FULL);
     full_sums<WRS>(wr, rr, px);
+    if (gl == 0) sums_all[g] = make_float4(px.Sw, px.Swr, px.Swrr, 0.f);
 
     // ---- phase A: 8 neighbour hypotheses x all views (ACMMP.cu:981-1142) ---------------------
     // quad Q of the group evaluates candidates 4Q..4Q+3 (the planes its own four lanes hold), tap-split
@@ -752,24 +786,32 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     const float4 cur_plane = planes_in[center];
     float cost_now = 0.0f;
     {
-        // quad Q takes the selected views Q, Q+2, ... (tap-split inside the quad)
+        // the warp's (pixel, selected view) pairs, one per quad and round (WarpPairs); tap-split inside the quad
         quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, cur_plane, q, tq);
         const int n_sel = valid ? __popc(temp_selected_views) : 0;
-        int rounds = (n_sel + 1) >> 1;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(FULL, rounds, off));
+        WarpPairs wp;
+        wp.build(valid ? temp_selected_views : 0u);
+        __syncwarp(FULL);                                  // every group's tap depths and sums are in shared memory
+        const int Qw = lane >> 2, g_own = lane >> 3;
+        const int rounds = (wp.pre[4] + 7) >> 3;
         float *row_now = cost_grp + 5 * nvp;
         for (int r = 0; r < rounds; ++r) {
-            const int idx = 2 * r + Q;
-            const bool want = idx < n_sel;
-            const int vsel = want ? (int)__fns(temp_selected_views, 0, idx + 1) : 0;
+            int go = g_own, vsel = 0;
+            const bool want = wp.get(8 * r + Qw, go, vsel);
+            const int o = (tid >> 5) * 4 + go;             // pixel slot of the pair's owner
+            PixCtx po = px;                                // same tile row; x from the owner's (unclamped, valid) position
+            po.tx = 2 * go + xpar + kHalo;
+            po.dx = static_cast<float>(x0 + 2 * go + xpar) - fc.cx;
+            const float4 so = sums_all[o];
+            po.Sw = so.x; po.Swr = so.y; po.Swrr = so.z;
+            float *row_o = cost_all + (o * 8 + 5) * nvp;
             const ViewK c = load_view(s_ncc + vsel);
             FetchLayer fetch;
             fetch.tex = (cudaTextureObject_t)fc.tex_src;
             fetch.layer = vsel;
             quad_ncc<MODEL, 1, TG::RW, WRS, TQS>(
-                c, px, aux, wr, rr, tq, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
-                [&](const int, const float cst) { row_now[vsel] = cst; });
+                c, po, aux, wr_all + o, rr_all + o, tq_all + o * 8 + q, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
+                [&](const int, const float cst) { row_o[vsel] = cst; });
         }
         __syncwarp(FULL);
         // weight (and, in geometric mode, add the geometric term): lane k of the group takes the k-th selected
@@ -952,21 +994,29 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         }
         __syncwarp(FULL);
         const int n_sel = (do_refine && valid) ? __popc(temp_selected_views) : 0;
-        int rounds = (n_sel + 1) >> 1;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) rounds = max(rounds, __shfl_xor_sync(FULL, rounds, off));
+        WarpPairs wp;
+        wp.build((do_refine && valid) ? temp_selected_views : 0u);
+        const int Qw = lane >> 2, g_own = lane >> 3;
+        const int rounds = (wp.pre[4] + 7) >> 3;
         for (int r = 0; r < rounds; ++r) {
-            const int idx = 2 * r + Q;
-            const bool want = idx < n_sel;
-            const int vsel = want ? (int)__fns(temp_selected_views, 0, idx + 1) : 0;
+            int go = g_own, vsel = 0;
+            const bool want = wp.get(8 * r + Qw, go, vsel);
+            const int o = (tid >> 5) * 4 + go;             // pixel slot of the pair's owner
+            PixCtx po = px;                                // same tile row; x from the owner's (unclamped, valid) position
+            po.tx = 2 * go + xpar + kHalo;
+            po.dx = static_cast<float>(x0 + 2 * go + xpar) - fc.cx;
+            const float4 so = sums_all[o];
+            po.Sw = so.x; po.Swr = so.y; po.Swrr = so.z;
+            float *grp_o = cost_all + (o * 8) * nvp;
             const ViewK c = load_view(s_ncc + vsel);
             FetchLayer fetch;
             fetch.tex = (cudaTextureObject_t)fc.tex_src;
             fetch.layer = vsel;
+            // tap depths of the owner: hypotheses 0-2 in the columns of its first quad, 3-4 in those of its second
             quad_ncc<MODEL, 5, TG::RW, WRS, TQS>(
-                c, px, aux, wr, rr, tq, fetch, q, want ? 0x1Fu : 0u,
-                [&](const int h) { return (h < 3 ? h : h - 3) * kTqPerHyp * TQS + ((h < 3 ? 0 : 1) - Q) * 4; },
-                [&](const int h, const float cst) { cost_grp[h * nvp + vsel] = cst; });
+                c, po, aux, wr_all + o, rr_all + o, tq_all + o * 8 + q, fetch, q, want ? 0x1Fu : 0u,
+                [&](const int h) { return (h < 3 ? h : h - 3) * kTqPerHyp * TQS + (h < 3 ? 0 : 4); },
+                [&](const int h, const float cst) { grp_o[h * nvp + vsel] = cst; });
         }
         __syncwarp(FULL);
         if (kGeom) {
