@@ -83,7 +83,7 @@ _EXPORTS = [
     "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_download_state", "acmmp_upload_state",
-    "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_geom", "acmmp_probe_warp",
+    "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_ncc_quad", "acmmp_probe_geom", "acmmp_probe_warp",
     "acmmp_probe_initcost", "acmmp_last_timings", "acmmp_launch_count",
 ]
 
@@ -340,6 +340,13 @@ class Context:
         p = _f32(planes4)
         out = np.empty((self.H, self.W), np.float32)
         self._ck(self._l.acmmp_probe_ncc(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_ncc")
+        return out
+
+    def probe_ncc_quad(self, planes4, view):
+        """The same cost through quad_ncc, the form the checkerboard pass runs."""
+        p = _f32(planes4)
+        out = np.empty((self.H, self.W), np.float32)
+        self._ck(self._l.acmmp_probe_ncc_quad(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_ncc_quad")
         return out
 
     def probe_geom(self, planes4, view):

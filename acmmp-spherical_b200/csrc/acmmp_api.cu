@@ -525,6 +525,7 @@ int configure_kernels(acmmp_ctx *ctx)
         SETATTR((k_pass<kModelSphere, kModePhoto>)) SETATTR((k_pass<kModelSphere, kModePrior>)) SETATTR((k_pass<kModelSphere, kModeGeom>))
         SETATTR(k_random_init<kModelPinhole>) SETATTR(k_random_init<kModelSphere>)
         SETATTR(k_probe<kModelPinhole>) SETATTR(k_probe<kModelSphere>)
+        SETATTR(k_probe_quad<kModelPinhole>) SETATTR(k_probe_quad<kModelSphere>)
 #undef SETATTR
     });
     if (result != cudaSuccess) return fail(ctx, ACMMP_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(result));
@@ -881,6 +882,19 @@ int launch_probe(acmmp_ctx *ctx, int mode, int view, const float4 *planes_dev, f
     return ACMMP_OK;
 }
 
+template <int MODEL>
+int launch_probe_quad(acmmp_ctx *ctx, int view, const float4 *planes_dev, float *out)
+{
+    const FrameConst fc = frame_const(ctx);
+    dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
+    const size_t smem = SmemLayout<MODEL, kTpTW, kTpTH, kPqWRS, kPqNT>(fc.nsrc, 0, 0, kTqPerHyp).total;
+    if (smem > 227 * 1024) return fail(ctx, ACMMP_E_UNSUPPORTED, "k_probe_quad: too many source views for one SM's shared memory");
+    k_probe_quad<MODEL><<<grid, kPqNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp, view, planes_dev, out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return ACMMP_OK;
+}
+
 int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *out, float *out4, uint32_t *out_views)
 {
     int rc = check_ready(ctx);
@@ -898,8 +912,12 @@ int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *o
     CK(pmalloc(ctx, &dout, sizeof(float) * npx));
     CK(pmalloc(ctx, &dv, sizeof(uint32_t) * npx));
     CK(cudaMemcpyAsync(dp, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
-    rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe<kModelPinhole>(ctx, mode, view, dp, dout, do4, dv)
-                                                     : launch_probe<kModelSphere>(ctx, mode, view, dp, dout, do4, dv);
+    if (mode == 4)
+        rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe_quad<kModelPinhole>(ctx, view, dp, dout)
+                                                         : launch_probe_quad<kModelSphere>(ctx, view, dp, dout);
+    else
+        rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe<kModelPinhole>(ctx, mode, view, dp, dout, do4, dv)
+                                                         : launch_probe<kModelSphere>(ctx, mode, view, dp, dout, do4, dv);
     if (rc == ACMMP_OK) {
         if (out) CK(cudaMemcpyAsync(out, dout, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
         if (out4) CK(cudaMemcpyAsync(out4, do4, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1436,6 +1454,7 @@ int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_
 }
 
 int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 0, view, planes4, out, nullptr, nullptr); }
+int acmmp_probe_ncc_quad(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 4, view, planes4, out, nullptr, nullptr); }
 int acmmp_probe_geom(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 1, view, planes4, out, nullptr, nullptr); }
 int acmmp_probe_warp(acmmp_ctx *ctx, const float *planes4, int view, float *out4) { return run_probe(ctx, 2, view, planes4, nullptr, out4, nullptr); }
 int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint32_t *selected_views)

@@ -209,6 +209,53 @@ k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable 
 }
 
 // ------------------------------------------------------------------------------------------
+// probe of the NCC form k_pass runs: fixed plane per pixel, one source view, through quad_ncc (four lanes per pixel,
+// one hypothesis) with the same tables fill_weights / full_sums / quad_fill_depths build inside k_pass.
+// 16x8 pixel tile, 512 threads.
+// ------------------------------------------------------------------------------------------
+constexpr int kPqPix = kTpTW * kTpTH, kPqNT = 4 * kPqPix, kPqWRS = kPqPix + 8;
+
+template <int MODEL>
+__global__ void __launch_bounds__(kPqNT)
+k_probe_quad(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap, const int view,
+             const float4 *__restrict__ planes, float *__restrict__ out)
+{
+    typedef TileGeom<kTpTW, kTpTH> TG;
+    typedef typename AuxType<MODEL>::type AuxT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout<MODEL, kTpTW, kTpTH, kPqWRS, kPqNT> L(fc.nsrc, 0, 0, kTqPerHyp);
+    float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
+    AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
+    ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
+    NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
+
+    const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
+    stage_tile<MODEL, kTpTW, kTpTH, kPqNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
+
+    const int tid = threadIdx.x;
+    const int p = tid >> 2, q = tid & 3;               // pixel slot, lane of its quad
+    const int xx = x0 + (p % kTpTW), yy = y0 + (p / kTpTW);
+    const bool valid = xx < fc.W && yy < fc.H;
+    const int x = min(xx, fc.W - 1), y = min(yy, fc.H - 1);
+    const int center = y * fc.W + x;
+    PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
+    float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr) + p;
+    float *rr = reinterpret_cast<float *>(smem + L.off_rr) + p;
+    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + tid;
+    fill_weights<MODEL, TG::PW, kPqWRS>(fc, tile_r, px, wr, rr, q, 4);
+    __syncwarp(0xffffffffu);
+    full_sums<kPqWRS>(wr, rr, px);
+    quad_fill_depths<MODEL, TG::RW, kPqNT>(fc, aux, px, planes[center], q, tq);
+    __syncwarp(0xffffffffu);
+    const ViewK c = load_view(s_ncc + (view - 1));
+    FetchView fetch;
+    fetch.tex = (cudaTextureObject_t)nt.tex[view - 1];
+    quad_ncc<MODEL, 1, TG::RW, kPqWRS, kPqNT>(
+        c, px, aux, wr, rr, tq, fetch, q, valid ? 1u : 0u, [](const int) { return 0; }, [&](const int, const float cst) { out[center] = cst; });
+}
+
+// ------------------------------------------------------------------------------------------
 // RandomInitialization, ACMMP.cu:673-795
 // ------------------------------------------------------------------------------------------
 // SpatialGauss / RangeGauss, ACMMP.cu:175-185 (double precision inside, float in/out)

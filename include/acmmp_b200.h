@@ -237,6 +237,8 @@ float acmmp_last_jbu_ms(void);
  *   initcost : ComputeMultiViewInitialCostandSelectedViews                     (ACMMP.cu:519-556)
  * Host pointers; planes4 and out4 are W*H*4 floats. */
 int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out);
+/* the same cost through the quad-cooperative form the checkerboard pass runs (quad_ncc: four lanes per pixel) */
+int acmmp_probe_ncc_quad(acmmp_ctx *ctx, const float *planes4, int view, float *out);
 int acmmp_probe_geom(acmmp_ctx *ctx, const float *planes4, int view, float *out);
 int acmmp_probe_warp(acmmp_ctx *ctx, const float *planes4, int view, float *out4);
 int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint32_t *selected_views);

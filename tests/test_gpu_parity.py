@@ -88,6 +88,36 @@ def test_ncc_fixed_planes_matches_reference(model):
 
 
 @pytest.mark.parametrize("model", ["pinhole", "sphere"])
+def test_ncc_through_the_quad_form_of_the_checkerboard_pass_matches_reference(model):
+    """The same sub-kernel check for quad_ncc, the device function k_pass evaluates every hypothesis with (four lanes
+    per pixel, 2x2 tap blocks, packed FP32, skipped samples zeroed + per-lane rebuilt reference sums): NCC at fixed
+    planes against the compiled reference, same thresholds as the lane-per-plane form above."""
+    scene = util.scene_of(model)
+    ctx, *_ = _mine(scene)
+    ref = _ref(scene)
+    res = {}
+    for name, perturb in (("gt", 0.0), ("jitter", 0.05), ("far", 0.5)):
+        planes = util.random_planes(scene, 0, seed=5, perturb=perturb)
+        for view in (1, 2, 4):
+            a = ctx.probe_ncc_quad(planes, view)
+            b = ref.probe_ncc(planes, view)
+            c = ctx.probe_ncc(planes, view)
+            d = np.abs(a - b)
+            res[f"{name}_v{view}"] = dict(
+                frac_1e4=close_frac(a, b, atol=1e-4, rtol=1e-4), frac_1e3=close_frac(a, b, atol=1e-3, rtol=1e-3),
+                max=float(d.max()), p999=float(np.quantile(d, 0.999)), frac_cost2_ref=float((b >= 2.0).mean()),
+                frac_cost2_mine=float((a >= 2.0).mean()), vs_lane_form_1e4=close_frac(a, c, atol=1e-4, rtol=1e-4))
+    dump(f"ncc_quad_{model}", res)
+    for k, v in res.items():
+        assert v["frac_1e4"] >= 0.98, (k, v)
+        assert v["frac_1e3"] >= 0.9995, (k, v)
+        assert abs(v["frac_cost2_ref"] - v["frac_cost2_mine"]) <= 1e-4, (k, v)
+        # the two forms of this library differ in summation order (4 partial sums vs one running sum) and in how the
+        # fetch coordinates are rounded (packed vs scalar, 2x2 tap blocks): same tolerance class as against the reference
+        assert v["vs_lane_form_1e4"] >= 0.98, (k, v)
+
+
+@pytest.mark.parametrize("model", ["pinhole", "sphere"])
 def test_initial_cost_and_views_match_reference(model):
     scene = util.scene_of(model)
     ctx, *_ = _mine(scene)
