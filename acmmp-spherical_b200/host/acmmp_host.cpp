@@ -309,11 +309,10 @@ float4 ACMMP::GetPlaneHypothesis(const int index)
 float ACMMP::GetCost(const int index) { return costs_host_[index]; }
 
 // reference ACMMP.cpp:904-930: per 5x5 cell the pixel of least cost, kept when that cost is below 0.1
-void ACMMP::GetSupportPoints(std::vector<cv::Point> &support2DPoints)
+void SupportPointsOf(const float *costs, int width, int height, std::vector<cv::Point> &support2DPoints)
 {
     support2DPoints.clear();
     const int step = 5;
-    const int width = GetReferenceImageWidth(), height = GetReferenceImageHeight();
     for (int col = 0; col < width; col += step) {
         for (int row = 0; row < height; row += step) {
             float best = 2.0f;
@@ -321,7 +320,7 @@ void ACMMP::GetSupportPoints(std::vector<cv::Point> &support2DPoints)
             const int c_end = std::min(width, col + step), r_end = std::min(height, row + step);
             for (int c = col; c < c_end; ++c) {
                 for (int r = row; r < r_end; ++r) {
-                    const float cst = costs_host_[(size_t)r * width + c];
+                    const float cst = costs[(size_t)r * width + c];
                     if (cst < 2.0f && best > cst) {
                         where = cv::Point(c, r);
                         best = cst;
@@ -331,6 +330,11 @@ void ACMMP::GetSupportPoints(std::vector<cv::Point> &support2DPoints)
             if (best < 0.1f) support2DPoints.push_back(where);
         }
     }
+}
+
+void ACMMP::GetSupportPoints(std::vector<cv::Point> &support2DPoints)
+{
+    SupportPointsOf(costs_host_, GetReferenceImageWidth(), GetReferenceImageHeight(), support2DPoints);
 }
 
 // reference ACMMP.cpp:932-954 (cv::Subdiv2D there)
@@ -367,11 +371,11 @@ float3 Get3DPointonRefCam(const int x, const int y, const float depth, const Cam
 // reference ACMMP.cpp:956-989: the plane through the three lifted vertices.  The reference takes the null vector
 // of the 3x4 system [X 1] with cv::SVD::solveZ; the same 1-D null space in closed form: n = (X2-X1) x (X3-X1),
 // w = -n.X1, then normalised so that |n| = 1 and w >= 0.
-float4 ACMMP::GetPriorPlaneParams(const Triangle triangle, const cv::Mat_<float> &depths)
+float4 PriorPlaneParamsOf(const Camera &cam0, const Triangle &triangle, const cv::Mat_<float> &depths)
 {
-    const float3 a = Get3DPointonRefCam(triangle.pt1.x, triangle.pt1.y, depths(triangle.pt1.y, triangle.pt1.x), cameras_[0]);
-    const float3 b = Get3DPointonRefCam(triangle.pt2.x, triangle.pt2.y, depths(triangle.pt2.y, triangle.pt2.x), cameras_[0]);
-    const float3 c = Get3DPointonRefCam(triangle.pt3.x, triangle.pt3.y, depths(triangle.pt3.y, triangle.pt3.x), cameras_[0]);
+    const float3 a = Get3DPointonRefCam(triangle.pt1.x, triangle.pt1.y, depths(triangle.pt1.y, triangle.pt1.x), cam0);
+    const float3 b = Get3DPointonRefCam(triangle.pt2.x, triangle.pt2.y, depths(triangle.pt2.y, triangle.pt2.x), cam0);
+    const float3 c = Get3DPointonRefCam(triangle.pt3.x, triangle.pt3.y, depths(triangle.pt3.y, triangle.pt3.x), cam0);
     const double ux = (double)b.x - a.x, uy = (double)b.y - a.y, uz = (double)b.z - a.z;
     const double vx = (double)c.x - a.x, vy = (double)c.y - a.y, vz = (double)c.z - a.z;
     double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
@@ -382,10 +386,14 @@ float4 ACMMP::GetPriorPlaneParams(const Triangle triangle, const cv::Mat_<float>
     return make_float4((float)(nx / norm), (float)(ny / norm), (float)(nz / norm), (float)(w / norm));
 }
 
-// reference ACMMP.cpp:991-1011
-float ACMMP::GetDepthFromPlaneParam(const float4 plane_hypothesis, const int x, const int y)
+float4 ACMMP::GetPriorPlaneParams(const Triangle triangle, const cv::Mat_<float> &depths)
 {
-    const Camera &cam = cameras_[0];
+    return PriorPlaneParamsOf(cameras_[0], triangle, depths);
+}
+
+// reference ACMMP.cpp:991-1011
+float DepthFromPlaneParamOf(const Camera &cam, const float4 plane_hypothesis, const int x, const int y)
+{
     if (cam.model == SPHERE) {
         const float lon = (static_cast<float>(x) - cam.params[1]) / static_cast<float>(cam.width) * 2.0f * (float)M_PI;
         const float lat = -(static_cast<float>(y) - cam.params[2]) / static_cast<float>(cam.height) * (float)M_PI;
@@ -395,6 +403,55 @@ float ACMMP::GetDepthFromPlaneParam(const float4 plane_hypothesis, const int x, 
     }
     return -plane_hypothesis.w * cam.K[0] /
            ((x - cam.K[2]) * plane_hypothesis.x + (cam.K[0] / cam.K[4]) * (y - cam.K[5]) * plane_hypothesis.y + cam.K[0] * plane_hypothesis.z);
+}
+
+float ACMMP::GetDepthFromPlaneParam(const float4 plane_hypothesis, const int x, const int y)
+{
+    return DepthFromPlaneParamOf(cameras_[0], plane_hypothesis, x, y);
+}
+
+// The CPU planar-prior stage, main.cpp:113-185: support points -> Delaunay triangles -> triangle-id mask (the
+// reference's barycentric stepping rasteriser) + one plane per triangle -> pixels whose prior depth leaves the depth
+// range dropped.
+void PlanarPriorCpu(const Camera &cam, const cv::Mat_<float> &depths, const float *costs, float depth_min, float depth_max,
+                    cv::Mat_<float> &mask_tri, std::vector<float4> &planeParams_tri)
+{
+    const int width = depths.cols, height = depths.rows;
+    const cv::Rect imageRC(0, 0, width, height);
+    std::vector<cv::Point> support2DPoints;
+    SupportPointsOf(costs, width, height, support2DPoints);
+    mask_tri = cv::Mat_<float>::zeros(height, width);
+    planeParams_tri.clear();
+    if (support2DPoints.empty()) return;
+    const std::vector<int> idx = DelaunayIndices(support2DPoints);
+    uint32_t tri_idx = 0;
+    for (size_t t = 0; t + 2 < idx.size(); t += 3) {
+        const Triangle triangle(support2DPoints[idx[t]], support2DPoints[idx[t + 1]], support2DPoints[idx[t + 2]]);
+        if (!(imageRC.contains(triangle.pt1) && imageRC.contains(triangle.pt2) && imageRC.contains(triangle.pt3))) continue;
+        const float L01 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt2.x, 2) + std::pow(triangle.pt1.y - triangle.pt2.y, 2));
+        const float L02 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt3.x, 2) + std::pow(triangle.pt1.y - triangle.pt3.y, 2));
+        const float L12 = std::sqrt(std::pow(triangle.pt2.x - triangle.pt3.x, 2) + std::pow(triangle.pt2.y - triangle.pt3.y, 2));
+        const float max_edge_length = std::max(L01, std::max(L02, L12));
+        const float step = 1.0 / max_edge_length;
+        // barycentric stepping rasteriser of the reference (main.cpp:153-159)
+        for (float p = 0; p < 1.0; p += step) {
+            for (float q = 0; q < 1.0 - p; q += step) {
+                const int x = p * triangle.pt1.x + q * triangle.pt2.x + (1.0 - p - q) * triangle.pt3.x;
+                const int y = p * triangle.pt1.y + q * triangle.pt2.y + (1.0 - p - q) * triangle.pt3.y;
+                mask_tri(y, x) = tri_idx + 1.0;
+            }
+        }
+        planeParams_tri.push_back(PriorPlaneParamsOf(cam, triangle, depths));
+        tri_idx++;
+    }
+    for (int i = 0; i < width; ++i) {
+        for (int j = 0; j < height; ++j) {
+            if (mask_tri(j, i) > 0) {
+                const float d = DepthFromPlaneParamOf(cam, planeParams_tri[(size_t)(mask_tri(j, i) - 1)], i, j);
+                if (!(d <= depth_max && d >= depth_min)) mask_tri(j, i) = 0;
+            }
+        }
+    }
 }
 
 // reference ACMMP.cpp:847-867: masks(j, i) = 1-based triangle id as float (0 = none), PlaneParams[id - 1]

@@ -73,6 +73,17 @@ float3 Get3DPointonRefCam(const int x, const int y, const float depth, const Cam
 // exact integer predicates, incremental insertion with walking point location.  Returns vertex index triples.
 std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points);
 
+// ---- the CPU planar-prior stage as free functions (what the ACMMP methods below and the driver use) -----------
+// GetSupportPoints, ACMMP.cpp:904-930, on a W x H cost map
+void SupportPointsOf(const float *costs, int width, int height, std::vector<cv::Point> &support2DPoints);
+// GetPriorPlaneParams, ACMMP.cpp:956-989 / GetDepthFromPlaneParam, ACMMP.cpp:991-1011 for camera `cam`
+float4 PriorPlaneParamsOf(const Camera &cam, const Triangle &triangle, const cv::Mat_<float> &depths);
+float DepthFromPlaneParamOf(const Camera &cam, const float4 plane_hypothesis, const int x, const int y);
+// The whole stage of main.cpp:113-185: support points -> Delaunay -> per-triangle plane + stepping rasteriser ->
+// depth-range test.  depths / costs: the photometric stage's maps; depth_min / depth_max: GetMinDepth / GetMaxDepth.
+void PlanarPriorCpu(const Camera &cam, const cv::Mat_<float> &depths, const float *costs, float depth_min, float depth_max,
+                    cv::Mat_<float> &mask_tri, std::vector<float4> &planeParams_tri);
+
 class ACMMP {
 public:
     explicit ACMMP(int device = 0);      // the reference hard-codes device 0 (main.cpp:77)
@@ -91,6 +102,7 @@ public:
     int GetReferenceImageWidth();
     int GetReferenceImageHeight();
     cv::Mat_<float> GetReferenceImage();
+    const Camera &GetReferenceCamera() const { return cameras_[0]; }      // not in the reference
     float4 GetPlaneHypothesis(const int index);
     float GetCost(const int index);
     void GetSupportPoints(std::vector<cv::Point> &support2DPoints);

@@ -101,41 +101,11 @@ void collect(ACMMP &acmmp, cv::Mat_<float> &depths, cv::Mat_<cv::Vec3f> &normals
 void PlanarPriorStage(ACMMP &acmmp, const cv::Mat_<float> &depths, cv::Mat_<float> &mask_tri, std::vector<float4> &planeParams_tri)
 {
     const double t0 = now_s();
-    const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
     acmmp.SetPlanarPriorParams();
-    const cv::Rect imageRC(0, 0, width, height);
-    std::vector<cv::Point> support2DPoints;
-    acmmp.GetSupportPoints(support2DPoints);
-    const auto triangles = acmmp.DelaunayTriangulation(imageRC, support2DPoints);
-    mask_tri = cv::Mat_<float>::zeros(height, width);
-    planeParams_tri.clear();
-    uint32_t tri_idx = 0;
-    for (const auto &triangle : triangles) {
-        if (!(imageRC.contains(triangle.pt1) && imageRC.contains(triangle.pt2) && imageRC.contains(triangle.pt3))) continue;
-        const float L01 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt2.x, 2) + std::pow(triangle.pt1.y - triangle.pt2.y, 2));
-        const float L02 = std::sqrt(std::pow(triangle.pt1.x - triangle.pt3.x, 2) + std::pow(triangle.pt1.y - triangle.pt3.y, 2));
-        const float L12 = std::sqrt(std::pow(triangle.pt2.x - triangle.pt3.x, 2) + std::pow(triangle.pt2.y - triangle.pt3.y, 2));
-        const float max_edge_length = std::max(L01, std::max(L02, L12));
-        const float step = 1.0 / max_edge_length;
-        // barycentric stepping rasteriser of the reference (main.cpp:153-159)
-        for (float p = 0; p < 1.0; p += step) {
-            for (float q = 0; q < 1.0 - p; q += step) {
-                const int x = p * triangle.pt1.x + q * triangle.pt2.x + (1.0 - p - q) * triangle.pt3.x;
-                const int y = p * triangle.pt1.y + q * triangle.pt2.y + (1.0 - p - q) * triangle.pt3.y;
-                mask_tri(y, x) = tri_idx + 1.0;
-            }
-        }
-        planeParams_tri.push_back(acmmp.GetPriorPlaneParams(triangle, depths));
-        tri_idx++;
-    }
-    for (int i = 0; i < width; ++i) {
-        for (int j = 0; j < height; ++j) {
-            if (mask_tri(j, i) > 0) {
-                const float d = acmmp.GetDepthFromPlaneParam(planeParams_tri[(size_t)(mask_tri(j, i) - 1)], i, j);
-                if (!(d <= acmmp.GetMaxDepth() && d >= acmmp.GetMinDepth())) mask_tri(j, i) = 0;
-            }
-        }
-    }
+    const int npx = acmmp.GetReferenceImageWidth() * acmmp.GetReferenceImageHeight();
+    std::vector<float> costs((size_t)npx);
+    for (int k = 0; k < npx; ++k) costs[k] = acmmp.GetCost(k);
+    PlanarPriorCpu(acmmp.GetReferenceCamera(), depths, costs.data(), acmmp.GetMinDepth(), acmmp.GetMaxDepth(), mask_tri, planeParams_tri);
     add_prior_s(now_s() - t0);
 }
 
@@ -261,6 +231,25 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         }
     }
     cudaSetDevice(g_device);
+    {   // One context per view stays alive: images of the view and its sources twice (layered + per-view textures), the
+        // padded reference, planes x 2, costs x 3, view masks, two RNG states, prior planes + masks, for all pyramid
+        // levels of the pool (1 + 1/4 + 1/16).  Scenes that do not fit fall back to the file-chained schedule.
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        double need = 0.0;
+        for (size_t i = 0; i < num_images; ++i) {
+            int cols = 0, rows = 0;
+            if (!ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) continue;
+            const double scale = std::min(1.0, (double)problems[i].max_image_size / std::max(cols, rows));
+            const double px = (double)cols * rows * scale * scale;
+            need += px * (8.0 * (problems[i].src_image_ids.size() + 1) + 160.0) * 1.32;
+        }
+        if (need > 0.85 * (double)free_b) {
+            std::cout << "resident schedule: " << num_images << " views need about " << need / 1e9 << " GB of device memory, "
+                      << free_b / 1e9 << " GB are free" << std::endl;
+            return false;
+        }
+    }
     std::vector<std::unique_ptr<ACMMP>> objs(num_images);
     std::vector<DeviceMap> dmap(num_images), gmap(num_images);
     std::vector<cv::Mat_<float>> final_prior_depth(num_images);

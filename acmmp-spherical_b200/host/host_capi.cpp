@@ -1,4 +1,5 @@
 // host_capi.cpp -- C entry points into the host-side helpers, for the CPU tests (ctypes); none touches the GPU.
+#include <algorithm>
 #include <cstring>
 #include "acmmp_host.h"
 
@@ -63,6 +64,25 @@ int acmmp_host_delaunay(const int32_t *points, int n, int32_t *out, int cap)
     const int nt = (int)(idx.size() / 3);
     for (int i = 0; i < std::min(nt, cap) * 3; ++i) out[i] = idx[i];
     return nt;
+}
+
+// The CPU planar-prior stage on host arrays: masks (w*h floats, 1-based triangle ids) and up to cap float4 plane
+// parameters; returns the number of triangles (planes).
+int acmmp_host_planar_prior(const acmmp_camera *cam, int w, int h, const float *depths, const float *costs, float depth_min,
+                            float depth_max, float *masks, float *params4, int cap)
+{
+    cv::Mat_<float> d(h, w), m;
+    std::memcpy(d.ptr(), depths, sizeof(float) * (size_t)w * h);
+    std::vector<float4> pp;
+    Camera c = *cam;
+    c.width = w;
+    c.height = h;
+    PlanarPriorCpu(c, d, costs, depth_min, depth_max, m, pp);
+    std::memcpy(masks, m.ptr(), sizeof(float) * (size_t)w * h);
+    for (int i = 0; i < std::min((int)pp.size(), cap); ++i) {
+        params4[4 * i] = pp[i].x; params4[4 * i + 1] = pp[i].y; params4[4 * i + 2] = pp[i].z; params4[4 * i + 3] = pp[i].w;
+    }
+    return (int)pp.size();
 }
 
 int acmmp_host_load_grey(const char *dense_folder, int id, float *dst, int cap, int *w, int *h)

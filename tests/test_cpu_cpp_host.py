@@ -152,3 +152,47 @@ def test_delaunay_scales_to_full_resolution_point_counts(host):
     dt = time.perf_counter() - t0
     assert 1.9 * len(pts) < nt < 2.0 * len(pts)
     assert dt < 20.0, f"{dt:.1f} s for {len(pts)} points"
+
+
+@pytest.mark.parametrize("model", ["pinhole", "sphere"])
+def test_cpu_planar_prior_stage_agrees_with_the_numpy_twin(host, model):
+    """PlanarPriorCpu (host/acmmp_host.cpp: main.cpp:113-185 with the reference's stepping rasteriser and the exact-integer
+    Delaunay stand-in) against acmmp_b200/prior.py (cv2.Subdiv2D + cv2.fillConvexPoly + closed-form planes): the Delaunay
+    triangulation of generic points is unique, so away from triangle edges every pixel must get the same prior plane."""
+    import sys
+    sys.path.insert(0, str(ROOT / "acmmp-spherical_b200"))
+    from acmmp_b200 import synth
+    from acmmp_b200.prior import planar_prior
+    rng = np.random.default_rng(3)
+    if model == "pinhole":
+        sc = synth.make_pinhole_scene(n_views=2, width=200, height=150, focal=160.0, seed=5)
+    else:
+        sc = synth.make_sphere_scene(n_views=2, width=256, height=128, seed=4)
+    cam = sc.cams[0]
+    gt = sc.depths_gt[0].astype(np.float32)
+    H, W = gt.shape
+    depths = np.ascontiguousarray(gt * (1.0 + 0.002 * rng.standard_normal((H, W)))).astype(np.float32)
+    costs = np.ascontiguousarray(rng.uniform(0.0, 0.09, (H, W))).astype(np.float32)      # every cell yields a generic support point
+    dmin, dmax = float(gt.min() * 0.6), float(gt.max() * 1.2)
+    masks = np.zeros((H, W), np.float32)
+    cap = 2 * ((W + 4) // 5) * ((H + 4) // 5) + 16
+    params = np.zeros((cap, 4), np.float32)
+    n = host.acmmp_host_planar_prior(C.byref(cam), W, H, _fp(depths), _fp(costs), C.c_float(dmin), C.c_float(dmax), _fp(masks), _fp(params), cap)
+    assert 0 < n <= cap and masks.max() == n
+    p_ref, m_ref = planar_prior(cam, depths, costs, dmin, dmax)
+    assert abs(len(p_ref) - n) <= 0.02 * n                       # co-circular quadruples may be split either way
+    assert abs((masks > 0).mean() - (m_ref > 0).mean()) < 0.03
+    # the same triangles => the same set of planes (ids differ: the two triangulators list triangles in different orders)
+    from scipy.spatial import cKDTree
+    scale = np.abs(p_ref).max(axis=0)
+    d_mine, _ = cKDTree(params[:n] / scale).query(p_ref / scale)
+    d_ref, _ = cKDTree(p_ref / scale).query(params[:n] / scale)
+    assert (d_mine < 1e-4).mean() > 0.98 and (d_ref < 1e-4).mean() > 0.98, ((d_mine < 1e-4).mean(), (d_ref < 1e-4).mean())
+    # per pixel: interior pixels carry the same plane; pixels on triangle edges (a large share for 5-pixel triangles) go to
+    # either neighbour depending on the rasteriser (reference stepping loop vs cv2 scan conversion), whose planes are close
+    both = (masks > 0) & (m_ref > 0)
+    assert both.mean() > 0.85
+    mine = params[masks[both].astype(np.int64) - 1]
+    theirs = p_ref[m_ref[both].astype(np.int64) - 1]
+    same = np.all(np.abs(mine - theirs) <= 1e-4 + 1e-4 * np.abs(theirs), axis=1)
+    assert same.mean() > 0.55, same.mean()
