@@ -3,20 +3,24 @@
 //   k_pass            : one red/black checkerboard pass      (reference Black/RedPixelUpdate,
 //                       CheckerboardPropagation + PlaneHypothesisRefinement, ACMMP.cu:797-1349)
 //   k_random_init     : RandomInitialization, all four branches            (ACMMP.cu:673-795)
-//   k_probe           : sub-kernel probes for parity tests (same device code as the two above)
+//   k_probe, k_probe_quad : sub-kernel probes for parity tests (the device code of the two above: lane-per-plane
+//                       NCC of the init kernel, quad-cooperative NCC of the pass)
 //   k_depth_normal    : GetDepthandNormal                                  (ACMMP.cu:1351-1364)
 //   k_median_filter   : Black/RedPixelFilter                               (ACMMP.cu:1366-1504)
 //   k_jbu             : JBU_cu                                             (ACMMP.cu:1558-1616)
-//   k_pad_reference, k_rng_fill, k_export_depth : data-layout helpers
+//   k_support_cells, k_tri_planes, k_tri_raster[_long], k_prior_finish : the planar-prior stage on the device
+//                       (reference: CPU, ACMMP.cpp:904-1011 + main.cpp:113-185)
+//   k_pad_reference, k_rng_fill, k_export_depth, k_expand_prior, k_make_coarse, ... : data-layout helpers
 //
-// Work decomposition of k_pass (the kernel that is >95 % of the time): a CTA owns an 8x16 pixel
-// tile = 64 pixels of the active colour; each pixel is served by a GROUP OF 8 LANES (4 pixels per
-// warp).  Lane l evaluates candidate direction l of the adaptive checkerboard (8 neighbour
-// hypotheses in parallel, argmin by warp shuffles); the current plane's cost and the five refinement
-// hypotheses are evaluated as (hypothesis, selected view) pairs dealt out to the 8 lanes.  The
-// reference tile (+5 px halo) arrives in shared memory by one TMA bulk-tensor copy; bilateral
-// weights and tap rays are computed once per pixel visit; source views are bilinear R32F
-// texture fetches (identical filtering to the reference's textures by construction).
+// Work decomposition of k_pass (the kernel that is >93 % of the time): persistent, one 512-thread CTA per SM walking
+// 8x16 pixel tiles (64 pixels of the active colour each) in lock step; each pixel is served by a GROUP OF 8 LANES
+// (4 pixels per warp).  Lane l scans candidate direction l of the adaptive checkerboard; the 8 neighbour hypotheses
+// are evaluated by the group's two quads (4 hypotheses each, the four lanes of a quad splitting the 36 taps into 2x2
+// blocks: quad_ncc), argmin by warp shuffles; the current plane and the five refinement hypotheses are evaluated per
+// (pixel, selected view) pair, the warp's pairs dealt across its eight quads (WarpPairs).  The reference tile (+5 px
+// halo) arrives in shared memory by TMA bulk-tensor copies, double-buffered two tiles ahead; bilateral weights and
+// tap rays are computed once per pixel visit; source views are bilinear R32F texture fetches (identical filtering to
+// the reference's textures by construction).
 #pragma once
 #include <cuda.h>
 #include "acmmp_device.cuh"
