@@ -159,75 +159,6 @@ class B200Backend:
                 self.ctx = None
 
 
-class ReferenceBackend:
-    """The same stages through the UNMODIFIED reference (oracle/_ref/libacmmp_ref.so): one new
-    `ACMMP` object per ProcessProblem call, state through .dmb files, exactly like main.cpp.
-    TEST / BASELINE INFRASTRUCTURE: imported lazily so that the product never loads the oracle."""
-    name = "reference"
-
-    def __init__(self, device=0, seed=1234):
-        self.seed = seed
-        self.t = StageTimes()
-        self.obj = None
-        self.prev = None
-        self.last = None
-
-    def begin_level(self, level, prev=None, first=True):
-        self.prev = prev
-
-    def _finish(self, stage, finest, t_setup):
-        obj = self.obj
-        t0 = time.perf_counter()
-        ms = obj.run_patch_match()
-        planes, costs = obj.get_result()
-        self.t.wall_s += t_setup + time.perf_counter() - t0
-        self.t.gpu_ms += ms
-        n_pass = 2 * (2 if stage == "geom" else 3)
-        self.t.passes += n_pass
-        if finest:
-            self.t.pass_ms.setdefault(stage, []).append(ms / n_pass)      # includes init + finalize (~5 %)
-        self.last = (planes, costs)
-        return planes, costs
-
-    def photometric(self, level, finest=False):
-        from oracle.ref_driver import RefACMMP, run_jbu
-        if self.obj is not None:
-            self.obj.close()
-        t0 = time.perf_counter()
-        if self.prev is None:
-            self.obj = RefACMMP(level.images, level.cams, seed=self.seed)
-        else:
-            planes_prev, costs_prev = self.prev
-            tj = time.perf_counter()
-            fine_depth = run_jbu(level.images[0], np.ascontiguousarray(planes_prev[..., 3]))     # RunJBU, ACMMP.cpp:1071
-            self.t.gpu_ms += (time.perf_counter() - tj) * 1e3      # RunJBU only printf's its time; wall is what there is
-            self.obj = RefACMMP(level.images, level.cams, seed=self.seed, hierarchy=True,
-                                coarse_normals=np.ascontiguousarray(planes_prev[..., :3]),
-                                coarse_costs=np.ascontiguousarray(costs_prev), fine_depth=fine_depth)
-        return self._finish("photometric", finest, time.perf_counter() - t0)
-
-    def prior(self, level, params, masks, finest=False):
-        t0 = time.perf_counter()
-        self.obj.set_prior(params, masks)
-        return self._finish("prior", finest, time.perf_counter() - t0)
-
-    def geom(self, level, multi, neighbour_depths, finest=False, last=False, device_ptrs=None):
-        from oracle.ref_driver import RefACMMP
-        own_planes, own_costs = self.last
-        if self.obj is not None:
-            self.obj.close()
-        t0 = time.perf_counter()
-        dm = [np.ascontiguousarray(own_planes[..., 3])] + list(neighbour_depths)
-        self.obj = RefACMMP(level.images, level.cams, seed=self.seed, geom=True, multi_geom=multi, depth_maps=dm,
-                            prev_planes=own_planes, prev_costs=own_costs)
-        return self._finish("geom", finest, time.perf_counter() - t0)
-
-    def end(self):
-        if self.obj is not None:
-            self.obj.close()
-            self.obj = None
-
-
 def run_view(levels, backend, prior_cache=None, exchange=None):
     """One reference view through every level and stage.  Returns (planes, costs) of the finest level
     -- planes = (world normal, depth) -- and leaves the timings in backend.t.

@@ -227,8 +227,9 @@ def scale_problem(images, cams, max_size):
             out_imgs.append(im); c.width, c.height = cols, rows; out_cams.append(c)
             continue
         factor = min(np.float32(max_size) / np.float32(cols), np.float32(max_size) / np.float32(rows))
-        new_cols = int(round(float(np.float32(cols) * factor)))
-        new_rows = int(round(float(np.float32(rows) * factor)))
+        # std::round (ACMMP.cpp:620-621) rounds halves away from zero -- 2130 / 4 = 532.5 -> 533; Python's round() gives 532
+        new_cols = int(np.floor(float(np.float32(cols) * factor) + 0.5))
+        new_rows = int(np.floor(float(np.float32(rows) * factor) + 0.5))
         sx = np.float32(new_cols) / np.float32(cols)
         sy = np.float32(new_rows) / np.float32(rows)
         scaled = cv2.resize(im, (new_cols, new_rows), interpolation=cv2.INTER_LINEAR)

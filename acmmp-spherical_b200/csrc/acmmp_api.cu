@@ -300,6 +300,30 @@ int fail(acmmp_ctx *ctx, int code, const std::string &msg)
     return code;
 }
 
+// Pooled temporaries of one call: returned to the pool on every exit path (CK returns early).
+struct PoolTemps {
+    acmmp_ctx *ctx;
+    std::vector<void *> dev, host;
+    explicit PoolTemps(acmmp_ctx *c) : ctx(c) {}
+    ~PoolTemps()
+    {
+        for (void *p : dev) ctx->pool.dfree(p);
+        for (void *p : host) ctx->pool.hfree(p);
+    }
+    template <typename T> cudaError_t d(T **p, size_t bytes)
+    {
+        cudaError_t e = pmalloc(ctx, p, bytes);
+        if (e == cudaSuccess) dev.push_back(*p);
+        return e;
+    }
+    template <typename T> cudaError_t h(T **p, size_t bytes)
+    {
+        cudaError_t e = phmalloc(ctx, p, bytes);
+        if (e == cudaSuccess) host.push_back(*p);
+        return e;
+    }
+};
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -515,9 +539,14 @@ template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPass
 
 int configure_kernels(acmmp_ctx *ctx)
 {
-    static std::once_flag once;
-    static cudaError_t result = cudaSuccess;
-    std::call_once(once, [] {
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: every device a context is created on
+    // needs its own opt-in (one process may drive several GPUs, host/acmmp_main.cpp --gpus N).
+    static std::mutex mu;
+    static std::map<int, cudaError_t> done;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find(ctx->device);
+    if (it == done.end()) {
+        cudaError_t result = cudaSetDevice(ctx->device);
         const int big = 227 * 1024;      // the per-CTA maximum of sm_100
         cudaError_t e;
 #define SETATTR(k) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) result = e;
@@ -527,8 +556,10 @@ int configure_kernels(acmmp_ctx *ctx)
         SETATTR(k_probe<kModelPinhole>) SETATTR(k_probe<kModelSphere>)
         SETATTR(k_probe_quad<kModelPinhole>) SETATTR(k_probe_quad<kModelSphere>)
 #undef SETATTR
-    });
-    if (result != cudaSuccess) return fail(ctx, ACMMP_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(result));
+        if (result != cudaSuccess) (void)cudaGetLastError();      // not sticky; a later context on this device retries
+        else done[ctx->device] = result;
+        if (result != cudaSuccess) return fail(ctx, ACMMP_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(result));
+    }
     return ACMMP_OK;
 }
 
@@ -719,6 +750,12 @@ int set_depths_common(acmmp_ctx *ctx, int n, const float *const *maps, bool on_d
 {
     if (!ctx || n != ctx->n || !maps || !widths || !heights)
         return fail(ctx, ACMMP_E_ARG, "acmmp_set_depth_maps: one map per view (after acmmp_set_views)");
+    // A null / empty neighbour map would make geom_address clamp to texel -1 of a null base (the file-chained host
+    // path produced exactly that when a depths.dmb was missing): refuse it here.
+    for (int i = 0; i < n; ++i) {
+        if (widths[i] <= 0 || heights[i] <= 0 || (maps[i] == nullptr && i > 0))
+            return fail(ctx, ACMMP_E_ARG, "acmmp_set_depth_maps: map " + std::to_string(i) + " is null or empty");
+    }
     CK(cudaSetDevice(ctx->device));
     free_depths(ctx);
     for (int i = 0; i < n; ++i) {
@@ -907,10 +944,11 @@ int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *o
     float4 *dp = nullptr, *do4 = nullptr;
     float *dout = nullptr;
     uint32_t *dv = nullptr;
-    CK(pmalloc(ctx, &dp, sizeof(float4) * npx));
-    CK(pmalloc(ctx, &do4, sizeof(float4) * npx));
-    CK(pmalloc(ctx, &dout, sizeof(float) * npx));
-    CK(pmalloc(ctx, &dv, sizeof(uint32_t) * npx));
+    PoolTemps tmp(ctx);
+    CK(tmp.d(&dp, sizeof(float4) * npx));
+    CK(tmp.d(&do4, sizeof(float4) * npx));
+    CK(tmp.d(&dout, sizeof(float) * npx));
+    CK(tmp.d(&dv, sizeof(uint32_t) * npx));
     CK(cudaMemcpyAsync(dp, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
     if (mode == 4)
         rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe_quad<kModelPinhole>(ctx, view, dp, dout)
@@ -924,7 +962,6 @@ int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *o
         if (out_views) CK(cudaMemcpyAsync(out_views, dv, sizeof(uint32_t) * npx, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    ctx->pool.dfree(dp); ctx->pool.dfree(do4); ctx->pool.dfree(dout); ctx->pool.dfree(dv);
     return rc;
 }
 
@@ -1146,8 +1183,9 @@ int acmmp_support_points(acmmp_ctx *ctx, int32_t *xy, int capacity, int *n)
     CK(cudaSetDevice(ctx->device));
     const int cells_x = (ctx->W + 4) / 5, cells_y = (ctx->H + 4) / 5, ncell = cells_x * cells_y;
     int2 *cells_dev = nullptr, *cells_host = nullptr;
-    CK(pmalloc(ctx, &cells_dev, sizeof(int2) * (size_t)ncell));
-    CK(phmalloc(ctx, &cells_host, sizeof(int2) * (size_t)ncell));
+    PoolTemps tmp(ctx);
+    CK(tmp.d(&cells_dev, sizeof(int2) * (size_t)ncell));
+    CK(tmp.h(&cells_host, sizeof(int2) * (size_t)ncell));
     k_support_cells<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(ctx->costs, ctx->W, ctx->H, cells_x, cells_y, cells_dev);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1162,8 +1200,6 @@ int acmmp_support_points(acmmp_ctx *ctx, int32_t *xy, int capacity, int *n)
         }
         ++count;
     }
-    ctx->pool.dfree(cells_dev);
-    ctx->pool.hfree(cells_host);
     *n = count;
     if (count > capacity) return fail(ctx, ACMMP_E_ARG, "acmmp_support_points: output array too small");
     return ACMMP_OK;
@@ -1233,6 +1269,9 @@ int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const in
         // depths.dmb; same size here means the coarse depth is the depth
         if (npx != snpx) { ctx->pool.dfree(coarse); ctx->pool.dfree(coarse_depth); ctx->pool.dfree(fine_depth); return fail(ctx, ACMMP_E_UNSUPPORTED, "level size ratio < 2"); }
         CK(cudaMemcpyAsync(fine_depth, coarse_depth, sizeof(float) * (size_t)npx, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_coarse_w_from_depth<<<(snpx + 255) / 256, 256, 0, ctx->stream>>>(coarse_depth, snpx, coarse);      // ACMMP.cpp:826-828
+        ctx->launches++;
+        CK(cudaGetLastError());
     } else {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1380,6 +1419,14 @@ int acmmp_export_depth_device(acmmp_ctx *ctx, float *depth_dev)
     return ACMMP_OK;
 }
 
+int acmmp_export_depth_device_sync(acmmp_ctx *ctx, float *depth_dev)
+{
+    const int rc = acmmp_export_depth_device(ctx, depth_dev);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ACMMP_OK;
+}
+
 int acmmp_download_state(acmmp_ctx *ctx, float *planes4, float *costs, uint32_t *selected_views, uint32_t *rand6,
                          float *pre_costs)
 {
@@ -1451,6 +1498,30 @@ int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_
     }
     cudaFree(di); cudaFree(dd); cudaFree(dout);
     return rc;
+}
+
+int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, float *out72)
+{
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!planes4 || !out72 || view < 1 || view >= ctx->n) return fail(ctx, ACMMP_E_ARG, "acmmp_probe_coords: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    PoolTemps tmp(ctx);
+    float4 *dp = nullptr;
+    float *dout = nullptr;
+    CK(tmp.d(&dp, sizeof(float4) * npx));
+    CK(tmp.d(&dout, sizeof(float) * 72 * npx));
+    CK(cudaMemcpyAsync(dp, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
+    const FrameConst fc = frame_const(ctx);
+    dim3 grid((ctx->W + 15) / 16, (ctx->H + 7) / 8);
+    if (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) k_probe_coords<kModelPinhole><<<grid, 128, 0, ctx->stream>>>(fc, ctx->ncc, view, dp, dout);
+    else k_probe_coords<kModelSphere><<<grid, 128, 0, ctx->stream>>>(fc, ctx->ncc, view, dp, dout);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out72, dout, sizeof(float) * 72 * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ACMMP_OK;
 }
 
 int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 0, view, planes4, out, nullptr, nullptr); }

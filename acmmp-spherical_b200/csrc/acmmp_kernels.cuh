@@ -260,6 +260,50 @@ k_probe_quad(const __grid_constant__ FrameConst fc, const __grid_constant__ NccT
 }
 
 // ------------------------------------------------------------------------------------------
+// probe of the sample COORDINATES quad_ncc fetches at: the same device functions in the same composition (folded ray of
+// the pixel -> shifted to the quad lane's first tap -> to the block row -> to the block column; PlaneRay depth of the
+// tap; tap_coords).  72 floats per pixel: (u, v) of tap k = ii * 6 + jj, texel-centre shift included -- to be compared
+// with the reference's unfolded chain (ACMMP.cu:458-476): a parity test uses it to show that the NCC residue above 1e-4
+// sits exactly on the pixels where a coordinate crosses a 1/256 boundary of the texture unit's 1.8 fixed-point fraction.
+// ------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+k_probe_coords(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const int view,
+               const float4 *__restrict__ planes, float *__restrict__ out)
+{
+    typedef typename AuxType<MODEL>::type AuxT;
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 8 + (threadIdx.x >> 4);
+    if (x >= fc.W || y >= fc.H) return;
+    const int center = y * fc.W + x;
+    PixCtx px = make_pix<MODEL>(fc, x, y, 0, 0);
+    ViewK c;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c.a[i] = nt.c[view - 1].a[i];
+    ViewPix<MODEL> vp;
+    vp.init(c, px);
+    PlaneRay<MODEL> ray;
+    ray.init(fc, px, planes[center]);
+    for (int q = 0; q < 4; ++q) {
+        const int qi = q & 1, qj = q >> 1;
+        const ViewPix<MODEL> vq = shift_y(c, shift_x(c, vp, (float)(2 * qi - 5)), (float)(2 * qj - 5));
+        for (int by = 0; by < 3; ++by) {
+            const ViewPix<MODEL> vrow = shift_y(c, vq, (float)(4 * by));
+            for (int bx = 0; bx < 3; ++bx) {
+                const ViewPix<MODEL> vt = (bx == 0) ? vrow : shift_x(c, vrow, (float)(4 * bx));
+                const int i = 2 * qi - 5 + 4 * bx, j = 2 * qj - 5 + 4 * by;
+                const AuxT a = make_aux<MODEL>(fc, x + i, y + j);
+                const float t = ray.depth(a, i, j);
+                float u, v;
+                tap_coords(c, vt, a, t, c.a[11], u, v);
+                const int k = (2 * bx + qi) * 6 + (2 * by + qj);
+                out[(size_t)center * 72 + 2 * k] = u;
+                out[(size_t)center * 72 + 2 * k + 1] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // RandomInitialization, ACMMP.cu:673-795
 // ------------------------------------------------------------------------------------------
 // SpatialGauss / RangeGauss, ACMMP.cu:175-185 (double precision inside, float in/out)
@@ -1560,6 +1604,15 @@ k_make_coarse(const float4 *__restrict__ planes, const float *__restrict__ costs
     const float4 p = planes[idx];
     coarse[idx] = make_float4(p.x, p.y, p.z, costs[idx]);
     coarse_depth[idx] = p.w;
+}
+
+// same-size hierarchy level (!upsample): the reference stores the DEPTH, not the cost, in scaled_plane_hypotheses.w
+// (ACMMP.cpp:826-828) and the reload branch of RandomInitialization reads it as depth (ACMMP.cu:781-792)
+__global__ void __launch_bounds__(256)
+k_coarse_w_from_depth(const float *__restrict__ depth, const int n, float4 *__restrict__ coarse)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) coarse[idx].w = depth[idx];
 }
 
 // plane = (0, 0, 0, fine depth): what the reference uploads in hierarchy mode (ACMMP.cpp:833-840)

@@ -6,6 +6,7 @@
 #include <iomanip>
 #include <iostream>
 #include <sstream>
+#include <unordered_map>
 #include <stdexcept>
 
 #include "acmmp_host.h"
@@ -72,9 +73,17 @@ void ACMMP::InuputInitialization(const std::string &dense_folder, const std::vec
     std::vector<int> ids;
     ids.push_back(problem.ref_image_id);
     ids.insert(ids.end(), problem.src_image_ids.begin(), problem.src_image_ids.end());
+    // The reference indexes the problem vector BY IMAGE ID here (ACMMP.cpp:609), which reads out of bounds -- or another
+    // view's size -- unless pair.txt lists the ids 0..N-1 in order.  Same result for well-formed scenes, defined for the
+    // others: look the source view's problem up by id; a view that is nobody's reference view takes this view's size.
+    std::unordered_map<int, size_t> index_of;
+    for (size_t k = 0; k < problems.size(); ++k) index_of.emplace(problems[k].ref_image_id, k);
     for (size_t i = 0; i < ids.size(); ++i) {
-        // note: the reference indexes the problem vector BY IMAGE ID here (ACMMP.cpp:609)
-        const int max_image_size = (i == 0) ? problems[idx].cur_image_size : problems[problem.src_image_ids[i - 1]].cur_image_size;
+        int max_image_size = problems[idx].cur_image_size;
+        if (i > 0) {
+            const auto it = index_of.find(ids[i]);
+            if (it != index_of.end()) max_image_size = problems[it->second].cur_image_size;
+        }
         cv::Mat_<float> img;
         Camera cam;
         LoadScaledView(dense_folder, ids[i], max_image_size, img, cam);
@@ -92,7 +101,10 @@ void ACMMP::InuputInitialization(const std::string &dense_folder, const std::vec
         const std::string suffix = params_.multi_geometry ? "/depths_geom.dmb" : "/depths.dmb";
         for (int id : ids) {
             cv::Mat_<float> d;
-            readDepthDmb(result_folder_of(dense_folder, id) + suffix, d);
+            const std::string path = result_folder_of(dense_folder, id) + suffix;
+            if (readDepthDmb(path, d) != 0 || d.rows <= 0 || d.cols <= 0)
+                throw std::runtime_error("geometric stage: cannot read the depth map " + path +
+                                         " (is every source view among the processed views?)");
             depths_.push_back(d);
         }
     }
@@ -252,9 +264,9 @@ void ACMMP::CudaSpaceInitialization(const std::string &dense_folder, const Probl
         const std::string suffix = params_.multi_geometry ? "/depths_geom.dmb" : "/depths.dmb";
         cv::Mat_<float> ref_depth, ref_cost;
         cv::Mat_<cv::Vec3f> ref_normal;
-        readDepthDmb(folder + suffix, ref_depth);
-        readNormalDmb(folder + "/normals.dmb", ref_normal);
-        readDepthDmb(folder + "/costs.dmb", ref_cost);
+        if (readDepthDmb(folder + suffix, ref_depth) != 0 || readNormalDmb(folder + "/normals.dmb", ref_normal) != 0 ||
+            readDepthDmb(folder + "/costs.dmb", ref_cost) != 0)
+            throw std::runtime_error("geometric stage: cannot read the previous stage's .dmb files in " + folder);
         if (ref_depth.rows != H || ref_depth.cols != W || ref_normal.rows != H || ref_cost.rows != H)
             throw std::runtime_error("geometric stage: previous-stage .dmb files do not match the image size");
         std::vector<float> planes((size_t)4 * W * H);
@@ -268,9 +280,10 @@ void ACMMP::CudaSpaceInitialization(const std::string &dense_folder, const Probl
     if (params_.hierarchy) {                                 // ACMMP.cpp:788-844
         cv::Mat_<float> fine_depth, coarse_cost;
         cv::Mat_<cv::Vec3f> coarse_normal;
-        readDepthDmb(folder + "/depths.dmb", fine_depth);             // JBU output, already at this level's size
-        readNormalDmb(folder + "/normals.dmb", coarse_normal);        // previous (coarser) level
-        readDepthDmb(folder + "/costs.dmb", coarse_cost);
+        if (readDepthDmb(folder + "/depths.dmb", fine_depth) != 0 ||            // JBU output, already at this level's size
+            readNormalDmb(folder + "/normals.dmb", coarse_normal) != 0 ||       // previous (coarser) level
+            readDepthDmb(folder + "/costs.dmb", coarse_cost) != 0)
+            throw std::runtime_error("hierarchy stage: cannot read the previous level's .dmb files in " + folder);
         const int sw = coarse_normal.cols, sh = coarse_normal.rows;
         if (fine_depth.rows != H || fine_depth.cols != W) throw std::runtime_error("hierarchy stage: depths.dmb is not at this level's size");
         const bool upsample = (sw != W || sh != H);

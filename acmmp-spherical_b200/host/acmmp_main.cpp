@@ -459,6 +459,24 @@ int main(int argc, char **argv)
     mkdir((dense_folder + "/ACMMP").c_str(), 0777);
     const size_t num_images = max_views ? std::min(max_views, problems.size()) : problems.size();
     std::cout << "There are " << num_images << " problems needed to be processed!" << std::endl;
+    if (num_images < problems.size()) {
+        // --max-views: a source view that is not processed has no depth map for the geometric stages (the file-chained
+        // schedule would read a depths.dmb nobody wrote).  The sub-scene keeps only neighbours that are processed.
+        std::map<int, size_t> pos;
+        for (size_t i = 0; i < problems.size(); ++i) pos[problems[i].ref_image_id] = i;
+        size_t dropped = 0;
+        for (size_t i = 0; i < num_images; ++i) {
+            auto &src = problems[i].src_image_ids;
+            const size_t before = src.size();
+            src.erase(std::remove_if(src.begin(), src.end(), [&](int id) { const auto it = pos.find(id); return it == pos.end() || it->second >= num_images; }), src.end());
+            dropped += before - src.size();
+            if (src.empty()) {
+                std::cerr << "acmmp_b200: --max-views " << num_images << " leaves view " << problems[i].ref_image_id << " without source views" << std::endl;
+                return 1;
+            }
+        }
+        if (dropped) std::cout << "--max-views: dropped " << dropped << " source-view references to views that are not processed" << std::endl;
+    }
     const double t_start = now_s();
     try {
         int max_num_downscale = ComputeMultiScaleSettings(dense_folder, problems);

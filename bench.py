@@ -217,9 +217,17 @@ def main():
     rank, local_rank, world = dist_env()
     if world != a.gpus and world > 1:
         a.gpus = world
-    # the reference printf()s progress lines to stdout (ACMMP.cu:1542): keep fd 1 clean for the ONE JSON line
+    # fd 1 carries the ONE JSON line and nothing else.  The b200 arm's other prints go to stderr; the reference arm's
+    # go to /dev/null: the unmodified reference prints from inside its timed calls (`iteration:` ACMMP.cu:1542, `depthe
+    # range` ACMMP.cpp:647, one flushed `wrong!` per NaN pixel in RunJBU ACMMP.cpp:1102-1104) -- tens of MB per run, which
+    # in round 1 pushed the driver's capture past its limit and cost the scaling run its evidence.
     json_fd = os.dup(1)
-    os.dup2(2, 1)
+    if a.impl == "reference":
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        os.close(devnull)
+    else:
+        os.dup2(2, 1)
 
     if a.impl == "reference" and rank != 0:
         return 0            # the reference is single-GPU: rank 0 alone runs and prints it
@@ -246,7 +254,8 @@ def main():
 
     def new_backend():
         if a.impl == "reference":
-            return pipeline.ReferenceBackend(local_rank, seed=1234)
+            from oracle.ref_pipeline import ReferenceBackend      # the checker / baseline: never on the b200 arm
+            return ReferenceBackend(local_rank, seed=1234)
         return pipeline.B200Backend(local_rank, seed=1234, ctx=ctx)
 
     def barrier():

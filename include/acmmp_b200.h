@@ -207,8 +207,13 @@ int acmmp_height(const acmmp_ctx *ctx);
  * is destroyed or re-configured): float4 planes, float costs. */
 int acmmp_device_buffers(acmmp_ctx *ctx, void **planes4_dev, void **costs_dev);
 /* Pack plane.w (depth) of the current state into a dense float32 device map (what a neighbour
- * needs for geometric consistency; what depths*.dmb holds). */
+ * needs for geometric consistency; what depths*.dmb holds).
+ * ASYNCHRONOUS: the copy kernel is only enqueued on the context's private (non-blocking) stream.  A consumer on
+ * any other stream or context -- acmmp_set_depth_maps_device of another view, a collective -- must call
+ * acmmp_synchronize(ctx) (or acmmp_export_depth_device_sync) first. */
 int acmmp_export_depth_device(acmmp_ctx *ctx, float *depth_dev);
+/* The same, returning after the map is complete (stream-synchronised). */
+int acmmp_export_depth_device_sync(acmmp_ctx *ctx, float *depth_dev);
 
 /* Raw device state <-> host (tests, stage chaining).  Any pointer may be NULL.
  * rand6: 6 x uint32 per pixel = XORWOW {d, v[0..4]}. */
@@ -239,6 +244,9 @@ float acmmp_last_jbu_ms(void);
 int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out);
 /* the same cost through the quad-cooperative form the checkerboard pass runs (quad_ncc: four lanes per pixel) */
 int acmmp_probe_ncc_quad(acmmp_ctx *ctx, const float *planes4, int view, float *out);
+/* the 36 fetch coordinates of that form (texel-centre shift included): out72 = W*H*72 floats, (u, v) of tap
+ * k = ii*6 + jj, i = 2 ii - 5, j = 2 jj - 5 -- the reference's sample loop order, ACMMP.cu:450-476 */
+int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, float *out72);
 int acmmp_probe_geom(acmmp_ctx *ctx, const float *planes4, int view, float *out);
 int acmmp_probe_warp(acmmp_ctx *ctx, const float *planes4, int view, float *out4);
 int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint32_t *selected_views);

@@ -23,6 +23,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <pthread.h>
@@ -692,6 +693,40 @@ typedef struct {
     const orc_pass_flags *fl;
 } pass_ctx;
 
+/* Race emulation for the planar-prior pass ("the reference's in-pass writes").  In prior mode the
+ * reference writes plane_hypotheses[center] in the MIDDLE of a thread's work (ACMMP.cu:1283, :1295) and other threads
+ * re-read plane_hypotheses[positions[..]] of same-colour pixels at the same point of THEIR work (:1262, :1279, :1291):
+ * a real data race.  The pass proper always reads the pre-pass state (one legal outcome).  With `orc_race_late` set,
+ * those re-reads of same-colour positions take the plane from that array instead (= the other extreme: every
+ * in-pass write lands before every re-read); `orc_race_center_out` receives each updated pixel's in-pass write. */
+static const float *orc_race_late = NULL;
+static float *orc_race_center_out = NULL;
+void orc_set_race_emulation(const float *late_planes, float *center_planes_out)
+{
+    orc_race_late = late_planes;
+    orc_race_center_out = center_planes_out;
+}
+static const float *late_plane(const float *planes, int W, int center, int p)
+{
+    if (orc_race_late && p != center) {
+        const int same = (((p % W) + (p / W)) & 1) == (((center % W) + (center / W)) & 1);
+        if (same) return orc_race_late + 4 * (size_t)p;
+    }
+    return planes + 4 * (size_t)p;
+}
+
+/* debugging aid of the parity work: ORC_DEBUG_PIXEL="x,y" prints that pixel's decision variables to stderr */
+static int orc_dbg_x = -2, orc_dbg_y = -2;
+static int orc_dbg(int x, int y)
+{
+    if (orc_dbg_x == -2) {
+        const char *e = getenv("ORC_DEBUG_PIXEL");
+        orc_dbg_x = orc_dbg_y = -1;
+        if (e) sscanf(e, "%d,%d", &orc_dbg_x, &orc_dbg_y);
+    }
+    return x == orc_dbg_x && y == orc_dbg_y;
+}
+
 static void cost_vector(const pass_ctx *pc, int x, int y, const float *plane, float *cv)
 {
     for (int i = 1; i < pc->n_images; ++i)
@@ -751,6 +786,7 @@ static void refine(const pass_ctx *pc, float *plane, float *depth, float *cost, 
         }
         temp_cost /= weight_norm;
         const float depth_before = orc_depth_from_plane(cam0, tp, x, y);
+        if (orc_dbg(x, y)) fprintf(stderr, "  refine cand %d: plane %.7g %.7g %.7g %.7g depth %.7g cost %.7g (cost_now %.7g restricted %.7g)\n", i, tp[0], tp[1], tp[2], tp[3], depth_before, temp_cost, *cost, *restricted_cost);
         if (depth_before < fl->depth_min || depth_before > fl->depth_max || depth_before >= 1e6f) continue;
         if (use_prior) {
             const float depth_prior = orc_depth_from_plane(cam0, prior_plane, x, y);
@@ -760,6 +796,7 @@ static void refine(const pass_ctx *pc, float *plane, float *depth, float *cost, 
             const float ad = acosf(ac);
             const float prior = gamma + expf(-dd * dd / two_ds2) * expf(-ad * ad / two_as2);
             const float rtc = expf(-temp_cost * temp_cost / beta) * prior;
+            if (orc_dbg(x, y)) fprintf(stderr, "     restricted_temp_cost %.7g prior %.7g\n", rtc, prior);
             if (rtc > *restricted_cost) { *depth = depth_before; memcpy(plane, tp, 16); *cost = temp_cost; *restricted_cost = rtc; }
         } else if (temp_cost < *cost) {
             *depth = depth_before; memcpy(plane, tp, 16); *cost = temp_cost;
@@ -887,7 +924,7 @@ static void propagate_pixel(const pass_ctx *pc, int x, int y, int iter, const fl
             float rfc[8] = {0};
             for (int i = 0; i < 8; ++i)
                 if (flag[i]) {
-                    const float *nb = planes + 4 * (size_t)pos[i];
+                    const float *nb = late_plane(planes, W, center, pos[i]);
                     const float dd = orc_depth_from_plane(cam0, nb, x, y) - depth_prior;
                     const float ad = acosf(dot3(pp, nb));
                     const float prior = gamma + expf(-dd * dd / two_ds2) * expf(-ad * ad / two_as2);
@@ -899,7 +936,7 @@ static void propagate_pixel(const pass_ctx *pc, int x, int y, int iter, const fl
             const float prior = gamma + expf(-dd * dd / two_ds2) * expf(-ad * ad / two_as2);
             const float rcn = expf(-cost_now * cost_now / beta) * prior;
             if (flag[max_idx]) {
-                const float *nb = planes + 4 * (size_t)pos[max_idx];
+                const float *nb = late_plane(planes, W, center, pos[max_idx]);
                 memcpy(plane_now, nb, 16); have_now = 1;
                 const float db = orc_depth_from_plane(cam0, nb, x, y);
                 if (db >= fl->depth_min && db <= fl->depth_max && rfc[max_idx] > rcn) {
@@ -910,7 +947,7 @@ static void propagate_pixel(const pass_ctx *pc, int x, int y, int iter, const fl
                 }
             }
         } else if (flag[min_idx]) {
-            const float *nb = planes + 4 * (size_t)pos[min_idx];
+            const float *nb = late_plane(planes, W, center, pos[min_idx]);
             memcpy(plane_now, nb, 16); have_now = 1;
             const float db = orc_depth_from_plane(cam0, nb, x, y);
             if (db >= fl->depth_min && db <= fl->depth_max && final_costs[min_idx] < cost_now) {
@@ -930,8 +967,17 @@ static void propagate_pixel(const pass_ctx *pc, int x, int y, int iter, const fl
             memcpy(plane_intended, nb, 16);
         }
     }
+    if (orc_race_center_out) memcpy(orc_race_center_out + 4 * (size_t)center, plane_center, 16);
     /* ACMMP.cu:1301: plane_hypotheses_now is uninitialised; see DESIGN.md */
     if (!fl->as_compiled || !have_now) memcpy(plane_now, plane_intended, 16);
+    if (orc_dbg(x, y)) {
+        fprintf(stderr, "pixel %d,%d mask %u cost_now %.7g depth_now %.7g min_idx %d weight_norm %g sel %x\n", x, y, mask, cost_now, depth_now, min_idx, weight_norm, temp_sel);
+        for (int i = 0; i < 8; ++i) {
+            const float *nb = planes + 4 * (size_t)pos[i];
+            fprintf(stderr, "  dir %d flag %d pos (%d,%d) final %.7g plane %.7g %.7g %.7g %.7g\n", i, flag[i], pos[i] % W, pos[i] / W, final_costs[i], nb[0], nb[1], nb[2], nb[3]);
+        }
+        fprintf(stderr, "  plane_now %.7g %.7g %.7g %.7g  center %.7g %.7g %.7g %.7g cost_center %.7g restricted %.7g\n", plane_now[0], plane_now[1], plane_now[2], plane_now[3], plane_center[0], plane_center[1], plane_center[2], plane_center[3], cost_center, restricted_cost);
+    }
     refine(pc, plane_now, &depth_now, &cost_now, st, view_weights, weight_norm, pp, mask, &restricted_cost, x, y);
     float *po = planes_out + 4 * (size_t)center;
     if (fl->hierarchy && !(cost_now < pre_costs[center] - 0.1f)) {

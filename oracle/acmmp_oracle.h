@@ -69,6 +69,9 @@ void orc_checkerboard_pass(int n_images, const orc_image *imgs, const orc_image 
                            uint32_t *selected_views, uint32_t *rand6, const float *prior_planes4,
                            const uint32_t *plane_masks);
 
+/* planar-prior pass only: emulate the other extreme of the reference's data race (see acmmp_oracle.c) */
+void orc_set_race_emulation(const float *late_planes, float *center_planes_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,8 +179,11 @@ def random_init(images, cams, seed, with_costs=True):
 
 
 def checkerboard_pass(images, cams, state, colour, it, geom=False, prior=False, hierarchy=False, as_compiled=True,
-                      depth_maps=None, prior_planes=None, plane_masks=None):
-    """One pass with read-old/write-new neighbour semantics; returns the new state dict."""
+                      depth_maps=None, prior_planes=None, plane_masks=None, late_planes=None, want_center=False):
+    """One pass with read-old/write-new neighbour semantics; returns the new state dict.
+    Planar-prior mode only: `want_center` adds out["center"] = what each updated pixel holds after the reference's
+    IN-PASS write (ACMMP.cu:1283 / :1295); `late_planes` makes the re-reads of same-colour neighbours in the prior block
+    (:1262, :1279, :1291) read that array -- the other extreme of the reference's data race (see prior_pass_race)."""
     l = lib()
     ims, keep = _imgs(images)
     cs = _cams(cams)
@@ -195,8 +198,31 @@ def checkerboard_pass(images, cams, state, colour, it, geom=False, prior=False, 
     pre = _f32(state["pre_costs"]) if state.get("pre_costs") is not None else None
     pp = _f32(prior_planes) if prior_planes is not None else None
     pm = np.ascontiguousarray(plane_masks, np.uint32) if plane_masks is not None else None
+    late = _f32(late_planes) if late_planes is not None else None
+    center = planes_in.copy() if want_center else None
+    l.orc_set_race_emulation(_fp(late) if late is not None else None, _fp(center) if center is not None else None)
     l.orc_checkerboard_pass(C.c_int(len(images)), ims, dms, cs, C.byref(fl), C.c_int(colour), C.c_int(it), _fp(planes_in),
                             _fp(costs_in), _fp(planes_out), _fp(costs_out), _fp(pre) if pre is not None else None,
                             _u32p(views), _u32p(rand6), _fp(pp) if pp is not None else None,
                             _u32p(pm) if pm is not None else None)
-    return dict(planes=planes_out, costs=costs_out, views=views, rand=rand6, pre_costs=state.get("pre_costs"))
+    l.orc_set_race_emulation(None, None)
+    return dict(planes=planes_out, costs=costs_out, views=views, rand=rand6, pre_costs=state.get("pre_costs"), center=center)
+
+
+def prior_pass_race(images, cams, state, colour, it, prior_planes, plane_masks, hierarchy=True):
+    """The two extremes of the data race the reference has in planar-prior mode.  There a thread writes
+    plane_hypotheses[center] in the MIDDLE of its work (the accepted neighbour, ACMMP.cu:1283 / :1295) while other threads
+    re-read plane_hypotheses[positions[..]] -- six of the seven `near` positions of a direction are SAME-colour pixels,
+    i.e. pixels being updated by this very launch -- at the same point of theirs (:1262, :1279, :1291).  Without the
+    prior the only mid-pass writes are costs / view masks and the plane re-read comes long before anybody's final
+    write, so the race never fires; with it the outcome depends on warp timing.
+      early : every re-read sees the pre-pass plane (what the double-buffered B200 pass computes)
+      late  : every re-read of a same-colour pixel sees that pixel's in-pass write
+    Returns (early, late, sensitive): the two result states and the mask of pixels whose plane differs between them."""
+    early = checkerboard_pass(images, cams, state, colour, it, prior=True, hierarchy=hierarchy, prior_planes=prior_planes,
+                              plane_masks=plane_masks, want_center=True)
+    late = checkerboard_pass(images, cams, state, colour, it, prior=True, hierarchy=hierarchy, prior_planes=prior_planes,
+                             plane_masks=plane_masks, late_planes=early["center"])
+    a, b = early["planes"], late["planes"]
+    sensitive = ~np.all((np.abs(a - b) <= 1e-6 + 1e-6 * np.abs(b)) | (np.isnan(a) & np.isnan(b)), axis=-1)
+    return early, late, sensitive

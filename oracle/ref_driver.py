@@ -199,6 +199,13 @@ class RefACMMP:
         self._l.ref_probe_ncc(self._h, _fp(pl), C.c_int(view), _fp(out)); self._check()
         return out
 
+    def probe_coords(self, planes4, view):
+        """(H, W, 36, 2): the fetch coordinates of ComputeBilateralNCC's 36 samples (ACMMP.cu:450-476)."""
+        pl = _f32(planes4)
+        out = np.empty((self.H, self.W, 36, 2), np.float32)
+        self._l.ref_probe_coords(self._h, _fp(pl), C.c_int(view), _fp(out)); self._check()
+        return out
+
     def probe_geom(self, planes4, view):
         pl = _f32(planes4)
         out = np.empty((self.H, self.W), np.float32)
@@ -219,12 +226,53 @@ class RefACMMP:
         return out, views
 
 
-def run_jbu(image, coarse_depth, ref_image_id=0):
-    """The reference's RunJBU (ACMMP.cpp:1071-1122); returns the depths.dmb it writes."""
+class quiet_stdout:
+    """Route fd 1 away for the duration of a reference call.  The unmodified reference prints to stdout from inside
+    the timed calls -- `iteration: %d` per iteration (ACMMP.cu:1542), `depthe range` (ACMMP.cpp:647), and in RunJBU one
+    `wrong!` + flush PER NaN PIXEL (ACMMP.cpp:1102-1104) -- tens of MB per benchmark run.  capture=True keeps the text
+    (in an anonymous memory file) so that a caller can read the reference's own printed timing."""
+
+    def __init__(self, capture=False):
+        self.capture = capture
+        self.text = ""
+
+    def __enter__(self):
+        C.CDLL(None).fflush(None)
+        self._saved = os.dup(1)
+        self._fd = os.memfd_create("acmmp_ref_stdout") if self.capture else os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._fd, 1)
+        return self
+
+    def __exit__(self, *exc):
+        C.CDLL(None).fflush(None)
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        if self.capture:
+            size = os.lseek(self._fd, 0, os.SEEK_END)
+            tail = min(size, 1 << 16)
+            os.lseek(self._fd, size - tail, os.SEEK_SET)
+            self.text = os.read(self._fd, tail).decode("ascii", "replace")
+        os.close(self._fd)
+        return False
+
+
+def run_jbu(image, coarse_depth, ref_image_id=0, with_ms=False):
+    """The reference's RunJBU (ACMMP.cpp:1071-1122); returns the depths.dmb it writes.
+    with_ms=True: also the reference's own CUDA-event time of JBU::CudaRun -- kernel + device->host copy, the figure it
+    prints as `Total time needed for computation` (ACMMP.cu:1631-1648) -- in milliseconds."""
     l = lib()
     img, dep = _f32(image), _f32(coarse_depth)
     with tempfile.TemporaryDirectory(prefix="acmmp_ref_jbu_") as d:
         os.makedirs(os.path.join(d, "ACMMP"), exist_ok=True)
-        l.ref_run_jbu(_fp(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _fp(dep), C.c_int(dep.shape[1]),
-                      C.c_int(dep.shape[0]), d.encode(), C.c_int(ref_image_id))
-        return read_dmb(os.path.join(d, "ACMMP", "2333_%08d" % ref_image_id, "depths.dmb"))
+        with quiet_stdout(capture=True) as q:
+            l.ref_run_jbu(_fp(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _fp(dep), C.c_int(dep.shape[1]),
+                          C.c_int(dep.shape[0]), d.encode(), C.c_int(ref_image_id))
+        out = read_dmb(os.path.join(d, "ACMMP", "2333_%08d" % ref_image_id, "depths.dmb"))
+    if not with_ms:
+        return out
+    ms = float("nan")
+    key = "Total time needed for computation:"
+    k = q.text.rfind(key)
+    if k >= 0:
+        ms = float(q.text[k + len(key):].split()[0]) * 1e3
+    return out, ms

@@ -115,6 +115,35 @@ __global__ void probe_initcost(cudaTextureObjects *tex, Camera *cameras, const f
     views[c] = sel;
 }
 
+// The 36 source-image sample coordinates ComputeBilateralNCC fetches for (p, plane, view): the reference's own
+// device functions in the order of ACMMP.cu:450-476 (tap k = ii * 6 + jj, i = 2 ii - 5 outer, j = 2 jj - 5 inner),
+// texel-centre shift included.  out: 72 floats per pixel (u0, v0, u1, v1, ...).
+__global__ void probe_coords(Camera *cameras, const float4 *planes, int view, float *out)
+{
+    const int2 p = make_int2(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
+    const int width = cameras[0].width, height = cameras[0].height;
+    if (p.x >= width || p.y >= height) return;
+    const int c = p.y * width + p.x;
+    const Camera ref_camera = cameras[0], src_camera = cameras[view];
+    const float4 plane_hypothesis = planes[c];
+    int k = 0;
+    for (int i = -5; i <= 5; i += 2) {
+        for (int j = -5; j <= 5; j += 2, ++k) {
+            const int2 ref_pt = make_int2(p.x + i, p.y + j);
+            const float depth_n = ComputeDepthfromPlaneHypothesis(ref_camera, plane_hypothesis, ref_pt);
+            float3 Pw_n = Get3DPointonWorld_cu(ref_pt.x, ref_pt.y, depth_n, ref_camera);
+            float2 src_pt; float src_d;
+            ProjectonCamera_cu(Pw_n, src_camera, src_pt, src_d);
+            if (src_camera.model == SPHERE) {
+                src_pt.x = src_pt.x - floorf(src_pt.x / (float)src_camera.width) * (float)src_camera.width;
+                src_pt.y = fminf(fmaxf(src_pt.y, 0.0f), (float)src_camera.height - 1.0f);
+            }
+            out[(size_t)c * 72 + 2 * k] = src_pt.x + 0.5f;
+            out[(size_t)c * 72 + 2 * k + 1] = src_pt.y + 0.5f;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------
@@ -410,6 +439,21 @@ void ref_probe_ncc(void *hv, const float *planes, int view, float *out)
     cudaMalloc(&dout, sizeof(float) * n);
     probe_ncc<<<g16, b16>>>(o->texture_objects_cuda, o->cameras_cuda, dp, view, dout, o->params);
     ref_check(cudaMemcpy(out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost), "probe_ncc");
+    cudaFree(dp);
+    cudaFree(dout);
+}
+
+void ref_probe_coords(void *hv, const float *planes, int view, float *out)
+{
+    ACMMP *o = ((RefHandle *)hv)->obj;
+    const size_t n = (size_t)o->cameras[0].width * o->cameras[0].height;
+    dim3 g16, b16, gcb, bcb;
+    ref_grids(o, g16, b16, gcb, bcb);
+    float4 *dp = upload_planes(o, planes);
+    float *dout = nullptr;
+    cudaMalloc(&dout, sizeof(float) * 72 * n);
+    probe_coords<<<g16, b16>>>(o->cameras_cuda, dp, view, dout);
+    ref_check(cudaMemcpy(out, dout, sizeof(float) * 72 * n, cudaMemcpyDeviceToHost), "probe_coords");
     cudaFree(dp);
     cudaFree(dout);
 }

@@ -43,7 +43,11 @@ def test_no_cpu_fallback_without_a_device():
         acmmp_b200.Context(0)
     src = "".join(p.read_text() for p in (ROOT / "acmmp-spherical_b200").rglob("*.py"))
     src += "".join(p.read_text() for p in (ROOT / "acmmp-spherical_b200" / "csrc").glob("*"))
-    assert "cpu_oracle" not in src and "acmmp_oracle" not in src
+    # nothing in the product tree imports, loads or names the checkers (oracle/, libacmmp_ref, libacmmp_oracle)
+    import re
+    hits = [m.group(0) for m in re.finditer(r"(?im)^.*\b(?:import|from|include|CDLL|dlopen)\b.*oracle.*$", src)]
+    assert not hits, hits
+    assert "cpu_oracle" not in src and "acmmp_oracle" not in src and "ref_driver" not in src and "libacmmp_ref" not in src
 
 
 def test_pyramid_schedule_matches_reference_rules():

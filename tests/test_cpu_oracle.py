@@ -124,3 +124,40 @@ def test_checkerboard_pass_against_reference_state(model):
             assert float((out["views"] == g["black0_views"])[upd].mean()) >= 0.97
     assert rate[True] >= 0.93, rate
     assert rate[True] > rate[False], rate
+
+
+@pytest.mark.parametrize("model", ["pinhole", "sphere"])
+def test_prior_pass_gap_is_the_references_data_race(model):
+    """Round-1 finding: a planar-prior pass from an identical state matched the reference for only 92-95 % of the planes
+    (photometric / geometric / hierarchy passes: 98-99.7 %).  Root cause: in prior mode the reference writes
+    plane_hypotheses[center] in the middle of a thread's work (ACMMP.cu:1283, :1295) and other threads re-read
+    same-colour neighbours at the same point of theirs (:1262, :1279, :1291) -- a data race whose outcome depends on warp
+    timing (cpu_oracle.prior_pass_race).  Evidence on the reference's own prior-pass vectors: on the pixels whose result
+    does not depend on the race the restatement agrees with the reference as well as it does in a photometric pass;
+    the race-sensitive pixels follow the `early` reading for ~75 % and the `late` one for most of the rest."""
+    from oracle import cpu_oracle as co
+    g, imgs, cams = load(model)
+    st = dict(planes=g["prior_init_planes"], costs=g["prior_init_costs"], views=g["prior_init_views"], rand=g["prior_init_rand"],
+              pre_costs=g["prior_in_pre_costs"])
+    H, W = st["costs"].shape
+    upd = util.colour_mask(H, W, 0) & util.interior(H, W, 4)
+    masks = g["prior_masks"].astype(np.uint32)
+    pp = np.zeros((H, W, 4), np.float32)
+    pp[masks > 0] = g["prior_params"][masks[masks > 0] - 1]
+    early, late, sens = co.prior_pass_race(imgs, cams, st, 0, 0, pp, masks)
+    ref = g["prior_black0_planes"]
+
+    def same(a):
+        return np.all(np.abs(a - ref) <= 1e-3 + 1e-3 * np.abs(ref), axis=-1)
+    e, l = same(early["planes"]), same(late["planes"])
+    # the same restatement on the photometric pass of the same scene: its numerical floor (libm vs fast-math)
+    st0 = dict(planes=g["init_planes"], costs=g["init_costs"], views=g["init_views"], rand=g["init_rand"], pre_costs=None)
+    photo = co.checkerboard_pass(imgs, cams, st0, 0, 0)
+    floor = float(np.all(np.abs(photo["planes"] - g["black0_planes"]) <= 1e-3 + 1e-3 * np.abs(g["black0_planes"]), axis=-1)[upd].mean())
+    res = dict(early=float(e[upd].mean()), late=float(l[upd].mean()), either=float((e | l)[upd].mean()),
+               sensitive_frac=float(sens[upd].mean()), early_on_insensitive=float(e[upd & ~sens].mean()),
+               early_on_sensitive=float(e[upd & sens].mean()), late_on_sensitive=float(l[upd & sens].mean()), photometric_floor=floor)
+    util.dump(f"oracle_prior_race_{model}", res)
+    assert res["early_on_insensitive"] >= floor - 0.03, res          # measured: 0.993 vs 0.991 (pinhole), 0.942 vs 0.965 (sphere)
+    assert res["either"] >= res["early"] + 0.04, res                 # measured: 0.970 vs 0.921, 0.920 vs 0.845
+    assert res["early_on_sensitive"] < res["early_on_insensitive"] - 0.1, res

@@ -117,6 +117,59 @@ def test_ncc_through_the_quad_form_of_the_checkerboard_pass_matches_reference(mo
         assert v["vs_lane_form_1e4"] >= 0.98, (k, v)
 
 
+def _fraction_codes(c):
+    """The 1.8 fixed-point bilinear fraction the texture unit derives from a fetch coordinate (texel centres at +0.5):
+    index of the 1/256 cell of x - 0.5, under round-to-nearest and under truncation (both conventions are checked)."""
+    xb = c.astype(np.float64) - 0.5
+    return np.floor(xb * 256.0 + 0.5), np.floor(xb * 256.0)
+
+
+@pytest.mark.parametrize("model", ["pinhole", "sphere"])
+def test_ncc_residue_above_1e4_is_the_texture_units_fraction_quantisation(model):
+    """north_star: NCC at fixed planes within 1e-4.  98.7-99.7 % of the pixels are; this test shows what the rest is.
+    Both sides fetch the source image with the SAME hardware bilinear filter, whose fractions are 1.8 fixed point: the
+    sample value is a step function of the coordinate with steps every 1/256 px.  The reference computes a sample's
+    coordinate through its unfolded chain (PixelToDir, ray/plane, lift, R^T X + C, R X + t, project: ACMMP.cu:458-476),
+    this library through one folded transform per view -- same maths, different roundings, coordinates 1e-5..1e-4 px
+    apart.  Where such a pair of coordinates straddles a step, one tap's sample moves by (gradient / 256) and the cost by
+    ~1e-4..1e-3.  Measured here per pixel, with the coordinates of all 36 taps from both implementations:
+      * pixels where no tap's (u, v) changes its 1/256 cell: the costs agree to 2e-5 -- every one of them,
+      * every pixel whose cost differs by more than 1e-4 has at least one tap that changed cell.
+    I.e. the residue is the texture unit's quantisation applied to two correctly rounded evaluations of the same
+    formula, not a different formula."""
+    scene = util.scene_of(model)
+    ctx, *_ = _mine(scene)
+    ref = _ref(scene)
+    H, W = scene.images[0].shape
+    res = {}
+    for name, perturb in (("gt", 0.0), ("jitter", 0.05)):
+        planes = util.random_planes(scene, 0, seed=5, perturb=perturb)
+        for view in (1, 2):
+            a = ctx.probe_ncc_quad(planes, view)
+            b = ref.probe_ncc(planes, view)
+            ca = ctx.probe_coords(planes, view)
+            cb = ref.probe_coords(planes, view)
+            fin = np.isfinite(ca).all(axis=(2, 3)) & np.isfinite(cb).all(axis=(2, 3))
+            a1, a0 = _fraction_codes(np.where(np.isfinite(ca), ca, 0))
+            b1, b0 = _fraction_codes(np.where(np.isfinite(cb), cb, 0))
+            flips = ((a1 != b1) | (a0 != b0)).any(axis=3).sum(axis=2)          # taps per pixel whose cell differs
+            clean = (flips == 0) & fin & util.interior(H, W, 6)
+            d = np.abs(a.astype(np.float64) - b)
+            tol = 1e-4 + 1e-4 * np.abs(b)
+            above = (d > tol) & fin & util.interior(H, W, 6)
+            res[f"{name}_v{view}"] = dict(
+                frac_1e4=float((d <= tol).mean()), clean_frac=float(clean.mean()),
+                clean_within_2e5=float((d[clean] <= 2e-5 + 2e-5 * np.abs(b[clean])).mean()) if clean.any() else 1.0,
+                clean_max=float(d[clean].max()) if clean.any() else 0.0,
+                above_1e4=int(above.sum()), above_with_flip=int((above & (flips > 0)).sum()),
+                max_coord_diff_px=float(np.abs(np.where(fin[..., None, None], ca - cb, 0)).max()),
+                mean_flipped_taps=float(flips[fin].mean()))
+    dump(f"ncc_residue_{model}", res)
+    for k, v in res.items():
+        assert v["clean_within_2e5"] >= 0.9999, (k, v)
+        assert v["above_with_flip"] == v["above_1e4"], (k, v)
+
+
 @pytest.mark.parametrize("model", ["pinhole", "sphere"])
 def test_initial_cost_and_views_match_reference(model):
     scene = util.scene_of(model)
@@ -247,10 +300,13 @@ def test_single_pass_photometric(model):
     res["red_it1"] = r2
     dump(f"pass_photo_{model}", res)
     for k, v in res.items():
-        best = max(v["mode0"]["plane_match"], v["mode1"]["plane_match"])
-        assert best >= 0.90, (k, v)
+        # as-compiled reading of the uninitialised plane variable (ACMMP.cu:1301) = the oracle's behaviour.  Measured (B200):
+        # 0.9975 / 0.9932 / 0.9806 pinhole, 0.9975 / 0.9943 / 0.9901 sphere; red_it1 starts from a state one more racy
+        # reference pass away
+        assert v["mode1"]["plane_match"] >= (0.975 if k == "red_it1" else 0.988), (k, v)
+        assert v["mode1"]["plane_match"] > v["mode0"]["plane_match"], (k, v)
         assert v["mode1"]["untouched_ok"] == 1.0, (k, v)
-        assert max(v["mode0"]["rng_match"], v["mode1"]["rng_match"]) >= 0.97, (k, v)
+        assert v["mode1"]["rng_match"] >= 0.995, (k, v)
 
 
 @pytest.mark.parametrize("model", ["pinhole", "sphere"])
@@ -279,12 +335,32 @@ def test_single_pass_geom(model):
     dump(f"pass_geom_{model}", res)
     assert res["init"]["planes"] >= 0.999 and res["init"]["costs"] >= 0.99, res
     for k in ("black_it0", "red_it0"):
-        assert max(res[k]["mode0"]["plane_match"], res[k]["mode1"]["plane_match"]) >= 0.90, (k, res[k])
+        assert res[k]["mode1"]["plane_match"] >= 0.99, (k, res[k])             # measured 0.9954 .. 0.9965
+
+
+def _race_sensitive(scene, st, colour, params, masks):
+    """Pixels whose result of a planar-prior pass depends on the reference's data race (oracle.cpu_oracle.prior_pass_race:
+    the CPU restatement run under both extreme interleavings)."""
+    from oracle import cpu_oracle
+    imgs, cams, _ = scene.problem(0)
+    H, W = masks.shape
+    m = masks.astype(np.uint32)
+    pp = np.zeros((H, W, 4), np.float32)
+    pp[m > 0] = np.asarray(params, np.float32)[m[m > 0] - 1]
+    _, _, sens = cpu_oracle.prior_pass_race(imgs, cams, st, colour, 0, pp, m, hierarchy=True)
+    return sens
 
 
 def test_single_pass_prior_and_hierarchy():
-    """Planar-prior stage on top of a hierarchy stage (the level > 0 schedule, main.cpp:453-458)."""
-    import cv2
+    """Planar-prior stage on top of a hierarchy stage (the level > 0 schedule, main.cpp:453-458).
+    Hierarchy passes must agree like photometric ones.  Planar-prior passes cannot: there the reference has a data race
+    that FIRES -- a thread stores plane_hypotheses[center] in the middle of its work (ACMMP.cu:1283, :1295) while threads
+    of other warps re-read that same-colour pixel at the same point of theirs (:1262, :1279, :1291); without the prior the
+    re-read comes long before anybody's store and the race is benign (tests/test_cpu_oracle.py::
+    test_prior_pass_gap_is_the_references_data_race has the evidence on the reference's own vectors).  This library reads
+    the pre-pass state throughout (double-buffered), one legal outcome.  Asserted: on the pixels whose result does not
+    depend on the race the agreement is that of a photometric pass; overall it is the measured 95 / 92 % minus a margin;
+    and the reference does not even reproduce itself across two launches from the same state on the sensitive pixels."""
     scene = util.pinhole_scene()
     H, W = scene.images[0].shape
     rng = np.random.default_rng(3)
@@ -321,13 +397,36 @@ def test_single_pass_prior_and_hierarchy():
     res["init_prior"] = dict(planes=close_frac(a["planes"], b["planes"], 1e-4, 1e-4),
                              costs=close_frac(a["costs"], b["costs"], 1e-4, 1e-4),
                              rng=float((a["rand"] == b["rand"]).all(axis=-1).mean()))
-    res["prior_black"], _, _ = _pass_compare(ctx, ref, 0, 0, H, W)
-    res["prior_red"], _, _ = _pass_compare(ctx, ref, 1, 0, H, W)
+    for name, colour in (("prior_black", 0), ("prior_red", 1)):
+        st0 = ref.download_state(rand=True, pre_costs=True)
+        sens = _race_sensitive(scene, st0, colour, params, masks)
+        r, out, b1 = _pass_compare(ctx, ref, colour, 0, H, W)
+        # the reference against ITSELF: the same launch again from the same state
+        ref.upload_state(planes=st0["planes"], costs=st0["costs"], views=st0["views"], rand=st0["rand"], pre_costs=st0["pre_costs"])
+        ref.launch_pass(colour, 0)
+        b2 = ref.download_state()
+        upd = util.colour_mask(H, W, colour) & util.interior(H, W, 4)
+
+        def same(p, q):
+            return np.all((np.abs(p - q) <= 1e-4 + 1e-4 * np.abs(q)) | (np.isnan(p) & np.isnan(q)), axis=-1)
+        mine_ok = same(out[1]["planes"], b1["planes"])
+        self_ok = same(b2["planes"], b1["planes"])
+        r["race"] = dict(sensitive_frac=float(sens[upd].mean()),
+                         mine_on_insensitive=float(mine_ok[upd & ~sens].mean()), mine_on_sensitive=float(mine_ok[upd & sens].mean()),
+                         ref_vs_ref=float(self_ok[upd].mean()), ref_vs_ref_on_insensitive=float(self_ok[upd & ~sens].mean()),
+                         ref_vs_ref_on_sensitive=float(self_ok[upd & sens].mean()))
+        res[name] = r
     dump("pass_prior_hier", res)
     assert res["init_upsample"]["planes"] >= 0.999 and res["init_upsample"]["pre_costs"] >= 0.99, res
     assert res["init_prior"]["planes"] >= 0.999 and res["init_prior"]["rng"] == 1.0, res
-    for k in ("hier_black", "hier_red", "prior_black", "prior_red"):
-        assert max(res[k]["mode0"]["plane_match"], res[k]["mode1"]["plane_match"]) >= 0.90, (k, res[k])
+    for k in ("hier_black", "hier_red"):
+        assert res[k]["mode1"]["plane_match"] >= 0.985, (k, res[k])            # measured 0.992 / 0.991
+    # measured 0.953 / 0.920 overall (round 1), minus 0.5 %
+    assert res["prior_black"]["mode1"]["plane_match"] >= 0.948, res["prior_black"]
+    assert res["prior_red"]["mode1"]["plane_match"] >= 0.915, res["prior_red"]
+    for k in ("prior_black", "prior_red"):
+        assert res[k]["race"]["mine_on_insensitive"] >= 0.98, (k, res[k])
+        assert res[k]["race"]["mine_on_sensitive"] < res[k]["race"]["mine_on_insensitive"], (k, res[k])
 
 
 # ------------------------------------------------------------------------------------------
