@@ -83,7 +83,7 @@ _EXPORTS = [
     "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_export_depth_device_sync", "acmmp_download_state", "acmmp_upload_state",
-    "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_ncc_quad", "acmmp_probe_coords", "acmmp_probe_geom", "acmmp_probe_warp",
+    "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_coords", "acmmp_probe_geom", "acmmp_probe_warp",
     "acmmp_probe_initcost", "acmmp_last_timings", "acmmp_launch_count",
 ]
 
@@ -342,18 +342,12 @@ class Context:
         self._ck(self._l.acmmp_probe_ncc(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_ncc")
         return out
 
-    def probe_ncc_quad(self, planes4, view):
-        """The same cost through quad_ncc, the form the checkerboard pass runs."""
-        p = _f32(planes4)
-        out = np.empty((self.H, self.W), np.float32)
-        self._ck(self._l.acmmp_probe_ncc_quad(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_ncc_quad")
-        return out
-
-    def probe_coords(self, planes4, view):
-        """(H, W, 36, 2): the fetch coordinates of quad_ncc's 36 samples, reference tap order."""
+    def probe_coords(self, planes4, view, variant=0):
+        """(H, W, 36, 2): the fetch coordinates of quad_ncc's 36 samples, reference tap order.
+        variant 1 / 2 (SPHERE): through the packed two-hypothesis form, as its first / second hypothesis."""
         p = _f32(planes4)
         out = np.empty((self.H, self.W, 36, 2), np.float32)
-        self._ck(self._l.acmmp_probe_coords(self._h, _fp(p), C.c_int(view), _fp(out)), "acmmp_probe_coords")
+        self._ck(self._l.acmmp_probe_coords(self._h, _fp(p), C.c_int(view), C.c_int(variant), _fp(out)), "acmmp_probe_coords")
         return out
 
     def probe_geom(self, planes4, view):

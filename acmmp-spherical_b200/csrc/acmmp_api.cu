@@ -534,7 +534,7 @@ NccTable ncc_table(const acmmp_ctx *ctx)
     return nt;
 }
 
-template <int MODEL> size_t smem_tp(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT>(nsrc, kTpNT, 0).total; }
+template <int MODEL> size_t smem_quad(int nsrc) { return SmemLayout<MODEL, kTpTW, kTpTH, kPqWRS, kPqNT>(nsrc, kPqPix, 0, kTqPerHyp).total; }
 template <int MODEL> size_t smem_pass(int nsrc) { return SmemLayout<MODEL, kPassTW, kPassTH, kPassWRS, kPassNT>(nsrc, kPassNT, kPassPix, kPassTq, 2).total; }
 
 int configure_kernels(acmmp_ctx *ctx)
@@ -553,7 +553,6 @@ int configure_kernels(acmmp_ctx *ctx)
         SETATTR((k_pass<kModelPinhole, kModePhoto>)) SETATTR((k_pass<kModelPinhole, kModePrior>)) SETATTR((k_pass<kModelPinhole, kModeGeom>))
         SETATTR((k_pass<kModelSphere, kModePhoto>)) SETATTR((k_pass<kModelSphere, kModePrior>)) SETATTR((k_pass<kModelSphere, kModeGeom>))
         SETATTR(k_random_init<kModelPinhole>) SETATTR(k_random_init<kModelSphere>)
-        SETATTR(k_probe<kModelPinhole>) SETATTR(k_probe<kModelSphere>)
         SETATTR(k_probe_quad<kModelPinhole>) SETATTR(k_probe_quad<kModelSphere>)
 #undef SETATTR
         if (result != cudaSuccess) (void)cudaGetLastError();      // not sticky; a later context on this device retries
@@ -799,7 +798,9 @@ int launch_init(acmmp_ctx *ctx)
 {
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
-    k_random_init<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp);
+    const size_t smem = smem_quad<MODEL>(fc.nsrc);
+    if (smem > 227 * 1024) return fail(ctx, ACMMP_E_UNSUPPORTED, "k_random_init: too many source views for one SM's shared memory");
+    k_random_init<MODEL><<<grid, kPqNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp);
     ctx->launches++;
     CK(cudaGetLastError());
     return ACMMP_OK;
@@ -909,24 +910,25 @@ int collect_timings(acmmp_ctx *ctx)
 }
 
 template <int MODEL>
-int launch_probe(acmmp_ctx *ctx, int mode, int view, const float4 *planes_dev, float *out, float4 *out4, uint32_t *out_views)
+int launch_probe(acmmp_ctx *ctx, int mode, int view, const float4 *planes_dev, float *out, float4 *out4)
 {
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
-    k_probe<MODEL><<<grid, kTpNT, smem_tp<MODEL>(fc.nsrc), ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp, mode, view, planes_dev, out, out4, out_views);
+    k_probe<MODEL><<<grid, 128, 0, ctx->stream>>>(fc, mode, view, planes_dev, out, out4);
     ctx->launches++;
     CK(cudaGetLastError());
     return ACMMP_OK;
 }
 
+// view >= 1: NCC against that view; view == 0: initial cost + selected views (all views)
 template <int MODEL>
-int launch_probe_quad(acmmp_ctx *ctx, int view, const float4 *planes_dev, float *out)
+int launch_probe_quad(acmmp_ctx *ctx, int view, const float4 *planes_dev, float *out, uint32_t *out_views)
 {
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + kTpTW - 1) / kTpTW, (ctx->H + kTpTH - 1) / kTpTH);
-    const size_t smem = SmemLayout<MODEL, kTpTW, kTpTH, kPqWRS, kPqNT>(fc.nsrc, 0, 0, kTqPerHyp).total;
+    const size_t smem = smem_quad<MODEL>(fc.nsrc);
     if (smem > 227 * 1024) return fail(ctx, ACMMP_E_UNSUPPORTED, "k_probe_quad: too many source views for one SM's shared memory");
-    k_probe_quad<MODEL><<<grid, kPqNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp, view, planes_dev, out);
+    k_probe_quad<MODEL><<<grid, kPqNT, smem, ctx->stream>>>(fc, ctx->ncc, ctx->tmap_tp, view, planes_dev, out, out_views);
     ctx->launches++;
     CK(cudaGetLastError());
     return ACMMP_OK;
@@ -950,12 +952,13 @@ int run_probe(acmmp_ctx *ctx, int mode, int view, const float *planes4, float *o
     CK(tmp.d(&dout, sizeof(float) * npx));
     CK(tmp.d(&dv, sizeof(uint32_t) * npx));
     CK(cudaMemcpyAsync(dp, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
-    if (mode == 4)
-        rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe_quad<kModelPinhole>(ctx, view, dp, dout)
-                                                         : launch_probe_quad<kModelSphere>(ctx, view, dp, dout);
-    else
-        rc = (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) ? launch_probe<kModelPinhole>(ctx, mode, view, dp, dout, do4, dv)
-                                                         : launch_probe<kModelSphere>(ctx, mode, view, dp, dout, do4, dv);
+    const bool pinhole = ctx->cams[0].model == ACMMP_MODEL_PINHOLE;
+    if (mode == 0 || mode == 3) {          // the NCC forms: through quad_ncc, like every kernel of the library
+        const int v = (mode == 3) ? 0 : view;
+        rc = pinhole ? launch_probe_quad<kModelPinhole>(ctx, v, dp, dout, dv) : launch_probe_quad<kModelSphere>(ctx, v, dp, dout, dv);
+    } else {
+        rc = pinhole ? launch_probe<kModelPinhole>(ctx, mode, view, dp, dout, do4) : launch_probe<kModelSphere>(ctx, mode, view, dp, dout, do4);
+    }
     if (rc == ACMMP_OK) {
         if (out) CK(cudaMemcpyAsync(out, dout, sizeof(float) * npx, cudaMemcpyDeviceToHost, ctx->stream));
         if (out4) CK(cudaMemcpyAsync(out4, do4, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1500,7 +1503,7 @@ int acmmp_jbu(int device, const float *image, int w, int h, const float *coarse_
     return rc;
 }
 
-int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, float *out72)
+int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, int variant, float *out72)
 {
     int rc = check_ready(ctx);
     if (rc) return rc;
@@ -1515,8 +1518,8 @@ int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, float *ou
     CK(cudaMemcpyAsync(dp, planes4, sizeof(float4) * npx, cudaMemcpyHostToDevice, ctx->stream));
     const FrameConst fc = frame_const(ctx);
     dim3 grid((ctx->W + 15) / 16, (ctx->H + 7) / 8);
-    if (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) k_probe_coords<kModelPinhole><<<grid, 128, 0, ctx->stream>>>(fc, ctx->ncc, view, dp, dout);
-    else k_probe_coords<kModelSphere><<<grid, 128, 0, ctx->stream>>>(fc, ctx->ncc, view, dp, dout);
+    if (ctx->cams[0].model == ACMMP_MODEL_PINHOLE) k_probe_coords<kModelPinhole><<<grid, 128, 0, ctx->stream>>>(fc, ctx->ncc, view, variant, dp, dout);
+    else k_probe_coords<kModelSphere><<<grid, 128, 0, ctx->stream>>>(fc, ctx->ncc, view, variant, dp, dout);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out72, dout, sizeof(float) * 72 * npx, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1525,7 +1528,6 @@ int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, float *ou
 }
 
 int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 0, view, planes4, out, nullptr, nullptr); }
-int acmmp_probe_ncc_quad(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 4, view, planes4, out, nullptr, nullptr); }
 int acmmp_probe_geom(acmmp_ctx *ctx, const float *planes4, int view, float *out) { return run_probe(ctx, 1, view, planes4, out, nullptr, nullptr); }
 int acmmp_probe_warp(acmmp_ctx *ctx, const float *planes4, int view, float *out4) { return run_probe(ctx, 2, view, planes4, nullptr, out4, nullptr); }
 int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint32_t *selected_views)

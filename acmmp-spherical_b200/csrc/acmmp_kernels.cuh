@@ -3,8 +3,8 @@
 //   k_pass            : one red/black checkerboard pass      (reference Black/RedPixelUpdate,
 //                       CheckerboardPropagation + PlaneHypothesisRefinement, ACMMP.cu:797-1349)
 //   k_random_init     : RandomInitialization, all four branches            (ACMMP.cu:673-795)
-//   k_probe, k_probe_quad : sub-kernel probes for parity tests (the device code of the two above: lane-per-plane
-//                       NCC of the init kernel, quad-cooperative NCC of the pass)
+//   k_probe, k_probe_quad, k_probe_coords : sub-kernel probes for parity tests (the device code of the two above:
+//                       warp chain / geometric term, the quad-cooperative NCC, its fetch coordinates)
 //   k_depth_normal    : GetDepthandNormal                                  (ACMMP.cu:1351-1364)
 //   k_median_filter   : Black/RedPixelFilter                               (ACMMP.cu:1366-1504)
 //   k_jbu             : JBU_cu                                             (ACMMP.cu:1558-1616)
@@ -113,20 +113,35 @@ __device__ __forceinline__ PixCtx make_pix(const FrameConst &fc, const int x, co
     return px;
 }
 
-// ComputeMultiViewInitialCostandSelectedViews, ACMMP.cu:519-556.  costrow: nsrc floats (scratch).
-// Must be called by all 32 lanes.
+// ComputeMultiViewInitialCostandSelectedViews, ACMMP.cu:519-556, in the quad-cooperative form: the four lanes of a quad
+// evaluate their pixel's plane against every source view with quad_ncc (2x2 tap blocks: one texture wavefront per quad
+// request; the lane-per-plane form this replaces needed 2.46), the view loop is warp-uniform, the cost row of the
+// pixel lives in shared memory and all four lanes then run the (cheap) top-k selection redundantly.
+// costrow: nsrc floats of scratch per pixel.  Must be called by all 32 lanes; `want` false = nothing evaluated.
 template <int MODEL, int RW, int WRS, int TQS>
-__device__ __forceinline__ float init_cost_and_views(const FrameConst &fc, const NccTable &nt, const NccConst *s_ncc,
-                                                     const typename AuxType<MODEL>::type *aux, const float2 *wr, const float *rr,
-                                                     const PixCtx &px, const float4 &plane, float *costrow, uint32_t &selected,
-                                                     float *tq)
+__device__ __forceinline__ float init_cost_and_views_quad(const FrameConst &fc, const NccTable &nt, const NccConst *s_ncc,
+                                                          const typename AuxType<MODEL>::type *aux, const float2 *wr, const float *rr,
+                                                          const PixCtx &px, const float4 &plane, const int q, const bool want,
+                                                          float *costrow, uint32_t &selected, float *tq)
 {
+    constexpr unsigned FULL = 0xffffffffu;
     const float cost_max = 2.0f;
-    const uint32_t all = (fc.nsrc >= 32) ? 0xffffffffu : ((1u << fc.nsrc) - 1u);
-    ncc_views<MODEL, RW, WRS, TQS>(fc, nt, s_ncc, aux, wr, rr, px, plane, all, costrow, 1, tq);
+    __syncwarp(FULL);                                   // the previous evaluation's rows and tap depths are free
+    quad_fill_depths<MODEL, RW, TQS>(fc, aux, px, plane, q, tq);
+    __syncwarp(FULL);
+    for (int v = 0; v < fc.nsrc; ++v) {
+        const ViewK c = load_view(s_ncc + v);
+        FetchView fetch;
+        fetch.tex = (cudaTextureObject_t)nt.tex[v];
+        quad_ncc<MODEL, 1, RW, WRS, TQS>(
+            c, px, aux, wr, rr, tq, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
+            [&](const int, const float cst) { costrow[v] = cst; });
+    }
+    __syncwarp(FULL);
+    selected = 0;
+    if (!want) return cost_max;
     int num_valid = 0;
     for (int i = 0; i < fc.nsrc; ++i) num_valid += (costrow[i] < cost_max) ? 1 : 0;
-    selected = 0;
     const int top_k = min(num_valid, 4);      // params.top_k, ACMMP.h:40
     if (top_k <= 0) return cost_max;
     // the top_k smallest costs in ascending order == the head of the reference's sorted vector
@@ -151,70 +166,36 @@ __device__ __forceinline__ float init_cost_and_views(const FrameConst &fc, const
 }
 
 // ------------------------------------------------------------------------------------------
-// probes (parity tests): mode 0 ncc(view), 1 geom(view), 2 warp(view), 3 initial cost + views
-// thread per pixel, 16x8 tile
+// probes (parity tests) of the per-pixel geometry: mode 1 geom(view), 2 warp(view); thread per pixel
 // ------------------------------------------------------------------------------------------
-constexpr int kTpTW = 16, kTpTH = 8, kTpNT = 128;
+constexpr int kTpTW = 16, kTpTH = 8;
 
 template <int MODEL>
-__global__ void __launch_bounds__(kTpNT)
-k_probe(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap, const int mode, const int view,
-        const float4 *__restrict__ planes, float *__restrict__ out, float4 *__restrict__ out4, uint32_t *__restrict__ out_views)
+__global__ void __launch_bounds__(128)
+k_probe(const __grid_constant__ FrameConst fc, const int mode, const int view, const float4 *__restrict__ planes,
+        float *__restrict__ out, float4 *__restrict__ out4)
 {
-    typedef TileGeom<kTpTW, kTpTH> TG;
-    typedef typename AuxType<MODEL>::type AuxT;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT> L(fc.nsrc, kTpNT, 0);
-    float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
-    AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
-    float2 *wr = reinterpret_cast<float2 *>(smem + L.off_wr) + threadIdx.x;
-    float *rr = reinterpret_cast<float *>(smem + L.off_rr) + threadIdx.x;
-    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
-    ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
-    NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
-    float *cost = reinterpret_cast<float *>(smem + L.off_cost);
-
-    const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
-    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
-
-    // Threads that fall outside the image stay alive on a clamped pixel (nothing stored): the warp
-    // walks the view loops in lock step, see ncc_views.
-    const int tid = threadIdx.x;
-    const int xx = x0 + (tid % kTpTW), yy = y0 + (tid / kTpTW);
-    const bool valid = xx < fc.W && yy < fc.H;
-    const int x = min(xx, fc.W - 1), y = min(yy, fc.H - 1);
+    const int x = blockIdx.x * kTpTW + (threadIdx.x % kTpTW), y = blockIdx.y * kTpTH + (threadIdx.x / kTpTW);
+    if (x >= fc.W || y >= fc.H) return;
     const int center = y * fc.W + x;
-    PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
-    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, wr, rr, 0, 1);
-    full_sums<kTpNT>(wr, rr, px);
+    const PixCtx px = make_pix<MODEL>(fc, x, y, 0, 0);
     const float4 plane = planes[center];
-    const int nvp = fc.nsrc | 1;
-    float *costrow = cost + tid * nvp;
-
-    if (mode == 0) {
-        ncc_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, wr, rr, px, plane, 1u << (view - 1), costrow, 1, tq);
-        if (valid) out[center] = costrow[view - 1];
-    } else if (mode == 1) {
-        if (valid) out[center] = geom_cost<MODEL>(fc, s_vc[view - 1], px, plane);
-    } else if (mode == 2) {
+    const ViewConst &vc = fc.views[view - 1];
+    if (mode == 1) {
+        out[center] = geom_cost<MODEL>(fc, vc, px, plane);
+    } else {
         const float depth = plane_depth(plane, px.dir);
         float sx, sy, sd;
-        forward_project<MODEL>(fc, s_vc[view - 1], px, depth, sx, sy, sd);
-        if (valid) out4[center] = make_float4(sx, sy, sd, depth);
-    } else {
-        uint32_t sel;
-        const float c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, wr, rr, px, plane, costrow, sel, tq);
-        if (valid) {
-            out[center] = c;
-            out_views[center] = sel;
-        }
+        forward_project<MODEL>(fc, vc, px, depth, sx, sy, sd);
+        out4[center] = make_float4(sx, sy, sd, depth);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// probe of the NCC form k_pass runs: fixed plane per pixel, one source view, through quad_ncc (four lanes per pixel,
-// one hypothesis) with the same tables fill_weights / full_sums / quad_fill_depths build inside k_pass.
+// probe of the NCC form every kernel here runs: fixed plane per pixel through quad_ncc (four lanes per pixel, one
+// hypothesis) with the same tables fill_weights / full_sums / quad_fill_depths build inside k_pass / k_random_init.
+//   view >= 1 : ComputeBilateralNCC against that source view                       -> out
+//   view == 0 : ComputeMultiViewInitialCostandSelectedViews (all views + top-k)    -> out, out_views
 // 16x8 pixel tile, 512 threads.
 // ------------------------------------------------------------------------------------------
 constexpr int kPqPix = kTpTW * kTpTH, kPqNT = 4 * kPqPix, kPqWRS = kPqPix + 8;
@@ -222,17 +203,18 @@ constexpr int kPqPix = kTpTW * kTpTH, kPqNT = 4 * kPqPix, kPqWRS = kPqPix + 8;
 template <int MODEL>
 __global__ void __launch_bounds__(kPqNT)
 k_probe_quad(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap, const int view,
-             const float4 *__restrict__ planes, float *__restrict__ out)
+             const float4 *__restrict__ planes, float *__restrict__ out, uint32_t *__restrict__ out_views)
 {
     typedef TileGeom<kTpTW, kTpTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kTpTW, kTpTH, kPqWRS, kPqNT> L(fc.nsrc, 0, 0, kTqPerHyp);
+    const SmemLayout<MODEL, kTpTW, kTpTH, kPqWRS, kPqNT> L(fc.nsrc, kPqPix, 0, kTqPerHyp);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
     NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
+    float *cost = reinterpret_cast<float *>(smem + L.off_cost);
 
     const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
     stage_tile<MODEL, kTpTW, kTpTH, kPqNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
@@ -250,6 +232,16 @@ k_probe_quad(const __grid_constant__ FrameConst fc, const __grid_constant__ NccT
     fill_weights<MODEL, TG::PW, kPqWRS>(fc, tile_r, px, wr, rr, q, 4);
     __syncwarp(0xffffffffu);
     full_sums<kPqWRS>(wr, rr, px);
+    if (view == 0) {
+        uint32_t sel;
+        const float c = init_cost_and_views_quad<MODEL, TG::RW, kPqWRS, kPqNT>(fc, nt, s_ncc, aux, wr, rr, px, planes[center], q, valid,
+                                                                               cost + p * (fc.nsrc | 1), sel, tq);
+        if (valid && q == 0) {
+            out[center] = c;
+            out_views[center] = sel;
+        }
+        return;
+    }
     quad_fill_depths<MODEL, TG::RW, kPqNT>(fc, aux, px, planes[center], q, tq);
     __syncwarp(0xffffffffu);
     const ViewK c = load_view(s_ncc + (view - 1));
@@ -268,7 +260,7 @@ k_probe_quad(const __grid_constant__ FrameConst fc, const __grid_constant__ NccT
 // ------------------------------------------------------------------------------------------
 template <int MODEL>
 __global__ void __launch_bounds__(128)
-k_probe_coords(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const int view,
+k_probe_coords(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const int view, const int variant,
                const float4 *__restrict__ planes, float *__restrict__ out)
 {
     typedef typename AuxType<MODEL>::type AuxT;
@@ -295,6 +287,15 @@ k_probe_coords(const __grid_constant__ FrameConst fc, const __grid_constant__ Nc
                 const float t = ray.depth(a, i, j);
                 float u, v;
                 tap_coords(c, vt, a, t, c.a[11], u, v);
+                if (MODEL == kModelSphere && variant != 0) {
+                    // the two-hypothesis packed form of the pass (sphere_coords2), this plane as its first / second
+                    // hypothesis next to an unrelated one: must give the same bits as the scalar form
+                    float2 uv0, uv1;
+                    const float4 *dir = reinterpret_cast<const float4 *>(&a);
+                    if (variant == 1) sphere_coords2(c, *dir, make_float2(t, 1.01f * t), uv0, uv1);
+                    else sphere_coords2(c, *dir, make_float2(0.97f * t, t), uv1, uv0);
+                    u = uv0.x; v = uv0.y;
+                }
                 const int k = (2 * bx + qi) * 6 + (2 * by + qj);
                 out[(size_t)center * 72 + 2 * k] = u;
                 out[(size_t)center * 72 + 2 * k + 1] = v;
@@ -319,37 +320,50 @@ __device__ __forceinline__ float range_gauss(float x, float sigma)
     return (float)exp(-1.0 * (double)(x_p * x_p) / (double)(2 * sigma * sigma));
 }
 
+// Four lanes per pixel (16x8 pixel tile, 512 threads): the per-pixel part (RNG draws, plane construction) is computed by
+// all four lanes redundantly -- same inputs, same operations, same bits -- and the cost evaluations run in the
+// quad-cooperative NCC form (init_cost_and_views_quad).
+#ifndef ACMMP_INIT_MIN_CTAS
+#define ACMMP_INIT_MIN_CTAS 2      // 64 registers: two 512-thread CTAs per SM (~92 KB of shared memory each)
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(kTpNT)
+__global__ void __launch_bounds__(kPqNT, ACMMP_INIT_MIN_CTAS)
 k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable nt, const __grid_constant__ CUtensorMap tmap)
 {
     typedef TileGeom<kTpTW, kTpTH> TG;
     typedef typename AuxType<MODEL>::type AuxT;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout<MODEL, kTpTW, kTpTH, kTpNT, kTpNT> L(fc.nsrc, kTpNT, 0);
+    const SmemLayout<MODEL, kTpTW, kTpTH, kPqWRS, kPqNT> L(fc.nsrc, kPqPix, 0, kTqPerHyp);
     float *tile_r = reinterpret_cast<float *>(smem + L.off_tile);
     AuxT *aux = reinterpret_cast<AuxT *>(smem + L.off_aux);
-    float2 *mywr = reinterpret_cast<float2 *>(smem + L.off_wr) + threadIdx.x;
-    float *myrr = reinterpret_cast<float *>(smem + L.off_rr) + threadIdx.x;
-    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + threadIdx.x;
     ViewConst *s_vc = reinterpret_cast<ViewConst *>(smem + L.off_vc);
     NccConst *s_ncc = reinterpret_cast<NccConst *>(smem + L.off_ncc);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.off_bar);
     float *cost = reinterpret_cast<float *>(smem + L.off_cost);
 
     const int x0 = blockIdx.x * kTpTW, y0 = blockIdx.y * kTpTH;
-    stage_tile<MODEL, kTpTW, kTpTH, kTpNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
+    stage_tile<MODEL, kTpTW, kTpTH, kPqNT>(fc, nt, &tmap, x0, y0, tile_r, aux, s_vc, s_ncc, bar);
 
-    // threads outside the image work on a clamped pixel and store nothing (lock-step view loops)
+    // pixels outside the image work on a clamped pixel and store nothing (lock-step view loops)
     const int tid = threadIdx.x;
-    const int xx = x0 + (tid % kTpTW), yy = y0 + (tid / kTpTW);
+    const int p = tid >> 2, q = tid & 3;               // pixel slot, lane of its quad
+    const int lane = tid & 31, qbase = lane & ~3;
+    const int xx = x0 + (p % kTpTW), yy = y0 + (p / kTpTW);
     const bool valid = xx < fc.W && yy < fc.H;
     const int x = min(xx, fc.W - 1), y = min(yy, fc.H - 1);
     const int center = y * fc.W + x;
     PixCtx px = make_pix<MODEL>(fc, x, y, x0, y0);
-    fill_weights<MODEL, TG::PW, kTpNT>(fc, tile_r, px, mywr, myrr, 0, 1);
-    full_sums<kTpNT>(mywr, myrr, px);
-    float *costrow = cost + tid * (fc.nsrc | 1);
+    float2 *mywr = reinterpret_cast<float2 *>(smem + L.off_wr) + p;
+    float *myrr = reinterpret_cast<float *>(smem + L.off_rr) + p;
+    float *tq = reinterpret_cast<float *>(smem + L.off_tq) + tid;
+    float *costrow = cost + p * (fc.nsrc | 1);
+    fill_weights<MODEL, TG::PW, kPqWRS>(fc, tile_r, px, mywr, myrr, q, 4);
+    __syncwarp(FULL);
+    full_sums<kPqWRS>(mywr, myrr, px);
+    auto evaluate = [&](const float4 &pl, uint32_t &sel_out) {
+        return init_cost_and_views_quad<MODEL, TG::RW, kPqWRS, kPqNT>(fc, nt, s_ncc, aux, mywr, myrr, px, pl, q, valid, costrow, sel_out, tq);
+    };
 
     Rng rs = rng_load(fc.rng_seeded + 3 * (size_t)center);     // curand_init(seed, y, x), ACMMP.cu:684
     uint32_t sel = 0;
@@ -361,7 +375,7 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
         const float depth = rng_uniform(rs) * (fc.depth_max - fc.depth_min) + fc.depth_min;
         plane = random_normal(rs, px.dir);
         plane.w = plane_offset(plane, px.dir, depth);
-        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
+        c = evaluate(plane, sel);
     } else if (fc.prior) {
         if (fc.plane_masks[center] > 0 && fc.costs[center] >= 0.1f) {      // ACMMP.cu:691-703
             const float perturbation = 0.02f;
@@ -377,38 +391,56 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
             const float depth = plane.w;
             plane.w = plane_offset(plane, px.dir, depth);
         }
-        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
+        c = evaluate(plane, sel);
     } else if (fc.upsample) {
-        // joint-bilateral NORMAL upsampling from the coarse level, ACMMP.cu:713-779
+        // joint-bilateral NORMAL upsampling from the coarse level, ACMMP.cu:713-779.  The window's taps (j outer, i inner)
+        // are dealt to the quad's four lanes four at a time -- the double-precision Gauss weights are the expensive
+        // part -- and every lane then accumulates the four in the reference's order, so the sums keep their bits.
         const float scaled_cols = (float)fc.scaled_cols, scaled_rows = (float)fc.scaled_rows;
         const float scale = (float)(1.0 * scaled_cols / fc.W);
         const float sigmad = 0.50f, sigmar = 25.5f;
         const int Imagescale = (int)fmaxf(fc.W / scaled_cols, fc.H / scaled_rows);
         const int WinWidth = Imagescale * Imagescale + 1;
         const int num_neighbors = WinWidth / 2;           // host guarantees <= kHalo
+        const int side = 2 * num_neighbors + 1, ntaps = side * side;
         const float o_y = y * scale, o_x = x * scale;
         const float refPix = tile_r[px.ty * TG::PW + px.tx];
         float normalizing_factor = 0.0f;
         float4 n_total = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = -num_neighbors; j <= num_neighbors; ++j) {
-            int r_y = (int)(o_y + j);
+        auto tap_of = [&](const int t, int &r_x, int &r_y, int &i, int &j) {
+            j = t / side - num_neighbors;
+            i = t % side - num_neighbors;
+            r_y = (int)(o_y + j);
             r_y = (r_y > 0 ? (r_y < scaled_rows ? r_y : (int)(scaled_rows - 1)) : 0);
-            for (int i = -num_neighbors; i <= num_neighbors; ++i) {
-                int r_x = (int)(o_x + i);
-                r_x = (r_x > 0 ? (r_x < scaled_cols ? r_x : (int)(scaled_cols - 1)) : 0);
-                const int s_center = (int)(r_y * scaled_cols + r_x);
-                float4 srcNorm = fc.coarse_planes[s_center];
+            r_x = (int)(o_x + i);
+            r_x = (r_x > 0 ? (r_x < scaled_cols ? r_x : (int)(scaled_cols - 1)) : 0);
+        };
+        for (int t0 = 0; t0 < ntaps; t0 += 4) {
+            float mine = 0.f;
+            if (t0 + q < ntaps) {
+                int r_x, r_y, i, j;
+                tap_of(t0 + q, r_x, r_y, i, j);
                 const float neighborPix = tile_r[(px.ty + j) * TG::PW + (px.tx + i)];
                 const float sgauss = spatial_gauss(o_x, o_y, (float)r_x, (float)r_y, sigmad);
                 const float rgauss = range_gauss(fabsf(refPix - neighborPix), sigmar);
-                const float totalgauss = sgauss * rgauss;
-                normalizing_factor += totalgauss;
-                srcNorm.x = srcNorm.x * totalgauss;
-                srcNorm.y = srcNorm.y * totalgauss;
-                srcNorm.z = srcNorm.z * totalgauss;
-                n_total.x = n_total.x + srcNorm.x;
-                n_total.y = n_total.y + srcNorm.y;
-                n_total.z = n_total.z + srcNorm.z;
+                mine = sgauss * rgauss;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float totalgauss = __shfl_sync(FULL, mine, qbase + k);
+                if (t0 + k < ntaps) {
+                    int r_x, r_y, i, j;
+                    tap_of(t0 + k, r_x, r_y, i, j);
+                    const int s_center = (int)(r_y * scaled_cols + r_x);
+                    float4 srcNorm = fc.coarse_planes[s_center];
+                    normalizing_factor += totalgauss;
+                    srcNorm.x = srcNorm.x * totalgauss;
+                    srcNorm.y = srcNorm.y * totalgauss;
+                    srcNorm.z = srcNorm.z * totalgauss;
+                    n_total.x = n_total.x + srcNorm.x;
+                    n_total.y = n_total.y + srcNorm.y;
+                    n_total.z = n_total.z + srcNorm.z;
+                }
             }
         }
         n_total.x = n_total.x / normalizing_factor;
@@ -418,20 +450,20 @@ k_random_init(const __grid_constant__ FrameConst fc, const __grid_constant__ Ncc
         // cost of the plane exactly as uploaded (normal part defined as 0 here) -> pre_costs, :770-771
         const float4 uploaded = fc.planes[center];
         uint32_t sel0;
-        const float c0 = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, uploaded, costrow, sel0, tq);
-        if (valid) fc.pre_costs[center] = c0;
+        const float c0 = evaluate(uploaded, sel0);
+        if (valid && q == 0) fc.pre_costs[center] = c0;
         plane = normal_to_cam(fc, n_total);
         plane.w = plane_offset(plane, px.dir, uploaded.w);
-        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
+        c = evaluate(plane, sel);
     } else {
         // reload, ACMMP.cu:780-793
         plane = fc.hierarchy ? fc.coarse_planes[center] : fc.planes[center];
         plane = normal_to_cam(fc, plane);
         const float depth = plane.w;
         plane.w = plane_offset(plane, px.dir, depth);
-        c = init_cost_and_views<MODEL, TG::RW, kTpNT, kTpNT>(fc, nt, s_ncc, aux, mywr, myrr, px, plane, costrow, sel, tq);
+        c = evaluate(plane, sel);
     }
-    if (valid) {
+    if (valid && q == 0) {
         fc.planes[center] = plane;
         fc.costs[center] = c;
         fc.selected_views[center] = sel;

@@ -1,31 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the PatchMatch hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C2|C3|C4]
 
-Workload (BASELINE.json configs[1], "C2"): 3200x2130 reference view, 10 source views, the FULL
-multi-scale ACMMP schedule for one reference view = 3 pyramid levels x (photometric, planar prior,
-geometric consistency x 2) = 30 checkerboard iterations + 12 initialisations + 2 JBU
-(reference main.cpp:417-476).  A "step" processes ONE reference view through all of it.
+Workloads (BASELINE.json configs):
+  C2 (default; configs[1]): 3200x2130 reference view, 10 source views, the FULL multi-scale ACMMP schedule for one
+      reference view = 3 pyramid levels x (photometric, planar prior, geometric consistency x 2) = 30 checkerboard
+      iterations + 12 initialisations + 2 JBU (reference main.cpp:417-476).  A step = ONE reference view per GPU.
+  C4 (configs[3]): equirectangular 4096x2048 panoramas (processed at 3200x1600: the reference caps the longer side at
+      3200, ACMMP.h:36), 8 source views, the same schedule through the fork's spherical projection.  A step = one view.
+  C3 (configs[2]): a 64-view 3200x2130 scene, 10 source views each, reference views dealt round-robin to the GPUs.  A step
+      = the WHOLE scene, level by level like the reference's pipeline loop (acmmp_b200/scene.py): every rank runs the
+      photometric + prior stage of the views it owns, the ranks all-gather the depth maps over NCCL, geometric round 0,
+      all-gather, geometric round 1.  Strong scaling: the scene is fixed, N varies.
 
-  value  : depth maps / s with inputs resident: (views per step over all ranks) / (sum of the
-           CUDA-event times of every kernel of the step, max over ranks)
-  e2e    : the same metric through the host-buffer C ABI, wall clock bracketed by barrier + synchronize, max over
-           ranks.  Inside the timed region: H2D (pinned) of every level's images, of the prior and of the stand-in
-           neighbour depth maps; D2H of the photometric result of every level (input of the CPU prior stage) and of
-           the view's final result; the stages in between hand their state over on the device
-  N > 1  : one process per GPU (torchrun), rank r owns reference view r of a 16-view scene (weak
-           scaling); after the prior stage and after the first geometric stage the ranks all-gather
-           their depth maps over NCCL and use them as neighbour depth maps wherever a source view is
-           another rank's reference view (the only collective of the path)
-  --impl reference : the UNMODIFIED reference kernels + host set-up (oracle/_ref/libacmmp_ref.so, its
-           own CUDA build for sm_100) through the same schedule on one B200.  The reference has no
-           CPU PatchMatch; BASELINE.json:north_star names this build as the timed baseline.
+  value  : depth maps / s with inputs resident: (views per step over all ranks) / (sum of the CUDA-event times of every
+           kernel of the step + the all-gathers, max over ranks)
+  e2e    : the same metric through the host-buffer C ABI, wall clock bracketed by barrier + synchronize, max over ranks.
+           Inside the timed region: H2D (pinned) of every level's images, of the prior and of the stand-in neighbour
+           depth maps; D2H of the results the host needs; the stages in between hand their state over on the device.
+           (C3: also the host part of the planar prior -- the Delaunay triangulation -- on worker threads.)
+  N > 1  : one process per GPU (torchrun).  C2 / C4: rank r owns reference view r of the scene (weak scaling); after the
+           prior stage and after the first geometric stage the ranks all-gather their depth maps over NCCL and use them as
+           neighbour depth maps wherever a source view is another rank's reference view (the only collective of the path)
+  --impl reference : the UNMODIFIED reference kernels + host set-up (oracle/_ref/libacmmp_ref.so, its own CUDA build for
+           sm_100) through the same schedule on one B200, one view per step (C3: a one-view sample of the scene).  The
+           reference has no CPU PatchMatch; BASELINE.json:north_star names this build as the timed baseline.
 
-The CPU planar-prior stage (Delaunay etc., reference ACMMP.cpp:904-1011) is out of scope for both
-arms: it runs once per level during warm-up and its output is re-used in the timed steps; its time is
-reported separately (`prior_cpu_s`).  Data are synthetic (acmmp_b200/synth.py), neighbour depth maps
-that no rank computes are rendered stand-ins.
+C2 / C4: the CPU planar-prior stage (Delaunay etc., reference ACMMP.cpp:904-1011) is out of scope for both arms: it runs
+once per level during warm-up and its output is re-used in the timed steps; its time is reported separately
+(`prior_cpu_s`).  `e2e_driver` (C2, N = 1) is the prior-INCLUSIVE number: the C++ driver `lib/acmmp_b200 --resident 1
+--gpu-prior 1` on an 11-view dense folder of the same shape, seconds per view of its own wall clock (image files in, .dmb
+files out).  Data are synthetic (acmmp_b200/synth.py), neighbour depth maps that no rank computes are rendered stand-ins.
 """
 import argparse
 import json
@@ -42,9 +48,22 @@ sys.path.insert(0, str(ROOT))
 
 import numpy as np
 
-METRIC = "depth maps/s @3200x2130, 10 src views (full ACMMP)"
 UNIT = "depth maps/s"
-WIDTH, HEIGHT, FOCAL, N_SRC, SCENE_VIEWS = 3200, 2130, 2800.0, 10, 16
+CONFIGS = {
+    "C2": dict(model="pinhole", width=3200, height=2130, focal=2800.0, n_src=10, scene_views=16, seed=2,
+               metric="depth maps/s @3200x2130, 10 src views (full ACMMP)",
+               workload="C2: 3200x2130 reference view, 10 source views, 3 pyramid levels x (photometric + planar prior + "
+                        "2 x geometric consistency), one reference view per step per GPU"),
+    "C4": dict(model="sphere", width=4096, height=2048, n_src=8, scene_views=9, seed=4,
+               metric="depth maps/s @4096x2048 equirectangular (processed at 3200x1600), 8 src views (full ACMMP)",
+               workload="C4: 4096x2048 equirectangular reference view (processed at 3200x1600, the reference's 3200 px cap), "
+                        "8 source views, 3 pyramid levels x (photometric + planar prior + 2 x geometric consistency), one "
+                        "reference view per step per GPU"),
+    "C3": dict(model="pinhole", width=3200, height=2130, focal=2800.0, n_src=10, scene_views=64, seed=3, ring=True,
+               metric="depth maps/s, 64-view 3200x2130 scene, 10 src views (full ACMMP), views sharded per GPU",
+               workload="C3: 64 reference views 3200x2130 on a ring, 10 source views each, whole scene per step, level by level "
+                        "(photometric + prior, all-gather, geometric 0, all-gather, geometric 1), views dealt round-robin to the GPUs"),
+}
 
 
 # ------------------------------------------------------------------------------------------
@@ -111,17 +130,29 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------
-def make_levels(rank, seed=2):
-    from acmmp_b200 import synth, pipeline
-    scene = synth.make_pinhole_scene(n_views=SCENE_VIEWS, width=WIDTH, height=HEIGHT, focal=FOCAL, seed=seed, n_src=N_SRC,
-                                     render_ids=[rank])
+def make_scene(cfg, render_ids):
+    from acmmp_b200 import synth
+    if cfg["model"] == "pinhole":
+        return synth.make_pinhole_scene(n_views=cfg["scene_views"], width=cfg["width"], height=cfg["height"], focal=cfg["focal"],
+                                        seed=cfg["seed"], n_src=cfg["n_src"], ring=cfg.get("ring", False), render_ids=render_ids)
+    return synth.make_sphere_scene(n_views=cfg["scene_views"], width=cfg["width"], height=cfg["height"], seed=cfg["seed"],
+                                   n_src=cfg["n_src"], render_ids=render_ids)
+
+
+def pin(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+
+def make_levels(cfg, rank):
+    from acmmp_b200 import pipeline
+    scene = make_scene(cfg, [rank])
     levels = pipeline.build_levels(scene, rank)
     ids = [rank] + list(scene.pairs[rank][1])
     # the step's host inputs live in pinned memory (contract: H2D from pinned host memory)
-    import torch
     for L in levels:
-        L.images = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory().numpy() for im in L.images]
-        L.neighbour_depths = [torch.from_numpy(np.ascontiguousarray(d)).pin_memory().numpy() for d in L.neighbour_depths]
+        L.images = [pin(im) for im in L.images]
+        L.neighbour_depths = [pin(d) for d in L.neighbour_depths]
     return scene, levels, ids
 
 

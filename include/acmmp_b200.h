@@ -235,18 +235,18 @@ float acmmp_last_jbu_ms(void);
 
 /* Deterministic sub-kernel probes (parity tests): evaluate, for every pixel p of the reference
  * view and a caller-supplied per-pixel plane (camera-frame normal, d), with the SAME device code
- * the checkerboard kernel runs:
+ * the checkerboard and initialisation kernels run (ncc / initcost: quad_ncc, four lanes per pixel):
  *   ncc      : ComputeBilateralNCC against source view `view` (1-based)      (ACMMP.cu:405-516)
  *   geom     : ComputeGeomConsistencyCost against depth map `view`            (ACMMP.cu:646-671)
  *   warp     : (src x, src y, src depth, ref depth) of p under the plane       (ACMMP.cu:187, :565, :602)
  *   initcost : ComputeMultiViewInitialCostandSelectedViews                     (ACMMP.cu:519-556)
  * Host pointers; planes4 and out4 are W*H*4 floats. */
 int acmmp_probe_ncc(acmmp_ctx *ctx, const float *planes4, int view, float *out);
-/* the same cost through the quad-cooperative form the checkerboard pass runs (quad_ncc: four lanes per pixel) */
-int acmmp_probe_ncc_quad(acmmp_ctx *ctx, const float *planes4, int view, float *out);
 /* the 36 fetch coordinates of that form (texel-centre shift included): out72 = W*H*72 floats, (u, v) of tap
- * k = ii*6 + jj, i = 2 ii - 5, j = 2 jj - 5 -- the reference's sample loop order, ACMMP.cu:450-476 */
-int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, float *out72);
+ * k = ii*6 + jj, i = 2 ii - 5, j = 2 jj - 5 -- the reference's sample loop order, ACMMP.cu:450-476.
+ * variant 0: one hypothesis at a time; 1 / 2 (SPHERE): the packed two-hypothesis form of the pass with this plane
+ * as its first / second hypothesis (same bits expected) */
+int acmmp_probe_coords(acmmp_ctx *ctx, const float *planes4, int view, int variant, float *out72);
 int acmmp_probe_geom(acmmp_ctx *ctx, const float *planes4, int view, float *out);
 int acmmp_probe_warp(acmmp_ctx *ctx, const float *planes4, int view, float *out4);
 int acmmp_probe_initcost(acmmp_ctx *ctx, const float *planes4, float *out, uint32_t *selected_views);

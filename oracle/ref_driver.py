@@ -248,10 +248,15 @@ class quiet_stdout:
         os.dup2(self._saved, 1)
         os.close(self._saved)
         if self.capture:
+            # head + tail: RunJBU prints its timing line first and the per-pixel `wrong!` flood after it
             size = os.lseek(self._fd, 0, os.SEEK_END)
-            tail = min(size, 1 << 16)
-            os.lseek(self._fd, size - tail, os.SEEK_SET)
-            self.text = os.read(self._fd, tail).decode("ascii", "replace")
+            os.lseek(self._fd, 0, os.SEEK_SET)
+            self.text = os.read(self._fd, min(size, 1 << 16)).decode("ascii", "replace")
+            self.bytes = size
+            if size > (1 << 16):
+                tail = min(size - (1 << 16), 1 << 16)
+                os.lseek(self._fd, size - tail, os.SEEK_SET)
+                self.text += os.read(self._fd, tail).decode("ascii", "replace")
         os.close(self._fd)
         return False
 
@@ -272,7 +277,7 @@ def run_jbu(image, coarse_depth, ref_image_id=0, with_ms=False):
         return out
     ms = float("nan")
     key = "Total time needed for computation:"
-    k = q.text.rfind(key)
+    k = q.text.find(key)
     if k >= 0:
         ms = float(q.text[k + len(key):].split()[0]) * 1e3
     return out, ms
