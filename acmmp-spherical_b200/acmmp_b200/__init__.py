@@ -80,11 +80,13 @@ _EXPORTS = [
     "acmmp_get_params", "acmmp_reset_modes", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
     "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_support_points",
     "acmmp_planar_prior_from_triangles", "acmmp_set_seed",
-    "acmmp_set_plane_now_semantics", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
+    "acmmp_set_plane_now_semantics", "acmmp_set_sphere_tap_pruning", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_export_depth_device_sync", "acmmp_download_state", "acmmp_upload_state",
     "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_coords", "acmmp_probe_geom", "acmmp_probe_warp",
     "acmmp_probe_initcost", "acmmp_last_timings", "acmmp_launch_count",
+    "acmmp_fusion_create", "acmmp_fusion_destroy", "acmmp_fusion_last_error", "acmmp_fusion_set_view", "acmmp_fusion_set_view_device",
+    "acmmp_fusion_run", "acmmp_fusion_last_flags",
 ]
 
 _lib = None
@@ -270,6 +272,10 @@ class Context:
     def set_seed(self, seed):
         self._ck(self._l.acmmp_set_seed(self._h, C.c_uint64(seed)), "acmmp_set_seed")
 
+    def set_sphere_tap_pruning(self, relative_weight: float):
+        """SPHERE: skip window taps whose bilateral weight is below relative_weight x (sum of the 36); 0 = sample all."""
+        self._ck(self._l.acmmp_set_sphere_tap_pruning(self._h, C.c_float(relative_weight)), "acmmp_set_sphere_tap_pruning")
+
     def set_plane_now_semantics(self, as_compiled: bool):
         self._ck(self._l.acmmp_set_plane_now_semantics(self._h, C.c_int(1 if as_compiled else 0)), "set_plane_now_semantics")
 
@@ -393,3 +399,66 @@ def jbu(image, coarse_depth, device=0):
 
 def last_jbu_ms() -> float:
     return float(lib().acmmp_last_jbu_ms())
+
+
+class Fusion:
+    """Depth-map fusion of a scene on the device (acmmp_fusion_*; reference RunFusionCuda / SimpleFusionKernel,
+    ACMMP.cu:1664-2105).  Views are set once (camera scaled to the depth map's size), then every reference view is fused
+    against its source views; points come back compacted in pixel order as an [n, 9] float32 array (PointList)."""
+
+    def __init__(self, n_views: int, device: int = 0):
+        self._l = lib()
+        self._l.acmmp_fusion_last_error.restype = C.c_char_p
+        h = C.c_void_p()
+        rc = self._l.acmmp_fusion_create(C.c_int(device), C.c_int(n_views), C.byref(h))
+        if rc != 0:
+            raise AcmmpError(f"acmmp_fusion_create failed ({rc}): no sm_100 device? there is no CPU fallback")
+        self._h, self.n = h, n_views
+        self.sizes = {}
+        self.kernel_ms = 0.0
+
+    def _ck(self, rc, what, allow=()):
+        if rc != 0 and rc not in allow:
+            raise AcmmpError(f"{what} failed ({rc}): {self._l.acmmp_fusion_last_error(self._h).decode()}")
+        return rc
+
+    def set_view(self, index, cam, depth, normals, gray):
+        d, n3, g = _f32(depth), _f32(normals), _f32(gray)
+        h, w = d.shape
+        assert n3.shape == (h, w, 3) and g.shape == (h, w)
+        self._ck(self._l.acmmp_fusion_set_view(self._h, C.c_int(index), C.byref(cam), C.c_int(w), C.c_int(h), _fp(d), _fp(n3), _fp(g)),
+                 "acmmp_fusion_set_view")
+        self.sizes[index] = (h, w)
+
+    def run(self, ref, src_indices):
+        src = np.ascontiguousarray(src_indices, np.int32)
+        h, w = self.sizes[ref]
+        cap = max(h * w // 4, 1024)
+        while True:
+            pts = np.empty((cap, 9), np.float32)
+            n, ms = C.c_int(0), C.c_float(0)
+            rc = self._ck(self._l.acmmp_fusion_run(self._h, C.c_int(ref), C.c_int(len(src)), src.ctypes.data_as(C.POINTER(C.c_int32)), _fp(pts),
+                                                   C.c_int(cap), C.byref(n), C.byref(ms)), "acmmp_fusion_run", allow=(-1,))
+            if rc == 0:
+                self.kernel_ms = float(ms.value)
+                return pts[: n.value].copy()
+            if n.value <= cap:
+                self._ck(rc, "acmmp_fusion_run")
+            cap = n.value
+
+    def last_flags(self, ref):
+        h, w = self.sizes[ref]
+        flags = np.zeros((h, w), np.uint8)
+        self._ck(self._l.acmmp_fusion_last_flags(self._h, C.c_int(ref), flags.ctypes.data_as(C.POINTER(C.c_ubyte))), "acmmp_fusion_last_flags")
+        return flags
+
+    def close(self):
+        if self._h:
+            self._l.acmmp_fusion_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

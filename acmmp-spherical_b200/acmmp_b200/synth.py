@@ -173,8 +173,10 @@ def make_pinhole_scene(n_views=5, width=640, height=480, focal=500.0, seed=1, n_
     return Scene(MODEL_PINHOLE, images, cams, depths, pairs, Rs, ts, [K] * n_views, quads)
 
 
-def make_sphere_scene(n_views=5, width=1024, height=512, seed=4, n_src=None, room=(8.0, 5.0, 6.0), spread=0.5) -> Scene:
-    """Textured box room seen by equirectangular cameras near its centre."""
+def make_sphere_scene(n_views=5, width=1024, height=512, seed=4, n_src=None, room=(8.0, 5.0, 6.0), spread=0.5,
+                      render_ids=None) -> Scene:
+    """Textured box room seen by equirectangular cameras near its centre.
+    render_ids: as in make_pinhole_scene (only these reference views and their sources are rendered)."""
     rng = np.random.default_rng(seed)
     lx, ly, lz = room
     texel = 0.7 * (2 * np.pi * 0.5 * min(room)) / width * 0.5
@@ -195,14 +197,28 @@ def make_sphere_scene(n_views=5, width=1024, height=512, seed=4, n_src=None, roo
         yaw = 0.2 * np.sin(ang)
         R = np.array([[np.cos(yaw), 0, -np.sin(yaw)], [0, 1, 0], [np.sin(yaw), 0, np.cos(yaw)]], np.float64)
         t = -R @ C
-        img, dep = _render(quads, MODEL_SPHERE, R, t, width, height, cx=cx, cy=cy)
-        Rs.append(R); ts.append(t); images.append(img); depths.append(dep)
-    dmin = min(float(d[d > 0].min()) for d in depths) * 0.9
-    dmax = max(float(d.max()) for d in depths) * 1.1
+        Rs.append(R); ts.append(t)
+    pairs = _nearest_pairs(Rs, ts, n_views, n_src if n_src is not None else n_views - 1)
+    wanted = None
+    if render_ids is not None:
+        wanted = set(render_ids)
+        for r in list(wanted):
+            wanted.update(pairs[r][1])
+    for i in range(n_views):
+        if wanted is None or i in wanted:
+            img, dep = _render(quads, MODEL_SPHERE, Rs[i], ts[i], width, height, cx=cx, cy=cy)
+        else:
+            img, dep = None, None
+        images.append(img); depths.append(dep)
+    if wanted is None:
+        dmin = min(float(d[d > 0].min()) for d in depths) * 0.9
+        dmax = max(float(d.max()) for d in depths) * 1.1
+    else:       # the same range on every rank: from the room, not from the rendered subset
+        dmin = 0.9 * (0.5 * min(room) - 1.2 * spread)
+        dmax = 1.1 * (0.5 * float(np.linalg.norm(room)) + 1.2 * spread)
     for i in range(n_views):
         cams.append(make_camera(MODEL_SPHERE, Rs[i], ts[i], sphere=(1.0, cx, cy, 0.0), width=width, height=height,
                                 depth_min=dmin, depth_max=dmax))
-    pairs = _nearest_pairs(Rs, ts, n_views, n_src if n_src is not None else n_views - 1)
     return Scene(MODEL_SPHERE, images, cams, depths, pairs, Rs, ts, [None] * n_views, quads)
 
 

@@ -21,6 +21,7 @@
 
 #include "../../include/acmmp_b200.h"
 #include "acmmp_kernels.cuh"
+#include "acmmp_fusion.cuh"
 
 using namespace acmmp;
 
@@ -230,6 +231,7 @@ struct acmmp_ctx {
     acmmp_params params;
     int as_compiled = 1;
     int use_tma = 1;
+    float tap_prune = 5.9604645e-08f;     // 2^-24, see acmmp_set_sphere_tap_pruning
     int num_sms = 148;
     uint64_t seed = 0;
     bool have_seeded = false;
@@ -498,6 +500,7 @@ FrameConst frame_const(const acmmp_ctx *ctx)
     fc.as_compiled = ctx->as_compiled;
     fc.ref_pitch = ctx->ref_pitch;
     fc.use_tma = ctx->use_tma;
+    fc.tap_prune = (ctx->cams[0].model == ACMMP_MODEL_SPHERE) ? ctx->tap_prune : 0.0f;
     fc.tex_src = (unsigned long long)ctx->src_tex;
     fc.ref_padded = ctx->ref_padded;
     fc.views = ctx->views_dev;
@@ -1319,6 +1322,13 @@ int acmmp_set_seed(acmmp_ctx *ctx, uint64_t seed)
     return ACMMP_OK;
 }
 
+int acmmp_set_sphere_tap_pruning(acmmp_ctx *ctx, float relative_weight)
+{
+    if (!ctx || !(relative_weight >= 0.0f) || relative_weight > 1e-3f) return fail(ctx, ACMMP_E_ARG, "acmmp_set_sphere_tap_pruning: threshold must be in [0, 1e-3]");
+    ctx->tap_prune = relative_weight;
+    return ACMMP_OK;
+}
+
 int acmmp_set_plane_now_semantics(acmmp_ctx *ctx, int as_compiled)
 {
     if (!ctx) return ACMMP_E_ARG;
@@ -1549,5 +1559,204 @@ int acmmp_last_timings(acmmp_ctx *ctx, float what[8])
 }
 
 int64_t acmmp_launch_count(const acmmp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+
+// ---------------------------------------------------------------------------------------------
+// fusion
+// ---------------------------------------------------------------------------------------------
+struct acmmp_fusion {
+    int device = 0;
+    int n = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<acmmp::FusionViewDev> views;          // host copy of the table
+    std::vector<std::vector<void *>> owned;           // device buffers this object allocated, per view
+    acmmp::FusionViewDev *views_dev = nullptr;
+    bool table_dirty = true;
+    acmmp_point *dense = nullptr, *out = nullptr;
+    unsigned char *flags = nullptr;
+    int *counts = nullptr, *total = nullptr;
+    size_t dense_cap = 0, out_cap = 0, count_cap = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::string err;
+};
+
+#define FCK(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            f->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+            return ACMMP_E_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+static int fusion_fail(acmmp_fusion *f, int code, const std::string &msg)
+{
+    if (f) f->err = msg;
+    return code;
+}
+
+static void fusion_free_view(acmmp_fusion *f, int i)
+{
+    for (void *p : f->owned[i]) cudaFree(p);
+    f->owned[i].clear();
+}
+
+int acmmp_fusion_create(int device, int n_views, acmmp_fusion **out)
+{
+    if (!out || n_views < 1) return ACMMP_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ACMMP_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return ACMMP_E_CUDA;      // sm_100a code only
+    acmmp_fusion *f = new acmmp_fusion();
+    f->device = device;
+    f->n = n_views;
+    f->views.resize(n_views);
+    f->owned.resize(n_views);
+    for (auto &v : f->views) std::memset(&v, 0, sizeof(v));
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&f->views_dev, sizeof(acmmp::FusionViewDev) * n_views) != cudaSuccess || cudaMalloc(&f->total, sizeof(int)) != cudaSuccess ||
+        cudaEventCreate(&f->ev[0]) != cudaSuccess || cudaEventCreate(&f->ev[1]) != cudaSuccess) {
+        acmmp_fusion_destroy(f);
+        return ACMMP_E_CUDA;
+    }
+    *out = f;
+    return ACMMP_OK;
+}
+
+void acmmp_fusion_destroy(acmmp_fusion *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->device);
+    for (int i = 0; i < f->n; ++i) fusion_free_view(f, i);
+    cudaFree(f->views_dev); cudaFree(f->dense); cudaFree(f->out); cudaFree(f->flags); cudaFree(f->counts); cudaFree(f->total);
+    if (f->ev[0]) cudaEventDestroy(f->ev[0]);
+    if (f->ev[1]) cudaEventDestroy(f->ev[1]);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+}
+
+const char *acmmp_fusion_last_error(const acmmp_fusion *f) { return f ? f->err.c_str() : "null fusion object"; }
+
+int acmmp_fusion_set_view_device(acmmp_fusion *f, int index, const acmmp_camera *cam, int w, int h, const float *depth_dev,
+                                 const void *normals4_dev, const float *gray_dev)
+{
+    if (!f || index < 0 || index >= f->n || !cam || w <= 0 || h <= 0 || !depth_dev || !normals4_dev || !gray_dev)
+        return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_set_view_device: bad arguments");
+    FCK(cudaSetDevice(f->device));
+    fusion_free_view(f, index);
+    acmmp::FusionViewDev &v = f->views[index];
+    v.cam = *cam;
+    v.cam.width = w;
+    v.cam.height = h;
+    v.depth = depth_dev;
+    v.normal = static_cast<const float4 *>(normals4_dev);
+    v.gray = gray_dev;
+    f->table_dirty = true;
+    return ACMMP_OK;
+}
+
+int acmmp_fusion_set_view(acmmp_fusion *f, int index, const acmmp_camera *cam, int w, int h, const float *depth,
+                          const float *normals3, const float *gray)
+{
+    if (!f || index < 0 || index >= f->n || !cam || w <= 0 || h <= 0 || !depth || !normals3 || !gray)
+        return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_set_view: bad arguments");
+    FCK(cudaSetDevice(f->device));
+    fusion_free_view(f, index);
+    const size_t npx = (size_t)w * h;
+    float *d = nullptr, *g = nullptr, *n3 = nullptr;
+    float4 *n4 = nullptr;
+    FCK(cudaMalloc(&d, sizeof(float) * npx));
+    f->owned[index].push_back(d);
+    FCK(cudaMalloc(&g, sizeof(float) * npx));
+    f->owned[index].push_back(g);
+    FCK(cudaMalloc(&n4, sizeof(float4) * npx));
+    f->owned[index].push_back(n4);
+    FCK(cudaMalloc(&n3, sizeof(float) * 3 * npx));
+    FCK(cudaMemcpyAsync(d, depth, sizeof(float) * npx, cudaMemcpyHostToDevice, f->stream));
+    FCK(cudaMemcpyAsync(g, gray, sizeof(float) * npx, cudaMemcpyHostToDevice, f->stream));
+    FCK(cudaMemcpyAsync(n3, normals3, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, f->stream));
+    acmmp::k_pack_normals<<<(unsigned)((npx + 255) / 256), 256, 0, f->stream>>>(n3, (int)npx, n4);
+    cudaError_t e = cudaStreamSynchronize(f->stream);
+    cudaFree(n3);
+    FCK(e);
+    acmmp::FusionViewDev &v = f->views[index];
+    v.cam = *cam;
+    v.cam.width = w;
+    v.cam.height = h;
+    v.depth = d;
+    v.normal = n4;
+    v.gray = g;
+    f->table_dirty = true;
+    return ACMMP_OK;
+}
+
+int acmmp_fusion_run(acmmp_fusion *f, int ref, int n_src, const int32_t *src, acmmp_point *points, int capacity,
+                     int *n_points, float *kernel_ms)
+{
+    if (!f || ref < 0 || ref >= f->n || n_src < 0 || (n_src > 0 && !src) || !n_points || capacity < 0 || (capacity > 0 && !points))
+        return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_run: bad arguments");
+    if (!f->views[ref].depth) return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_run: the reference view was not set");
+    FCK(cudaSetDevice(f->device));
+    acmmp::FusionProblemDev prob;
+    prob.num_src = std::min(n_src, acmmp::kFuseMaxSrc);
+    for (int j = 0; j < acmmp::kFuseMaxSrc; ++j) {
+        int s = (j < prob.num_src) ? src[j] : -1;
+        if (s >= f->n || (s >= 0 && !f->views[s].depth)) s = -1;
+        prob.src[j] = s;
+    }
+    if (f->table_dirty) {
+        FCK(cudaMemcpyAsync(f->views_dev, f->views.data(), sizeof(acmmp::FusionViewDev) * f->n, cudaMemcpyHostToDevice, f->stream));
+        FCK(cudaStreamSynchronize(f->stream));      // the host table may change right after
+        f->table_dirty = false;
+    }
+    const int npx = f->views[ref].cam.width * f->views[ref].cam.height;
+    const int nblocks = (npx + acmmp::kFuseBlock - 1) / acmmp::kFuseBlock;
+    if ((size_t)npx > f->dense_cap) {
+        cudaFree(f->dense); cudaFree(f->flags);
+        f->dense = nullptr; f->flags = nullptr; f->dense_cap = 0;
+        FCK(cudaMalloc(&f->dense, sizeof(acmmp_point) * (size_t)npx));
+        FCK(cudaMalloc(&f->flags, (size_t)npx));
+        f->dense_cap = (size_t)npx;
+    }
+    if ((size_t)nblocks > f->count_cap) {
+        cudaFree(f->counts);
+        f->counts = nullptr; f->count_cap = 0;
+        FCK(cudaMalloc(&f->counts, sizeof(int) * (size_t)nblocks));
+        f->count_cap = (size_t)nblocks;
+    }
+    if ((size_t)capacity > f->out_cap) {
+        cudaFree(f->out);
+        f->out = nullptr; f->out_cap = 0;
+        FCK(cudaMalloc(&f->out, sizeof(acmmp_point) * (size_t)capacity));
+        f->out_cap = (size_t)capacity;
+    }
+    cudaEventRecord(f->ev[0], f->stream);
+    acmmp::k_fuse_view<<<nblocks, acmmp::kFuseBlock, 0, f->stream>>>(f->views_dev, ref, prob, f->dense, f->flags, f->counts);
+    acmmp::k_scan_blocks<<<1, 1024, 0, f->stream>>>(f->counts, nblocks, f->total);
+    if (capacity > 0) acmmp::k_compact_points<<<nblocks, acmmp::kFuseBlock, 0, f->stream>>>(f->dense, f->flags, f->counts, npx, f->out, capacity);
+    cudaEventRecord(f->ev[1], f->stream);
+    FCK(cudaGetLastError());
+    int total = 0;
+    FCK(cudaMemcpyAsync(&total, f->total, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+    FCK(cudaStreamSynchronize(f->stream));
+    *n_points = total;
+    if (kernel_ms) cudaEventElapsedTime(kernel_ms, f->ev[0], f->ev[1]);
+    if (total > capacity) return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_run: capacity too small (n_points holds the need)");
+    if (total > 0) FCK(cudaMemcpy(points, f->out, sizeof(acmmp_point) * (size_t)total, cudaMemcpyDeviceToHost));
+    return ACMMP_OK;
+}
+
+/* test / inspection hook: which pixels of the last fused reference view produced a point (w*h bytes, host) */
+int acmmp_fusion_last_flags(acmmp_fusion *f, int ref, unsigned char *flags)
+{
+    if (!f || ref < 0 || ref >= f->n || !flags || !f->flags) return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_last_flags: nothing fused yet");
+    FCK(cudaSetDevice(f->device));
+    const size_t npx = (size_t)f->views[ref].cam.width * f->views[ref].cam.height;
+    if (npx > f->dense_cap) return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_last_flags: not the view of the last run");
+    FCK(cudaMemcpy(flags, f->flags, npx, cudaMemcpyDeviceToHost));
+    return ACMMP_OK;
+}
 
 } // extern "C"

@@ -127,7 +127,8 @@ __device__ __forceinline__ float init_cost_and_views_quad(const FrameConst &fc, 
     constexpr unsigned FULL = 0xffffffffu;
     const float cost_max = 2.0f;
     __syncwarp(FULL);                                   // the previous evaluation's rows and tap depths are free
-    quad_fill_depths<MODEL, RW, TQS>(fc, aux, px, plane, q, tq);
+    const unsigned steps = (MODEL == kModelSphere) ? sphere_tap_steps<WRS>(wr, q, px.Sw, fc.tap_prune) : 0x1FFu;
+    quad_fill_depths<MODEL, RW, TQS>(fc, aux, px, plane, q, tq, steps);
     __syncwarp(FULL);
     for (int v = 0; v < fc.nsrc; ++v) {
         const ViewK c = load_view(s_ncc + v);
@@ -135,7 +136,7 @@ __device__ __forceinline__ float init_cost_and_views_quad(const FrameConst &fc, 
         fetch.tex = (cudaTextureObject_t)nt.tex[v];
         quad_ncc<MODEL, 1, RW, WRS, TQS>(
             c, px, aux, wr, rr, tq, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
-            [&](const int, const float cst) { costrow[v] = cst; });
+            [&](const int, const float cst) { costrow[v] = cst; }, steps);
     }
     __syncwarp(FULL);
     selected = 0;
@@ -242,13 +243,15 @@ k_probe_quad(const __grid_constant__ FrameConst fc, const __grid_constant__ NccT
         }
         return;
     }
-    quad_fill_depths<MODEL, TG::RW, kPqNT>(fc, aux, px, planes[center], q, tq);
+    const unsigned steps = (MODEL == kModelSphere) ? sphere_tap_steps<kPqWRS>(wr, q, px.Sw, fc.tap_prune) : 0x1FFu;
+    quad_fill_depths<MODEL, TG::RW, kPqNT>(fc, aux, px, planes[center], q, tq, steps);
     __syncwarp(0xffffffffu);
     const ViewK c = load_view(s_ncc + (view - 1));
     FetchView fetch;
     fetch.tex = (cudaTextureObject_t)nt.tex[view - 1];
     quad_ncc<MODEL, 1, TG::RW, kPqWRS, kPqNT>(
-        c, px, aux, wr, rr, tq, fetch, q, valid ? 1u : 0u, [](const int) { return 0; }, [&](const int, const float cst) { out[center] = cst; });
+        c, px, aux, wr, rr, tq, fetch, q, valid ? 1u : 0u, [](const int) { return 0; }, [&](const int, const float cst) { out[center] = cst; },
+        steps);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -759,10 +762,12 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     // quad Q of the group evaluates candidates 4Q..4Q+3 (the planes its own four lanes hold), tap-split
     const int Q = gl >> 2, q = gl & 3;
     const int qbase = lane & ~3;
+    // SPHERE: the tap steps worth sampling for the four pixels of this warp (all nine unless pruning is on)
+    const unsigned steps = (MODEL == kModelSphere) ? sphere_tap_steps<WRS>(wr, q, px.Sw, fc.tap_prune) : 0x1FFu;
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
         const float4 hp = shfl_plane(FULL, cand, qbase + h);
-        quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, hp, q, tq + h * kTqPerHyp * TQS);
+        quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, hp, q, tq + h * kTqPerHyp * TQS, steps);
     }
     {
         const unsigned wantA = valid ? ((flagbits >> (4 * Q)) & 0xFu) : 0u;
@@ -772,7 +777,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             fetch.tex = (cudaTextureObject_t)nt.tex[v];
             quad_ncc<MODEL, 4, TG::RW, WRS, TQS>(
                 c, px, aux, wr, rr, tq, fetch, q, wantA, [](const int h) { return h * kTqPerHyp * TQS; },
-                [&](const int h, const float cst) { cost_grp[(4 * Q + h) * nvp + v] = cst; });
+                [&](const int h, const float cst) { cost_grp[(4 * Q + h) * nvp + v] = cst; }, steps);
         }
     }
     if (!flag) {
@@ -914,7 +919,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
     float cost_now = 0.0f;
     {
         // the warp's (pixel, selected view) pairs, one per quad and round (WarpPairs); tap-split inside the quad
-        quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, cur_plane, q, tq);
+        quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, cur_plane, q, tq, steps);
         const int n_sel = valid ? __popc(temp_selected_views) : 0;
         WarpPairs wp;
         wp.build(valid ? temp_selected_views : 0u);
@@ -938,7 +943,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             fetch.layer = vsel;
             quad_ncc<MODEL, 1, TG::RW, WRS, TQS>(
                 c, po, aux, wr_all + o, rr_all + o, tq_all + o * 8 + q, fetch, q, want ? 1u : 0u, [](const int) { return 0; },
-                [&](const int, const float cst) { row_o[vsel] = cst; });
+                [&](const int, const float cst) { row_o[vsel] = cst; }, steps);
         }
         __syncwarp(FULL);
         // weight (and, in geometric mode, add the geometric term): lane k of the group takes the k-th selected
@@ -1117,7 +1122,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
         for (int k = 0; k < 3; ++k) {
             const int h = 3 * Q + k;
             const float4 hp = shfl_plane(FULL, temp_plane, gbase + min(h, 4));
-            if (h < 5) quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, hp, q, tq + k * kTqPerHyp * TQS);
+            if (h < 5) quad_fill_depths<MODEL, TG::RW, TQS>(fc, aux, px, hp, q, tq + k * kTqPerHyp * TQS, steps);
         }
         __syncwarp(FULL);
         const int n_sel = (do_refine && valid) ? __popc(temp_selected_views) : 0;
@@ -1143,7 +1148,7 @@ k_pass(const __grid_constant__ FrameConst fc, const __grid_constant__ NccTable n
             quad_ncc<MODEL, 5, TG::RW, WRS, TQS>(
                 c, po, aux, wr_all + o, rr_all + o, tq_all + o * 8 + q, fetch, q, want ? 0x1Fu : 0u,
                 [&](const int h) { return (h < 3 ? h : h - 3) * kTqPerHyp * TQS + (h < 3 ? 0 : 4); },
-                [&](const int h, const float cst) { grp_o[h * nvp + vsel] = cst; });
+                [&](const int h, const float cst) { grp_o[h * nvp + vsel] = cst; }, steps);
         }
         __syncwarp(FULL);
         if (kGeom) {

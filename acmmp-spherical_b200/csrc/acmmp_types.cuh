@@ -76,6 +76,7 @@ struct FrameConst {
     int as_compiled;       // plane_hypotheses_now semantics, see acmmp_b200.h
     int ref_pitch;         // floats per row of the padded reference image
     int use_tma;           // 1: tile staged by a TMA bulk-tensor copy; 0: same tile by plain loads (debug aid)
+    float tap_prune;       // SPHERE: window taps whose bilateral weight is below tap_prune * (sum of the 36) are not sampled; 0 = off
     unsigned long long tex_src;   // layered R32F bilinear texture of the source views
     const float *ref_padded;      // (H + 2*kRefPad) rows, border replicated
     const ViewConst *views;       // nsrc entries (device)

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <sstream>
 #include <unordered_map>
 #include <stdexcept>
@@ -492,4 +493,112 @@ void RunJBU(const cv::Mat_<float> &scaled_image_float, const cv::Mat_<float> &sr
     for (size_t i = 0; i < depthmap.total(); ++i)
         if (depthmap.ptr()[i] != depthmap.ptr()[i]) { std::cout << "wrong!" << std::endl; break; }     // the reference's NaN check
     writeDepthDmb(result_folder_of(dense_folder, problem.ref_image_id) + "/depths.dmb", depthmap);
+}
+
+// reference ACMMP.cu:1817-2105 (host part) over acmmp_fusion_* (device part)
+size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem> &problems, bool geom_consistency, int device, double *kernel_ms)
+{
+    static_assert(sizeof(PointList) == sizeof(acmmp_point), "PointList must mirror acmmp_point");
+    const size_t N = problems.size();
+    std::cout << "[CUDA Fusion] Starting simple fusion with " << N << " images..." << std::endl;
+    struct View {
+        Camera cam;
+        cv::Mat_<float> depth, gray;
+        cv::Mat_<cv::Vec3f> normal;
+        Problem problem;
+    };
+    std::vector<View> views;
+    std::map<int, int> id_to_index;
+    for (size_t i = 0; i < N; ++i) {
+        const int id = problems[i].ref_image_id;
+        View v;
+        std::stringstream cam_path;
+        cam_path << dense_folder << "/cams/" << std::setw(8) << std::setfill('0') << id << "_cam.txt";
+        v.cam = ReadCamera(cam_path.str());
+        const std::string folder = result_folder_of(dense_folder, id);
+        if (readDepthDmb(folder + (geom_consistency ? "/depths_geom.dmb" : "/depths.dmb"), v.depth) != 0) {
+            std::cerr << "Warning: Could not load depth for image " << id << std::endl;
+            continue;
+        }
+        if (readNormalDmb(folder + "/normals.dmb", v.normal) != 0) {
+            std::cerr << "Warning: Could not load normals for image " << id << std::endl;
+            continue;
+        }
+        cv::Mat_<float> image;
+        if (!LoadGreyImage(dense_folder, id, image)) {
+            std::cerr << "Warning: Could not load image " << id << std::endl;
+            continue;
+        }
+        // RescaleImageAndCamera (ACMMP.cpp:213-245): image and intrinsics to the depth map's resolution
+        const int cols = v.depth.cols, rows = v.depth.rows;
+        v.cam.width = cols;
+        v.cam.height = rows;
+        if (cols == image.cols && rows == image.rows) {
+            v.gray = image;
+        } else {
+            const float scale_x = cols / static_cast<float>(image.cols), scale_y = rows / static_cast<float>(image.rows);
+            ResizeLinear(image, v.gray, cols, rows);
+            if (v.cam.model == SPHERE) {
+                v.cam.params[1] *= scale_x;
+                v.cam.params[2] *= scale_y;
+            } else {
+                v.cam.K[0] *= scale_x; v.cam.K[2] *= scale_x;
+                v.cam.K[4] *= scale_y; v.cam.K[5] *= scale_y;
+            }
+        }
+        v.problem = problems[i];
+        id_to_index[id] = (int)views.size();
+        views.push_back(v);
+    }
+    const size_t num_valid = views.size();
+    std::cout << "[CUDA Fusion] Successfully loaded " << num_valid << "/" << N << " images" << std::endl;
+    if (num_valid == 0) {
+        std::cerr << "Error: No valid images to process!" << std::endl;
+        return 0;
+    }
+    acmmp_fusion *f = nullptr;
+    if (acmmp_fusion_create(device, (int)num_valid, &f) != ACMMP_OK) throw std::runtime_error("RunFusionCuda: no usable sm_100 device (there is no CPU fallback)");
+    auto fail = [&](const char *what) {
+        const std::string msg = std::string("RunFusionCuda (") + what + "): " + acmmp_fusion_last_error(f);
+        acmmp_fusion_destroy(f);
+        throw std::runtime_error(msg);
+    };
+    for (size_t i = 0; i < num_valid; ++i) {
+        const View &v = views[i];
+        if (acmmp_fusion_set_view(f, (int)i, &v.cam, v.depth.cols, v.depth.rows, v.depth.ptr(), reinterpret_cast<const float *>(v.normal.ptr()),
+                                  v.gray.ptr()) != ACMMP_OK)
+            fail("set_view");
+    }
+    std::vector<PointList> all_points;
+    double ms_sum = 0.0;
+    for (size_t i = 0; i < num_valid; ++i) {
+        const View &v = views[i];
+        const int width = v.cam.width, height = v.cam.height;
+        std::cout << "[CUDA Fusion] Processing image " << (i + 1) << "/" << num_valid << " (ID=" << v.problem.ref_image_id << ", " << width << "x"
+                  << height << ")" << std::endl;
+        std::vector<int32_t> src;
+        for (size_t j = 0; j < std::min<size_t>(v.problem.src_image_ids.size(), 32); ++j) {
+            const auto it = id_to_index.find(v.problem.src_image_ids[j]);
+            src.push_back(it != id_to_index.end() ? it->second : -1);
+        }
+        int capacity = std::max(width * height / 2, 1024), count = 0;
+        std::vector<PointList> points((size_t)capacity);
+        float ms = 0.f;
+        int rc = acmmp_fusion_run(f, (int)i, (int)src.size(), src.data(), reinterpret_cast<acmmp_point *>(points.data()), capacity, &count, &ms);
+        if (rc == ACMMP_E_ARG && count > capacity) {
+            capacity = count;
+            points.resize((size_t)capacity);
+            rc = acmmp_fusion_run(f, (int)i, (int)src.size(), src.data(), reinterpret_cast<acmmp_point *>(points.data()), capacity, &count, &ms);
+        }
+        if (rc != ACMMP_OK) fail("run");
+        ms_sum += ms;
+        all_points.insert(all_points.end(), points.begin(), points.begin() + count);
+        std::cout << "  -> Generated " << count << " points" << std::endl;
+    }
+    acmmp_fusion_destroy(f);
+    const std::string output_path = dense_folder + "/ACMMP/ACMM_model_cuda_5.ply";
+    StoreColorPlyFileBinaryPointCloud(output_path, all_points);
+    std::cout << "[CUDA Fusion] Complete! Wrote " << all_points.size() << " points to " << output_path << std::endl;
+    if (kernel_ms) *kernel_ms = ms_sum;
+    return all_points.size();
 }

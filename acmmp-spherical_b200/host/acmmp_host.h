@@ -47,6 +47,13 @@ struct Triangle {
     Triangle(const cv::Point a, const cv::Point b, const cv::Point c) : pt1(a), pt2(b), pt3(c) {}
 };
 
+// reference main.h:71-75 (layout == acmmp_point of the C ABI)
+struct PointList {
+    float3 coord;
+    float3 normal;
+    float3 color;
+};
+
 // ---- on-disk contract (reference ACMMP.cpp:146-209, :352-479, main.cpp:4-33) ---------------------------
 int readDepthDmb(const std::string file_path, cv::Mat_<float> &depth);
 int readNormalDmb(const std::string file_path, cv::Mat_<cv::Vec3f> &normal);
@@ -151,6 +158,18 @@ private:
     const float *planes_host_ = nullptr;      // pinned result buffers owned by the library
     const float *costs_host_ = nullptr;
 };
+
+// StoreColorPlyFileBinaryPointCloud (ACMMP.cpp:481-534): binary little-endian PLY, x y z nx ny nz (float) + red green blue
+// (uchar); non-finite coordinates are written as 0
+void StoreColorPlyFileBinaryPointCloud(const std::string &plyFilePath, const std::vector<PointList> &pc);
+
+// RunFusionCuda (ACMMP.cu:1817-2105): fuse the depth / normal maps of every view (depths_geom.dmb when geom_consistency,
+// else depths.dmb; normals.dmb) into ACMMP/ACMM_model_cuda_5.ply.  The per-pixel consistency kernel and the compaction
+// of its points run on the device (acmmp_fusion_*).  Colours: the grey level of the image the PatchMatch stages read
+// (the reference decodes the JPEG in colour).  Returns the number of points written.  kernel_ms: optional, sum of the
+// CUDA-event kernel times.
+size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem> &problems, bool geom_consistency, int device = 0,
+                     double *kernel_ms = nullptr);
 
 // RunJBU (ACMMP.cpp:1071-1122): joint-bilateral upsampling of depths_geom.dmb to the new level, written as depths.dmb
 void RunJBU(const cv::Mat_<float> &scaled_image_float, const cv::Mat_<float> &src_depthmap, const std::string &dense_folder,

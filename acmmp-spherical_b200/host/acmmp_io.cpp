@@ -2,7 +2,9 @@
 // pair.txt in; ACMMP/2333_%08d/{depths,depths_geom,normals,costs}.dmb out.  Formats: SURVEY.md section 8(b)/(f) N4.
 #include <cmath>
 #include <cstdio>
+#include <cfloat>
 #include <cstring>
+#include <stdexcept>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -325,4 +327,42 @@ void ResizeLinear(const cv::Mat_<float> &src, cv::Mat_<float> &dst, int new_cols
         float *D = dst.ptr() + (size_t)dy * new_cols;
         for (int dx = 0; dx < new_cols; ++dx) D[dx] = row0[dx] * b0 + row1[dx] * b1;
     }
+}
+
+// reference ACMMP.cpp:481-534
+void StoreColorPlyFileBinaryPointCloud(const std::string &plyFilePath, const std::vector<PointList> &pc)
+{
+    std::cout << "store 3D points to ply file" << std::endl;
+    FILE *outputPly = fopen(plyFilePath.c_str(), "wb");
+    if (!outputPly) throw std::runtime_error("cannot write " + plyFilePath);
+    fprintf(outputPly, "ply\n");
+    fprintf(outputPly, "format binary_little_endian 1.0\n");
+    fprintf(outputPly, "element vertex %zu\n", pc.size());
+    fprintf(outputPly, "property float x\n");
+    fprintf(outputPly, "property float y\n");
+    fprintf(outputPly, "property float z\n");
+    fprintf(outputPly, "property float nx\n");
+    fprintf(outputPly, "property float ny\n");
+    fprintf(outputPly, "property float nz\n");
+    fprintf(outputPly, "property uchar red\n");
+    fprintf(outputPly, "property uchar green\n");
+    fprintf(outputPly, "property uchar blue\n");
+    fprintf(outputPly, "end_header\n");
+    // one 27-byte record per point, assembled in memory and written in one go (the reference issues nine fwrite calls per
+    // point inside an omp critical section)
+    std::vector<unsigned char> buf(pc.size() * 27);
+    for (size_t i = 0; i < pc.size(); ++i) {
+        const PointList &p = pc[i];
+        float3 X = p.coord;
+        if (!(X.x < FLT_MAX && X.x > -FLT_MAX) || !(X.y < FLT_MAX && X.y > -FLT_MAX) || !(X.z < FLT_MAX && X.z >= -FLT_MAX)) {
+            X.x = 0.0f; X.y = 0.0f; X.z = 0.0f;
+        }
+        const char b_color = (char)(int)p.color.x, g_color = (char)(int)p.color.y, r_color = (char)(int)p.color.z;
+        unsigned char *o = buf.data() + 27 * i;
+        std::memcpy(o, &X.x, 4); std::memcpy(o + 4, &X.y, 4); std::memcpy(o + 8, &X.z, 4);
+        std::memcpy(o + 12, &p.normal.x, 4); std::memcpy(o + 16, &p.normal.y, 4); std::memcpy(o + 20, &p.normal.z, 4);
+        o[24] = (unsigned char)r_color; o[25] = (unsigned char)g_color; o[26] = (unsigned char)b_color;
+    }
+    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), outputPly);
+    fclose(outputPly);
 }

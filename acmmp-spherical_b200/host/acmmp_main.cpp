@@ -1,12 +1,13 @@
-// acmmp_main.cpp -- `acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N] [--resident 1]`: the reference's pipeline
+// acmmp_main.cpp -- `acmmp_b200 dense_folder [--seed S] [--device D] [--gpus N] [--max-views N] [--resident 1]`: the reference's pipeline
 // schedule (main.cpp:392-482) on top of the B200 library, stage by stage through the same .dmb files:
 //   per pyramid level (coarsest first):
 //     [level > 0] JBU of depths_geom.dmb -> depths.dmb, then photometric stage with hierarchy
 //     photometric stage -> CPU planar prior -> prior stage (same object)            -> depths.dmb
 //     2 x geometric-consistency stage (the second one with multi_geometry)          -> depths_geom.dmb
 // `--resident 1` runs the same stages GPU-resident (RunResident below): no .dmb round trips between stages, every
-// image read once per level; it writes the same final maps.
-// Fusion (RunFusionCuda, main.cpp:478-479) is not part of this path.
+// image read once per level; it writes the same final maps.  `--gpus N` deals the reference views to N devices (one host
+// thread each) and exchanges the depth maps with peer copies at the two exchange points of a level.
+// Fusion (RunFusionCuda, main.cpp:478-479) follows the last level (`--fusion 0` skips it): ACMMP/ACMM_model_cuda_5.ply.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -17,8 +18,10 @@
 #include <iostream>
 #include <map>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
 #include <sstream>
+#include <thread>
 #include <stdexcept>
 #include <sys/stat.h>
 #include <sys/types.h>
@@ -37,6 +40,9 @@ double g_gpu_ms = 0.0, g_prior_s = 0.0;
 // change (incl. context creation), stage runs (kernels + waits + downloads), depth-map export, result output
 double g_t_load = 0.0, g_t_views = 0.0, g_t_run = 0.0, g_t_export = 0.0, g_t_output = 0.0, g_t_join = 0.0;
 double g_t_sweep1 = 0.0, g_t_geom = 0.0;   // totals: first sweep, geometric sweeps
+double g_t_exchange = 0.0;                 // --gpus N: peer copies of the depth maps
+int g_gpus = 1, g_devices_used = 1;
+int g_fusion = 1;                          // RunFusionCuda after the last level, like main.cpp:478-479
 
 std::mutex g_prior_mutex;
 void add_prior_s(double dt)      // the CPU prior stages of two views may overlap on worker threads
@@ -219,7 +225,45 @@ struct DeviceMap {
     }
 };
 
-bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems, const size_t num_images, int max_num_downscale)
+// Rendezvous of the per-device host threads; abort() releases everybody when one of them failed.
+class PhaseBarrier {
+public:
+    explicit PhaseBarrier(int n) : n_(n) {}
+    bool wait()                                           // false: the run was aborted
+    {
+        std::unique_lock<std::mutex> lock(m_);
+        if (aborted_) return false;
+        const int gen = gen_;
+        if (++count_ == n_) {
+            count_ = 0;
+            ++gen_;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lock, [&] { return gen != gen_ || aborted_; });
+        }
+        return !aborted_;
+    }
+    void abort()
+    {
+        std::lock_guard<std::mutex> lock(m_);
+        aborted_ = true;
+        cv_.notify_all();
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+    bool aborted_ = false;
+};
+
+// Multi-GPU: the reference views are dealt round-robin to `ndev` devices, one host thread per
+// device issues that device's work.  Views are independent inside a stage (main.cpp:431-446); the only cross-view input
+// is the neighbours' depth maps of the geometric stages, so every device keeps a table with the current map of EVERY
+// view and pulls the maps other devices own at the two exchange points of a level (after the prior stage, after the first
+// geometric round) with peer copies over NVLink -- what the reference passes through depths.dmb / depths_geom.dmb.
+// Inside a device the second geometric round stays Gauss-Seidel (a view reads the maps its own device rewrote earlier in
+// the round), across devices it is Jacobi (the maps of the first round); one device = the reference's order exactly.
+bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems, const size_t num_images, int max_num_downscale, int ndev)
 {
     std::map<int, int> index_of;                      // image id -> position in `problems`
     for (size_t i = 0; i < problems.size(); ++i) index_of[problems[i].ref_image_id] = (int)i;
@@ -230,10 +274,20 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (it == index_of.end() || (size_t)it->second >= num_images) return false;    // a neighbour that is not processed
         }
     }
-    cudaSetDevice(g_device);
-    {   // One context per view stays alive: images of the view and its sources twice (layered + per-view textures), the
+    int avail = 0;
+    cudaGetDeviceCount(&avail);
+    if (ndev < 1 || g_device + ndev > avail) {
+        std::cout << "resident schedule: " << ndev << " devices from device " << g_device << " requested, " << avail << " present" << std::endl;
+        return false;
+    }
+    ndev = (int)std::min<size_t>((size_t)ndev, std::max<size_t>(num_images, 1));
+    const auto device_of = [&](size_t view) { return (int)(view % (size_t)ndev); };
+    for (int d = 0; d < ndev; ++d) {
+        // One context per view stays alive: images of the view and its sources twice (layered + per-view textures), the
         // padded reference, planes x 2, costs x 3, view masks, two RNG states, prior planes + masks, for all pyramid
-        // levels of the pool (1 + 1/4 + 1/16).  Scenes that do not fit fall back to the file-chained schedule.
+        // levels of the pool (1 + 1/4 + 1/16); plus two depth-map tables of all views.  Scenes that do not fit fall back
+        // to the file-chained schedule.
+        cudaSetDevice(g_device + d);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         double need = 0.0;
@@ -242,197 +296,285 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (!ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) continue;
             const double scale = std::min(1.0, (double)problems[i].max_image_size / std::max(cols, rows));
             const double px = (double)cols * rows * scale * scale;
-            need += px * (8.0 * (problems[i].src_image_ids.size() + 1) + 160.0) * 1.32;
+            if (device_of(i) == d) need += px * (8.0 * (problems[i].src_image_ids.size() + 1) + 160.0) * 1.32;
+            need += px * 8.0 * (ndev > 1 ? 1.0 : 0.0);
         }
         if (need > 0.85 * (double)free_b) {
-            std::cout << "resident schedule: " << num_images << " views need about " << need / 1e9 << " GB of device memory, "
+            std::cout << "resident schedule: device " << g_device + d << " needs about " << need / 1e9 << " GB of device memory, "
                       << free_b / 1e9 << " GB are free" << std::endl;
             return false;
         }
     }
+    if (ndev > 1) {
+        for (int a = 0; a < ndev; ++a)
+            for (int b = 0; b < ndev; ++b)
+                if (a != b) {
+                    cudaSetDevice(g_device + a);
+                    if (cudaDeviceEnablePeerAccess(g_device + b, 0) != cudaSuccess) (void)cudaGetLastError();      // copies then stage through the host
+                }
+        std::cout << "resident schedule on " << ndev << " devices, views dealt round-robin" << std::endl;
+    }
+
     std::vector<std::unique_ptr<ACMMP>> objs(num_images);
-    std::vector<DeviceMap> dmap(num_images), gmap(num_images);
+    // tab[d][v]: the map of view v on device d ("d" = what depths.dmb would hold, "g" = depths_geom.dmb)
+    std::vector<std::vector<DeviceMap>> dtab(ndev, std::vector<DeviceMap>(num_images)), gtab(ndev, std::vector<DeviceMap>(num_images));
     std::vector<cv::Mat_<float>> final_prior_depth(num_images);
     std::vector<size_t> full_px(num_images, 0);         // upper bound of a view's pixel count at any level
     for (size_t i = 0; i < num_images; ++i) {
         int cols = 0, rows = 0;
         if (ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) full_px[i] = (size_t)cols * rows;
     }
-    bool first_level = true;
-    while (max_num_downscale >= 0) {
-        std::cout << "Scale: " << max_num_downscale << std::endl;
-        for (auto &problem : problems) {
-            if (problem.num_downscale >= 0) {
-                problem.cur_image_size = problem.max_image_size / (int)std::pow(2, problem.num_downscale);
-                problem.num_downscale--;
-            }
-        }
-        const bool finest = max_num_downscale == 0;
-        // every view of this level, read and scaled once
-        std::vector<cv::Mat_<float>> level_image(num_images);
-        std::vector<Camera> level_camera(num_images);
-        double tp = now_s();
+    // which views does device d need the maps of (its own views' source views that another device owns)
+    std::vector<std::vector<size_t>> remote(ndev);
+    for (int d = 0; d < ndev; ++d) {
+        std::vector<char> need(num_images, 0);
         for (size_t i = 0; i < num_images; ++i)
-            LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].cur_image_size, level_image[i], level_camera[i]);
-        g_t_load += now_s() - tp;
+            if (device_of(i) == d)
+                for (int id : problems[i].src_image_ids) need[index_of[id]] = 1;
+        for (size_t v = 0; v < num_images; ++v)
+            if (need[v] && device_of(v) != d) remote[d].push_back(v);
+    }
+    std::vector<cv::Mat_<float>> level_image(num_images);
+    std::vector<Camera> level_camera(num_images);
+    std::vector<int> level_w(num_images, 0), level_h(num_images, 0);
+    PhaseBarrier barrier(ndev);
+    std::mutex stats_mutex;
+    std::string failure;
+    const int levels = max_num_downscale + 1;
 
-        struct PriorJob {
-            std::future<void> done;
-            std::vector<cv::Point> support;
-            std::vector<Triangle> inside;                  // --gpu-prior 1: triangles inside the image, id order
-            cv::Mat_<float> mask_tri;                      // --gpu-prior 0: the CPU stage's outputs
-            std::vector<float4> planeParams_tri;
-            double host_s = 0.0;
+    auto device_main = [&](const int d) {
+        // per-thread wall-clock attribution, merged into the globals at the end
+        double t_load = 0, t_views = 0, t_run = 0, t_export = 0, t_output = 0, t_join = 0, t_sweep1 = 0, t_geom = 0, t_exchange = 0, gpu_ms = 0;
+        cudaSetDevice(g_device + d);
+        std::vector<size_t> mine;
+        for (size_t i = 0; i < num_images; ++i)
+            if (device_of(i) == d) mine.push_back(i);
+        auto pull = [&](std::vector<std::vector<DeviceMap>> &tab) {
+            // the maps other devices own, straight from their tables into mine (NVLink peer copies)
+            const double t0 = now_s();
+            for (size_t v : remote[d]) {
+                const int o = device_of(v);
+                tab[d][v].fit(level_w[v], level_h[v], full_px[v]);
+                if (cudaMemcpyPeerAsync(tab[d][v].ptr, g_device + d, tab[o][v].ptr, g_device + o, sizeof(float) * (size_t)level_w[v] * level_h[v], 0) != cudaSuccess)
+                    throw std::runtime_error("peer copy of a depth map failed");
+            }
+            if (cudaStreamSynchronize(0) != cudaSuccess) throw std::runtime_error("peer copies of the depth maps failed");
+            t_exchange += now_s() - t0;
         };
-        std::vector<std::unique_ptr<PriorJob>> pending(num_images);
-        auto finish_view = [&](const size_t v) {
-            ACMMP &a = *objs[v];
-            double tw = now_s();
-            pending[v]->done.get();                        // rethrows a worker exception
-            g_t_join += now_s() - tw;
-            tw = now_s();
-            if (g_gpu_prior) {
-                a.CudaPlanarPriorFromTriangles(pending[v]->inside);
-                add_prior_s(pending[v]->host_s + (now_s() - tw));
-            } else {
-                a.CudaPlanarPriorInitialization(pending[v]->planeParams_tri, pending[v]->mask_tri);
-            }
-            pending[v].reset();
-            const int width = a.GetReferenceImageWidth(), height = a.GetReferenceImageHeight();
-            tw = now_s();
-            a.RunPatchMatchResident(finest);                                     // finest level: depths.dmb is an output
-            g_t_run += now_s() - tw;
-            float tt[8];
-            a.GetTimings(tt);
-            g_gpu_ms += tt[0] + tt[1] + tt[2];
-            tw = now_s();
-            if (finest) {
-                final_prior_depth[v] = cv::Mat_<float>(height, width);
-                for (int k = 0; k < width * height; ++k) final_prior_depth[v].ptr()[k] = a.GetPlaneHypothesis(k).w;
-            }
-            g_t_output += now_s() - tw;
-            tw = now_s();
-            dmap[v].fit(width, height, full_px[v]);
-            a.ExportDepthDevice(dmap[v].ptr);
-            g_t_export += now_s() - tw;
-        };
-        const double t_sweep1 = now_s();
-        for (size_t i = 0; i < num_images; ++i) {                                // photometric + prior stage
-            const Problem &problem = problems[i];
-            std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << "..." << std::endl;
-            std::vector<cv::Mat_<float>> images{level_image[i]};
-            std::vector<Camera> cameras{level_camera[i]};
-            for (int id : problem.src_image_ids) {
-                images.push_back(level_image[index_of[id]]);
-                cameras.push_back(level_camera[index_of[id]]);
-            }
-            tp = now_s();
-            if (first_level) {
-                objs[i].reset(new ACMMP(g_device));
-                objs[i]->SetSeed(g_seed);
-            }
-            ACMMP &acmmp = *objs[i];
-            acmmp.SetViewsHost(images, cameras, !first_level);
-            g_t_views += now_s() - tp;
-            tp = now_s();
-            acmmp.RunPatchMatchResident(!g_gpu_prior);                           // the CPU prior stage reads the result
-            g_t_run += now_s() - tp;
-            float t[8];
-            acmmp.GetTimings(t);
-            g_gpu_ms += t[0] + t[1] + t[2];
-            // The host part of the planar-prior stage of view i (the Delaunay triangulation; with --gpu-prior 0 the whole
-            // CPU stage) runs on a worker thread while this thread -- which issues ALL device work, in a fixed order --
-            // goes on with the photometric stage of view i + 1; view i is finished (prior upload, prior-stage
-            // PatchMatch, depth export) one iteration later.  (Device work from two threads would queue behind each
-            // other's persistent kernels: a k_pass launch holds every SM for its ~20 ms.)
-            pending[i].reset(new PriorJob());
-            PriorJob *job = pending[i].get();
-            ACMMP *obj = objs[i].get();
-            if (g_gpu_prior) {
-                const double t0 = now_s();
-                acmmp.SetPlanarPriorParams();
-                acmmp.GetSupportPointsDevice(job->support);
-                add_prior_s(now_s() - t0);
-                job->done = std::async(std::launch::async, [job, obj]() {
-                    const double t1 = now_s();
-                    const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
-                    const cv::Rect imageRC(0, 0, width, height);
-                    const auto triangles = obj->DelaunayTriangulation(imageRC, job->support);
-                    job->inside.reserve(triangles.size());
-                    for (const auto &tr : triangles)
-                        if (imageRC.contains(tr.pt1) && imageRC.contains(tr.pt2) && imageRC.contains(tr.pt3)) job->inside.push_back(tr);
-                    job->host_s = now_s() - t1;
-                });
-            } else {
-                job->done = std::async(std::launch::async, [job, obj]() {
-                    const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
-                    cv::Mat_<float> depths(height, width);
-                    for (int k = 0; k < width * height; ++k) depths.ptr()[k] = obj->GetPlaneHypothesis(k).w;
-                    PlanarPriorStage(*obj, depths, job->mask_tri, job->planeParams_tri);        // adds its time to g_prior_s
-                });
-            }
-            if (i > 0) finish_view(i - 1);
-        }
-        if (num_images > 0) finish_view(num_images - 1);
-        g_t_sweep1 += now_s() - t_sweep1;
-        const double t_geom = now_s();
-        for (int geom_iter = 0; geom_iter < 2; ++geom_iter) {                    // geometric sweeps
-            const bool multi_geometry = geom_iter > 0;
-            for (size_t i = 0; i < num_images; ++i) {
-                const Problem &problem = problems[i];
-                ACMMP &acmmp = *objs[i];
-                acmmp.ResetModes();
-                acmmp.SetGeomConsistencyParams(multi_geometry);
-                std::vector<const float *> maps;
-                std::vector<int> ws, hs;
-                for (int id : problem.src_image_ids) {
-                    const DeviceMap &m = multi_geometry ? gmap[index_of[id]] : dmap[index_of[id]];
-                    maps.push_back(m.ptr);
-                    ws.push_back(m.w);
-                    hs.push_back(m.h);
+        bool first_level = true;
+        for (int level = 0; level < levels; ++level) {
+            const int scale = max_num_downscale - level;
+            const bool finest = scale == 0;
+            if (d == 0) {
+                std::cout << "Scale: " << scale << std::endl;
+                for (auto &problem : problems) {
+                    if (problem.num_downscale >= 0) {
+                        problem.cur_image_size = problem.max_image_size / (int)std::pow(2, problem.num_downscale);
+                        problem.num_downscale--;
+                    }
                 }
-                acmmp.SetNeighbourDepthMapsDevice(maps, ws, hs);
-                const bool last = finest && multi_geometry;
-                double tg = now_s();
-                acmmp.RunPatchMatchResident(last);
-                g_t_run += now_s() - tg;
+            }
+            if (!barrier.wait()) return;
+            // every view of this level, read and scaled once (each thread its share, all of them shared afterwards)
+            double tp = now_s();
+            for (size_t i : mine) {
+                LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].cur_image_size, level_image[i], level_camera[i]);
+                level_w[i] = level_image[i].cols;
+                level_h[i] = level_image[i].rows;
+            }
+            t_load += now_s() - tp;
+            if (!barrier.wait()) return;
+
+            struct PriorJob {
+                std::future<void> done;
+                std::vector<cv::Point> support;
+                std::vector<Triangle> inside;                  // --gpu-prior 1: triangles inside the image, id order
+                cv::Mat_<float> mask_tri;                      // --gpu-prior 0: the CPU stage's outputs
+                std::vector<float4> planeParams_tri;
+                double host_s = 0.0;
+            };
+            std::map<size_t, std::unique_ptr<PriorJob>> pending;
+            auto finish_view = [&](const size_t v) {
+                ACMMP &a = *objs[v];
+                double tw = now_s();
+                pending[v]->done.get();                        // rethrows a worker exception
+                t_join += now_s() - tw;
+                tw = now_s();
+                if (g_gpu_prior) {
+                    a.CudaPlanarPriorFromTriangles(pending[v]->inside);
+                    add_prior_s(pending[v]->host_s + (now_s() - tw));
+                } else {
+                    a.CudaPlanarPriorInitialization(pending[v]->planeParams_tri, pending[v]->mask_tri);
+                }
+                pending.erase(v);
+                const int width = a.GetReferenceImageWidth(), height = a.GetReferenceImageHeight();
+                tw = now_s();
+                a.RunPatchMatchResident(finest);                                     // finest level: depths.dmb is an output
+                t_run += now_s() - tw;
+                float tt[8];
+                a.GetTimings(tt);
+                gpu_ms += tt[0] + tt[1] + tt[2];
+                tw = now_s();
+                if (finest) {
+                    final_prior_depth[v] = cv::Mat_<float>(height, width);
+                    for (int k = 0; k < width * height; ++k) final_prior_depth[v].ptr()[k] = a.GetPlaneHypothesis(k).w;
+                }
+                t_output += now_s() - tw;
+                tw = now_s();
+                dtab[d][v].fit(width, height, full_px[v]);
+                a.ExportDepthDevice(dtab[d][v].ptr);
+                t_export += now_s() - tw;
+            };
+            const double t_s1 = now_s();
+            size_t previous = (size_t)-1;
+            for (size_t i : mine) {                                                  // photometric + prior stage
+                const Problem &problem = problems[i];
+                std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << "..." << std::endl;
+                std::vector<cv::Mat_<float>> images{level_image[i]};
+                std::vector<Camera> cameras{level_camera[i]};
+                for (int id : problem.src_image_ids) {
+                    images.push_back(level_image[index_of[id]]);
+                    cameras.push_back(level_camera[index_of[id]]);
+                }
+                tp = now_s();
+                if (first_level) {
+                    objs[i].reset(new ACMMP(g_device + d));
+                    objs[i]->SetSeed(g_seed);
+                }
+                ACMMP &acmmp = *objs[i];
+                acmmp.SetViewsHost(images, cameras, !first_level);
+                t_views += now_s() - tp;
+                tp = now_s();
+                acmmp.RunPatchMatchResident(!g_gpu_prior);                           // the CPU prior stage reads the result
+                t_run += now_s() - tp;
                 float t[8];
                 acmmp.GetTimings(t);
-                g_gpu_ms += t[0] + t[1] + t[2];
-                tg = now_s();
-                gmap[i].fit(acmmp.GetReferenceImageWidth(), acmmp.GetReferenceImageHeight(), full_px[i]);
-                acmmp.ExportDepthDevice(gmap[i].ptr);
-                g_t_export += now_s() - tg;
-                tg = now_s();
-                if (last) {
-                    const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
-                    cv::Mat_<float> depths = cv::Mat_<float>::zeros(height, width), costs = cv::Mat_<float>::zeros(height, width);
-                    cv::Mat_<cv::Vec3f> normals = cv::Mat_<cv::Vec3f>::zeros(height, width);
-                    for (int k = 0; k < width * height; ++k) {
-                        const float4 ph = acmmp.GetPlaneHypothesis(k);
-                        depths.ptr()[k] = ph.w;
-                        normals.ptr()[k] = cv::Vec3f(ph.x, ph.y, ph.z);
-                        costs.ptr()[k] = acmmp.GetCost(k);
-                    }
-                    const std::string result_folder = result_folder_of(dense_folder, problem.ref_image_id);
-                    mkdir(result_folder.c_str(), 0777);
-                    writeDepthDmb(result_folder + "/depths.dmb", final_prior_depth[i]);
-                    writeDepthDmb(result_folder + "/depths_geom.dmb", depths);
-                    writeNormalDmb(result_folder + "/normals.dmb", normals);
-                    writeDepthDmb(result_folder + "/costs.dmb", costs);
-                    std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << " done!" << std::endl;
+                gpu_ms += t[0] + t[1] + t[2];
+                // The host part of the planar-prior stage of view i (the Delaunay triangulation; with --gpu-prior 0 the whole
+                // CPU stage) runs on a worker thread while this thread -- which issues ALL work of its device, in a fixed
+                // order -- goes on with the photometric stage of its next view; view i is finished (prior upload, prior-stage
+                // PatchMatch, depth export) one iteration later.  (Device work from two threads would queue behind each
+                // other's persistent kernels: a k_pass launch holds every SM for its ~20 ms.)
+                pending[i].reset(new PriorJob());
+                PriorJob *job = pending[i].get();
+                ACMMP *obj = objs[i].get();
+                if (g_gpu_prior) {
+                    const double t0 = now_s();
+                    acmmp.SetPlanarPriorParams();
+                    acmmp.GetSupportPointsDevice(job->support);
+                    add_prior_s(now_s() - t0);
+                    job->done = std::async(std::launch::async, [job, obj]() {
+                        const double t1 = now_s();
+                        const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
+                        const cv::Rect imageRC(0, 0, width, height);
+                        const auto triangles = obj->DelaunayTriangulation(imageRC, job->support);
+                        job->inside.reserve(triangles.size());
+                        for (const auto &tr : triangles)
+                            if (imageRC.contains(tr.pt1) && imageRC.contains(tr.pt2) && imageRC.contains(tr.pt3)) job->inside.push_back(tr);
+                        job->host_s = now_s() - t1;
+                    });
+                } else {
+                    job->done = std::async(std::launch::async, [job, obj]() {
+                        const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
+                        cv::Mat_<float> depths(height, width);
+                        for (int k = 0; k < width * height; ++k) depths.ptr()[k] = obj->GetPlaneHypothesis(k).w;
+                        PlanarPriorStage(*obj, depths, job->mask_tri, job->planeParams_tri);        // adds its time to g_prior_s
+                    });
                 }
-                g_t_output += now_s() - tg;
+                if (previous != (size_t)-1) finish_view(previous);
+                previous = i;
             }
+            if (previous != (size_t)-1) finish_view(previous);
+            t_sweep1 += now_s() - t_s1;
+            if (!barrier.wait()) return;                                             // every owner's map is in its table
+            if (ndev > 1) pull(dtab);
+            if (!barrier.wait()) return;
+            const double t_g = now_s();
+            for (int geom_iter = 0; geom_iter < 2; ++geom_iter) {                    // geometric sweeps
+                const bool multi_geometry = geom_iter > 0;
+                for (size_t i : mine) {
+                    const Problem &problem = problems[i];
+                    ACMMP &acmmp = *objs[i];
+                    acmmp.ResetModes();
+                    acmmp.SetGeomConsistencyParams(multi_geometry);
+                    std::vector<const float *> maps;
+                    std::vector<int> ws, hs;
+                    for (int id : problem.src_image_ids) {
+                        const DeviceMap &m = multi_geometry ? gtab[d][index_of[id]] : dtab[d][index_of[id]];
+                        maps.push_back(m.ptr);
+                        ws.push_back(m.w);
+                        hs.push_back(m.h);
+                    }
+                    acmmp.SetNeighbourDepthMapsDevice(maps, ws, hs);
+                    const bool last = finest && multi_geometry;
+                    double tg = now_s();
+                    acmmp.RunPatchMatchResident(last);
+                    t_run += now_s() - tg;
+                    float t[8];
+                    acmmp.GetTimings(t);
+                    gpu_ms += t[0] + t[1] + t[2];
+                    tg = now_s();
+                    gtab[d][i].fit(acmmp.GetReferenceImageWidth(), acmmp.GetReferenceImageHeight(), full_px[i]);
+                    acmmp.ExportDepthDevice(gtab[d][i].ptr);
+                    t_export += now_s() - tg;
+                    tg = now_s();
+                    if (last) {
+                        const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
+                        cv::Mat_<float> depths = cv::Mat_<float>::zeros(height, width), costs = cv::Mat_<float>::zeros(height, width);
+                        cv::Mat_<cv::Vec3f> normals = cv::Mat_<cv::Vec3f>::zeros(height, width);
+                        for (int k = 0; k < width * height; ++k) {
+                            const float4 ph = acmmp.GetPlaneHypothesis(k);
+                            depths.ptr()[k] = ph.w;
+                            normals.ptr()[k] = cv::Vec3f(ph.x, ph.y, ph.z);
+                            costs.ptr()[k] = acmmp.GetCost(k);
+                        }
+                        const std::string result_folder = result_folder_of(dense_folder, problem.ref_image_id);
+                        mkdir(result_folder.c_str(), 0777);
+                        writeDepthDmb(result_folder + "/depths.dmb", final_prior_depth[i]);
+                        writeDepthDmb(result_folder + "/depths_geom.dmb", depths);
+                        writeNormalDmb(result_folder + "/normals.dmb", normals);
+                        writeDepthDmb(result_folder + "/costs.dmb", costs);
+                        std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << " done!" << std::endl;
+                    }
+                    t_output += now_s() - tg;
+                }
+                if (!multi_geometry && ndev > 1) {
+                    if (!barrier.wait()) return;                                     // ExportDepthDevice waits for its copy
+                    pull(gtab);
+                    if (!barrier.wait()) return;
+                }
+            }
+            t_geom += now_s() - t_g;
+            first_level = false;
+            if (!barrier.wait()) return;                                             // nobody overwrites a table somebody still reads
         }
-        g_t_geom += now_s() - t_geom;
-        first_level = false;
-        max_num_downscale--;
-    }
+        std::lock_guard<std::mutex> lock(stats_mutex);
+        g_gpu_ms += gpu_ms;
+        g_t_load = std::max(g_t_load, t_load); g_t_views = std::max(g_t_views, t_views); g_t_run = std::max(g_t_run, t_run);
+        g_t_export = std::max(g_t_export, t_export); g_t_output = std::max(g_t_output, t_output); g_t_join = std::max(g_t_join, t_join);
+        g_t_sweep1 = std::max(g_t_sweep1, t_sweep1); g_t_geom = std::max(g_t_geom, t_geom); g_t_exchange = std::max(g_t_exchange, t_exchange);
+    };
+    auto guarded = [&](const int d) {
+        try {
+            device_main(d);
+        } catch (const std::exception &e) {
+            {
+                std::lock_guard<std::mutex> lock(stats_mutex);
+                if (failure.empty()) failure = e.what();
+            }
+            barrier.abort();
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int d = 1; d < ndev; ++d) threads.emplace_back(guarded, d);
+    guarded(0);
+    for (auto &t : threads) t.join();
     // The process ends right after this schedule: the contexts (a few GB of pooled device and pinned buffers each)
     // are left to the driver's process teardown, which reclaims them much faster than hundreds of cudaFree /
     // cudaFreeHost calls would (measured: ~0.4 s per view at C2 size).
     for (auto &o : objs) o.release();
+    if (!failure.empty()) throw std::runtime_error(failure);
+    g_devices_used = ndev;
     return true;
 }
 
@@ -441,7 +583,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
 int main(int argc, char **argv)
 {
     if (argc < 2) {
-        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--max-views N] [--resident 0|1] [--gpu-prior 0|1]" << std::endl;
+        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--gpus N] [--max-views N] [--resident 0|1] [--gpu-prior 0|1] [--fusion 0|1]" << std::endl;
         return -1;
     }
     const std::string dense_folder = argv[1];
@@ -453,6 +595,8 @@ int main(int argc, char **argv)
         if (!std::strcmp(argv[i], "--seed")) g_seed = std::strtoull(argv[i + 1], nullptr, 10);
         else if (!std::strcmp(argv[i], "--device")) g_device = std::atoi(argv[i + 1]);
         else if (!std::strcmp(argv[i], "--max-views")) max_views = (size_t)std::atoi(argv[i + 1]);
+        else if (!std::strcmp(argv[i], "--gpus")) { g_gpus = std::atoi(argv[i + 1]); resident = 1; }      // multi-GPU is a resident schedule
+        else if (!std::strcmp(argv[i], "--fusion")) g_fusion = std::atoi(argv[i + 1]);
     }
     std::vector<Problem> problems;
     GenerateSampleList(dense_folder, problems);
@@ -482,7 +626,7 @@ int main(int argc, char **argv)
         int max_num_downscale = ComputeMultiScaleSettings(dense_folder, problems);
         if (resident) {
             std::vector<Problem> work = problems;
-            if (RunResident(dense_folder, work, num_images, max_num_downscale)) max_num_downscale = -1;     // done
+            if (RunResident(dense_folder, work, num_images, max_num_downscale, g_gpus)) max_num_downscale = -1;     // done
             else { std::cout << "resident schedule not applicable to this scene; running the file-chained schedule" << std::endl; resident = 0; }
         }
         int flag = 0;
@@ -512,8 +656,24 @@ int main(int argc, char **argv)
         std::cerr << "acmmp_b200: " << e.what() << std::endl;
         return 1;
     }
-    std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << now_s() - t_start << ", \"kernel_ms\": " << g_gpu_ms
+    const double wall_patchmatch = now_s() - t_start;
+    double fusion_s = 0.0, fusion_kernel_ms = 0.0;
+    size_t fusion_points = 0;
+    if (g_fusion) {                                            // main.cpp:478-479
+        try {
+            const double t0 = now_s();
+            std::vector<Problem> fused(problems.begin(), problems.begin() + num_images);
+            fusion_points = RunFusionCuda(dense_folder, fused, true, g_device, &fusion_kernel_ms);
+            fusion_s = now_s() - t0;
+        } catch (const std::exception &e) {
+            std::cerr << "acmmp_b200: " << e.what() << std::endl;
+            return 1;
+        }
+    }
+    std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << wall_patchmatch << ", \"kernel_ms\": " << g_gpu_ms
               << ", \"prior_cpu_s\": " << g_prior_s << ", \"load_s\": " << g_t_load << ", \"views_s\": " << g_t_views << ", \"run_s\": " << g_t_run
-              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"sweep1_s\": " << g_t_sweep1 << ", \"geom_s\": " << g_t_geom << "}" << std::endl;
+              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"sweep1_s\": " << g_t_sweep1 << ", \"geom_s\": " << g_t_geom
+              << ", \"gpus\": " << (resident ? g_devices_used : 1) << ", \"exchange_s\": " << g_t_exchange
+              << ", \"fusion_s\": " << fusion_s << ", \"fusion_kernel_ms\": " << fusion_kernel_ms << ", \"fusion_points\": " << fusion_points << "}" << std::endl;
     return 0;
 }

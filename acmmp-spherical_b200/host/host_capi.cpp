@@ -104,4 +104,17 @@ int acmmp_host_pair_count(const char *dense_folder)
     return total;      // 1000 * views + kept source views
 }
 
+// points: n x 9 floats (PointList); writes the PLY the reference's StoreColorPlyFileBinaryPointCloud writes
+int acmmp_host_write_ply(const char *path, const float *points9, int n)
+{
+    std::vector<PointList> pc((size_t)n);
+    std::memcpy(static_cast<void *>(pc.data()), points9, sizeof(PointList) * (size_t)n);
+    try {
+        StoreColorPlyFileBinaryPointCloud(path, pc);
+    } catch (...) {
+        return -1;
+    }
+    return 0;
+}
+
 } // extern "C"

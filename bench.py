@@ -117,11 +117,12 @@ def algorithmic_samples_per_pass(w, h, nsrc):
 
 
 def load_peaks():
-    peaks = dict(hbm_gbs=6650.0, source="fallback")
+    peaks = dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         try:
-            peaks = dict(hbm_gbs=float(json.load(open(p))["hbm_gbs"]), source="MEASURED_PEAKS.json")
+            m = json.load(open(p))
+            peaks = dict(hbm_gbs=float(m["hbm_gbs"]), sm_max_mhz=float(m.get("sm_max_mhz", 1965.0)), source="MEASURED_PEAKS.json")
         except Exception:
             pass
     t = ROOT / "profiles" / "tex_peak_b200.json"
@@ -214,26 +215,213 @@ def run_step(levels, backend, prior_cache, exch):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_baseline_port(levels):
+def cpu_baseline_port(levels, n_src):
     """The CPU restatement (oracle/acmmp_oracle.c) on a bounded sample of the same workload: one black
     photometric pass at the coarsest level (all source views)."""
     from oracle import cpu_oracle
     L = levels[0]
     H, W = L.images[0].shape
-    nsrc = len(L.images) - 1
     st = cpu_oracle.random_init(L.images, L.cams, seed=1234, with_costs=False)
     st["costs"] = np.full((H, W), 1.0, np.float32)
     st["views"] = np.zeros((H, W), np.uint32)
     t0 = time.perf_counter()
     cpu_oracle.checkerboard_pass(L.images, L.cams, st, 0, 0)
     dt = time.perf_counter() - t0
-    samples = algorithmic_samples_per_pass(W, H, nsrc)
+    samples = algorithmic_samples_per_pass(W, H, n_src)
     rate = samples / dt
     # samples of one whole view: per level 20 passes (+ ~4 % for the initialisations, ignored)
-    per_view = sum(20 * algorithmic_samples_per_pass(l.images[0].shape[1], l.images[0].shape[0], nsrc) for l in levels)
+    per_view = sum(20 * algorithmic_samples_per_pass(l.images[0].shape[1], l.images[0].shape[0], n_src) for l in levels)
     return dict(value=rate / per_view, unit=UNIT, cores=cpu_oracle.num_threads(), kind="port",
-                sample=f"one black photometric checkerboard pass at the coarsest level ({W}x{H}, {nsrc} source views) "
+                sample=f"one black photometric checkerboard pass at the coarsest level ({W}x{H}, {n_src} source views) "
                        f"in {dt:.1f} s = {rate:.3g} NCC samples/s, extrapolated to the {per_view:.3g} samples of one view")
+
+
+def roofline_of(cfg, Wf, Hf, pass_ms, peaks):
+    """Roofline object of the dominant kernel (k_pass, photometric, finest level).  Unit of work: the NCC sample
+    (pixel x hypothesis x source view x tap).  PINHOLE is bound by the texture pipe (1 bilinear fetch per
+    sample: peak = the measured R32F fetch rate); SPHERE by the special-function unit (6 MUFU-class operations per sample:
+    sqrt, 3 rcp, rsqrt, floor; peak = 16 per clock per SM x 148 SMs x max clock / 6)."""
+    photometric_ms = pass_ms.get("photometric")
+    if not photometric_ms:
+        return None
+    n_src = cfg["n_src"]
+    alg = algorithmic_samples_per_pass(Wf, Hf, n_src)
+    ach = alg / (photometric_ms * 1e-3) / 1e9
+    facts = {}
+    fp = ROOT / "profiles" / "k_pass_ncu_facts.json"
+    if fp.exists():
+        facts = json.load(open(fp)).get(cfg["model"], {})
+    if cfg["model"] == "pinhole":
+        bound, peak, peak_how = "tex", peaks["tex_gfetch_s"], "measured R32F bilinear fetch rate of this pool's B200 (profiles/tex_peak_b200.json)"
+    else:
+        peak = 16 * 148 * peaks["sm_max_mhz"] * 1e6 / 6 / 1e9
+        bound, peak_how = "sfu", f"16 special-function results per clock per SM x 148 SMs x {peaks['sm_max_mhz']:.0f} MHz / 6 per sample (nominal; no measured SFU peak)"
+    hbm_bytes = 190 * (Wf * Hf // 2)
+    return {
+        "bound": bound, "kernel": f"k_pass<{cfg['model'].upper()}, photometric>, finest level", "achieved": ach, "peak": peak,
+        "unit": "Gsample/s", "frac": ach / peak, "traffic": facts.get("dram_bytes_per_launch"),
+        "algorithmic_samples_per_launch": alg,
+        "executed_samples_per_launch": facts.get("executed_lane_fetches_per_launch"),
+        "tex_pipe_pct": facts.get("tex_data_pipe_pct"), "issue_slots_pct": facts.get("issue_slots_pct"),
+        "xu_pipe_pct": facts.get("xu_pipe_pct"), "ncu_source": facts.get("source"),
+        "note": f"not HBM bound (SURVEY.md 8(d)): achieved = algorithmic NCC samples (14 hypotheses x {n_src} views x 36 taps x pixels/2) / mean "
+                f"launch time (CUDA events, this run); peak = {peak_how}; traffic / executed samples / pipe utilisation: static, from the ncu "
+                "capture named in ncu_source (same kernel build, same shape) -- zero-weight views are legitimately skipped, so executed < algorithmic",
+        "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / (photometric_ms * 1e-3) / 1e9,
+                "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"]},
+    }
+
+
+def driver_leg(cfg, scene, ids, device):
+    """The product's own end to end: the C++ driver (`lib/acmmp_b200 --resident 1 --gpu-prior 1`) on a dense folder of the
+    step's 11 views (each using the other ten as source views): image files in, .dmb files out, planar prior INCLUDED
+    (support points + plane fit + rasteriser on the device, Delaunay on a host thread).  Returns seconds per view."""
+    import shutil
+    import tempfile
+    from acmmp_b200 import synth
+    driver = ROOT / "acmmp-spherical_b200" / "lib" / "acmmp_b200"
+    if not driver.exists() or cfg["model"] != "pinhole":
+        return None
+    sub = synth.Scene(scene.model, [scene.images[i] for i in ids], [scene.cams[i] for i in ids], [scene.depths_gt[i] for i in ids],
+                      [(k, [j for j in range(len(ids)) if j != k][: cfg["n_src"]]) for k in range(len(ids))],
+                      [scene.Rs[i] for i in ids], [scene.ts[i] for i in ids], [scene.Ks[i] for i in ids], scene.quads)
+    tmp = tempfile.mkdtemp(prefix="acmmp_bench_driver_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        synth.write_dense_folder(sub, tmp, pgm=True)
+        t0 = time.perf_counter()
+        r = subprocess.run([str(driver), tmp, "--seed", "1234", "--resident", "1", "--gpu-prior", "1", "--device", str(device)],
+                           capture_output=True, text=True, timeout=900)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": (r.stdout[-300:] + r.stderr[-300:])}
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        n = d["views"]
+        return {"views": n, "src_views": cfg["n_src"], "s_per_view": d["wall_s"] / n, "value": n / d["wall_s"], "unit": UNIT,
+                "kernel_s_per_view": d["kernel_ms"] / 1e3 / n, "prior_s_per_view": d["prior_cpu_s"] / n, "process_wall_s": wall,
+                "breakdown_s": {k: d[k] for k in ("load_s", "views_s", "run_s", "export_s", "output_s", "join_s") if k in d},
+                "what": "lib/acmmp_b200 <dense_folder> --resident 1 --gpu-prior 1: wall clock inside the process from pair.txt to the "
+                        "last .dmb file, all levels and stages of every view, planar prior included"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_c3(a, cfg, rank, local_rank, world, use_dist, json_fd):
+    """C3: the whole 64-view scene per step, views sharded over the ranks (acmmp_b200/scene.py)."""
+    import torch
+    import torch.distributed as dist
+    from acmmp_b200 import scene as sc, shard
+    n_views = cfg["scene_views"]
+    # every rank renders the views v = rank (mod world) and shares them through /dev/shm: each rank needs every view as a
+    # source view of its own reference views (ring, 10 nearest)
+    from acmmp_b200 import synth
+    full = make_scene(cfg, [])                                  # cameras + pairs, nothing rendered
+    share = Path("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp") / f"acmmp_bench_c3_{os.environ.get('MASTER_PORT', '0')}"
+    share.mkdir(exist_ok=True)
+    mine = shard.views_of(rank, n_views, world)
+    for v in mine:
+        img, dep = synth._render(full.quads, synth.MODEL_PINHOLE, full.Rs[v], full.ts[v], cfg["width"], cfg["height"], K=full.Ks[v])
+        np.save(share / f"img_{v}.npy", img)
+        np.save(share / f"dep_{v}.npy", dep)
+    torch.cuda.synchronize()
+    if use_dist:
+        dist.barrier()
+    full.images = [np.load(share / f"img_{v}.npy") for v in range(n_views)]
+    gt_mine = {v: np.load(share / f"dep_{v}.npy") for v in mine}
+    if use_dist:
+        dist.barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(share, ignore_errors=True)
+    levels = sc.SceneLevels.build(full, pin=pin)
+    dev = torch.device("cuda", local_rank)
+
+    def alloc(shape):
+        t = torch.empty(shape, dtype=torch.float32, device=dev)
+        return t, t.data_ptr()
+
+    def all_gather(table):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if use_dist:
+            dist.all_gather_into_tensor(table.all.view(-1), table.mine.view(-1))       # NCCL over NVLink: the path's only collective
+        else:
+            table.all[0].copy_(table.mine)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    results = {}
+
+    def on_result(v, planes, costs):
+        gt = gt_mine[v]
+        results[v] = float((np.abs(planes[..., 3] - gt) / gt <= 0.01)[8:-8, 8:-8].mean())
+
+    def step():
+        return sc.run_scene(levels, full.pairs, rank, world, lambda: sc.GpuWorker(local_rank, 1234), alloc, all_gather, on_result=on_result)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    tot = sc.SceneTimes()
+    for _ in range(a.steps):
+        t = step()
+        tot.gpu_ms += t.gpu_ms; tot.exchange_ms += t.exchange_ms; tot.exchange_bytes += t.exchange_bytes; tot.prior_host_s += t.prior_host_s
+        tot.h2d_bytes += t.h2d_bytes; tot.d2h_bytes += t.d2h_bytes; tot.launches += t.launches; tot.passes += t.passes
+        for k, v in t.pass_ms.items():
+            tot.pass_ms.setdefault(k, []).extend(v)
+    barrier()
+    wall_step = (time.perf_counter() - t0) / a.steps
+    clocks = sampler.stop()
+    gpu_ms_step = (tot.gpu_ms + tot.exchange_ms) / a.steps
+    quality = float(np.mean(list(results.values()))) if results else float("nan")
+    if use_dist:
+        tt = torch.tensor([gpu_ms_step, wall_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        gpu_ms_step, wall_step = float(tt[0]), float(tt[1])
+        qq = torch.tensor([quality * len(mine), float(len(mine)), float(tot.launches), float(tot.h2d_bytes), float(tot.d2h_bytes)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(qq, op=dist.ReduceOp.SUM)
+        quality, launches, h2d, d2h = float(qq[0] / qq[1]), int(qq[2]), int(qq[3]), int(qq[4])
+        nranks = dist.get_world_size()
+    else:
+        launches, h2d, d2h, nranks = tot.launches, tot.h2d_bytes, tot.d2h_bytes, 1
+    if rank == 0:
+        peaks = load_peaks()
+        Hf, Wf = levels.images[-1][0].shape
+        pass_ms = {k: float(np.mean(v)) for k, v in tot.pass_ms.items()}
+        line = {
+            "metric": cfg["metric"], "value": n_views / (gpu_ms_step / 1e3), "unit": UNIT, "n_gpus": nranks, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": gpu_ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "views": n_views, "views_per_rank": len(mine), "n_src": cfg["n_src"],
+                       "levels": [list(l[0].shape[::-1]) for l in levels.images],
+                       "l2": "working set per pass (planes 109 MB + 11 x 27 MB images) exceeds the 126 MB L2",
+                       "timing": "value: sum of CUDA-event kernel times + all-gathers, max over ranks; e2e: wall clock incl. H2D of "
+                                 "every image, the host Delaunay of the planar prior (worker threads) and D2H of every final map",
+                       "exchange": "2 NCCL all-gathers per level of [views_per_rank, H, W] float32 depth maps",
+                       "nccl_nranks": nranks},
+            "clocks": clocks,
+            "e2e": {"value": n_views / wall_step, "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
+                    "ms_per_step": wall_step * 1e3},
+            "gpu_launches": launches, "ms_per_checkerboard_pass": pass_ms,
+            "prior_host_s_not_hidden_per_step": tot.prior_host_s / a.steps,
+            "depth_within_1pct_of_ground_truth": quality,
+            "nccl_allgather": {"ms_per_step": tot.exchange_ms / a.steps, "bytes_per_step": tot.exchange_bytes // a.steps},
+        }
+        rl = roofline_of(cfg, Wf, Hf, pass_ms, peaks)
+        if rl:
+            line["roofline"] = rl
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        print(f"[bench] C3: NCCL communicator nranks={nranks}, {n_views} views, {len(mine)} per rank", file=sys.stderr)
+    return 0
 
 
 def main():
@@ -242,9 +430,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-driver-leg", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    cfg = CONFIGS[a.config]
     rank, local_rank, world = dist_env()
     if world != a.gpus and world > 1:
         a.gpus = world
@@ -272,9 +463,26 @@ def main():
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        if a.config == "C3" and a.impl == "b200":
+            return run_c3(a, cfg, rank, local_rank, world, use_dist, json_fd)
+        return run_views(a, cfg, rank, local_rank, world, use_dist, json_fd)
+    finally:
+        if use_dist:
+            dist.barrier()
+            dist.destroy_process_group()
 
+
+def run_views(a, cfg, rank, local_rank, world, use_dist, json_fd):
+    """C2 / C4 (and the reference arm of every config): one reference view per step per GPU."""
+    import torch
+    if use_dist:
+        import torch.distributed as dist
     from acmmp_b200 import pipeline
-    scene, levels, ids = make_levels(rank if a.impl == "b200" else 0)
+    if a.config == "C3":                       # reference arm: a one-view sample of the scene
+        cfg = dict(cfg, scene_views=16, ring=False)
+    n_src = cfg["n_src"]
+    scene, levels, ids = make_levels(cfg, rank if a.impl == "b200" else 0)
     exch = Exchange(world if use_dist else 1, rank, local_rank, ids)
     prior_cache = {}
 
@@ -303,8 +511,7 @@ def main():
 
     # the prior (computed once in warm-up) is a step input like the images: pinned host memory
     for k, (pp, mm) in list(prior_cache.items()):
-        prior_cache[k] = (torch.from_numpy(np.ascontiguousarray(pp)).pin_memory().numpy(),
-                          torch.from_numpy(np.ascontiguousarray(mm)).pin_memory().numpy())
+        prior_cache[k] = (pin(pp), pin(mm))
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -329,34 +536,37 @@ def main():
 
     gpu_ms_step = (tot.gpu_ms + exch.ms) / a.steps
     wall_step = wall / a.steps
+    nranks = 1
     if use_dist:
         tt = torch.tensor([gpu_ms_step, wall_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         gpu_ms_step, wall_step = float(tt[0]), float(tt[1])
+        nranks = dist.get_world_size()
     n_gpus = world if use_dist else 1
 
     # quality of what was computed (not part of the metric): finest level vs ground truth
     planes, costs = result
     gt = scene.depths_gt[ids[0]]
+    if gt.shape != planes.shape[:2]:
+        import cv2
+        gt = cv2.resize(gt, (planes.shape[1], planes.shape[0]), interpolation=cv2.INTER_NEAREST)
     within = float((np.abs(planes[..., 3] - gt) / gt <= 0.01)[8:-8, 8:-8].mean())
 
     if rank == 0:
         peaks = load_peaks()
         Hf, Wf = levels[-1].images[0].shape
-        alg = algorithmic_samples_per_pass(Wf, Hf, N_SRC)
         pass_ms = {k: float(np.mean(v)) for k, v in tot.pass_ms.items()}
-        photometric_ms = pass_ms.get("photometric")
         line = {
-            "metric": METRIC, "value": n_gpus / (gpu_ms_step / 1e3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+            "metric": cfg["metric"], "value": n_gpus / (gpu_ms_step / 1e3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": gpu_ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 3200x2130 reference view, 10 source views, 3 pyramid levels x (photometric + planar prior + "
-                                   "2 x geometric consistency), one reference view per step per GPU",
-                       "levels": [list(l.images[0].shape[::-1]) for l in levels], "n_src": N_SRC,
-                       "l2": "working set per pass (planes 109 MB + 11 x 27 MB images) exceeds the 126 MB L2",
+            "config": {"workload": cfg["workload"],
+                       "levels": [list(l.images[0].shape[::-1]) for l in levels], "n_src": n_src,
+                       "l2": "working set per pass (planes + source images of the finest level, > 300 MB) exceeds the 126 MB L2",
                        "timing": "value: sum of CUDA-event kernel times; e2e: wall clock of the host-buffer API calls",
                        "neighbour_depths": "other ranks' maps via NCCL all-gather where available, else rendered stand-ins",
-                       "cpu_prior_stage": "run once in warm-up, reused (out of scope, timed separately)"},
+                       "cpu_prior_stage": "run once in warm-up, reused (out of scope, timed separately); e2e_driver includes it",
+                       "nccl_nranks": nranks},
             "clocks": clocks,
             "e2e": {"value": n_gpus / wall_step, "unit": UNIT, "h2d_bytes_per_step": (tot.h2d_bytes + exch.h2d) // a.steps,
                     "d2h_bytes_per_step": tot.d2h_bytes // a.steps, "ms_per_step": wall_step * 1e3},
@@ -366,38 +576,55 @@ def main():
             "depth_within_1pct_of_ground_truth": within,
             "nccl_allgather": {"ms_per_step": exch.ms / a.steps, "bytes_per_step": exch.bytes // a.steps},
         }
-        if photometric_ms:
-            ach = alg / (photometric_ms * 1e-3) / 1e9
-            traffic = None
-            tp = ROOT / "profiles" / "pass_traffic.json"
-            if tp.exists():
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch_full_res")
-            line["roofline"] = {
-                "bound": "tex", "kernel": "k_pass (photometric, finest level)", "achieved": ach, "peak": peaks["tex_gfetch_s"],
-                "unit": "Gsample/s", "frac": ach / peaks["tex_gfetch_s"], "traffic": traffic,
-                "algorithmic_samples_per_launch": alg,
-                "note": "the pass is texture/FP32 bound, not HBM bound (SURVEY.md 8(d)): achieved = algorithmic NCC samples "
-                        "(14 hypotheses x 10 views x 36 taps x pixels/2) / mean launch time; peak = measured R32F bilinear fetch "
-                        "rate of this pool's B200 (profiles/tex_peak_b200.json)",
-                "hbm": {"algorithmic_bytes_per_launch": 190 * (Wf * Hf // 2), "achieved_gbs": 190 * (Wf * Hf // 2) / (photometric_ms * 1e-3) / 1e9,
-                        "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"]},
-            }
+        rl = roofline_of(cfg, Wf, Hf, pass_ms, peaks)
+        if rl:
+            line["roofline"] = rl
         if a.impl == "reference":
             line["impl"] = "reference"
+            line["config"]["timing"] = ("value: CUDA events around the reference's RunPatchMatch (kernels + its device-wide syncs + its "
+                                        "device->host copy of the result, ACMMP.cu:1506-1556) + the reference's own CUDA-event figure of "
+                                        "JBU::CudaRun; e2e: wall clock of one ACMMP object per stage with .dmb hand-over, like main.cpp")
+            if a.config == "C3":
+                line["config"]["sample"] = "one reference view of the scene per step (the reference is single-GPU and sequential over views)"
             line["cpu_baseline"] = {"value": line["value"], "unit": UNIT, "cores": 0, "kind": "reference",
                                     "sample": "the reference's own CUDA build (sm_100) of the same step on this B200: the "
                                               "reference has no CPU PatchMatch path (north_star)"}
             line["e2e"]["h2d_bytes_per_step"] = 0
             line["e2e"]["d2h_bytes_per_step"] = 0
-        elif not a.no_cpu_baseline:
-            try:
-                line["cpu_baseline"] = cpu_baseline_port(levels)
-            except Exception as e:      # the checker is optional for the number, never for the product
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+        else:
+            if not a.no_cpu_baseline:
+                try:
+                    line["cpu_baseline"] = cpu_baseline_port(levels, n_src)
+                except Exception as e:      # the checker is optional for the number, never for the product
+                    line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+            if cfg["model"] == "sphere":
+                # the same photometric stage at the finest level with EVERY window tap sampled (acmmp_set_sphere_tap_pruning 0):
+                # the default skips taps whose bilateral weight is below 2^-24 of the window's weight sum
+                try:
+                    ctx.set_sphere_tap_pruning(0.0)
+                    ctx.reset_modes()
+                    ctx.set_views(levels[-1].images, levels[-1].cams)
+                    ctx.run_patch_match(download=False)
+                    tm = ctx.timings()
+                    unpruned = tm["pass_sum_ms"] / max(tm["n_pass"], 1)
+                    ctx.set_sphere_tap_pruning(2.0 ** -24)
+                    line["sphere_tap_pruning"] = {
+                        "relative_weight_threshold": 2.0 ** -24, "photometric_pass_ms_all_taps": unpruned,
+                        "photometric_pass_ms_default": pass_ms.get("photometric"),
+                        "note": "default: taps below the threshold are not sampled (within the reference's own one-ulp sensitivity, "
+                                "tests/test_gpu_parity.py::test_sphere_tap_pruning_*); roofline.achieved counts ALGORITHMIC samples, so "
+                                "it can exceed the all-taps roofline; executed samples: roofline.executed_samples_per_launch"}
+                except Exception as e:
+                    line["sphere_tap_pruning"] = {"error": str(e)[:200]}
+            if not a.no_driver_leg and n_gpus == 1 and a.config == "C2":
+                try:
+                    ctx.close()
+                    line["e2e_driver"] = driver_leg(cfg, scene, ids, local_rank)
+                except Exception as e:
+                    line["e2e_driver"] = {"error": str(e)[:300]}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if use_dist:
-        dist.barrier()
-        dist.destroy_process_group()
+        if use_dist:
+            print(f"[bench] NCCL communicator nranks={nranks}", file=sys.stderr)
     return 0
 
 

@@ -173,6 +173,15 @@ int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int
  * explicit: state(pixel) = curand_init(seed, subsequence = y, offset = x). */
 int acmmp_set_seed(acmmp_ctx *ctx, uint64_t seed);
 
+/* SPHERE camera model only.  The fork's angular bilateral weight (ACMMP.cu:436-442, :479-486) shrinks with the image
+ * height (sigma_eff = 5 pi / H): at 3200x1600 the four nearest window taps weigh 5.6e-7, the next ring 1e-14, the corners
+ * 5e-32 -- most of the 36 samples ComputeBilateralNCC (ACMMP.cu:450-495) takes per (hypothesis, view) add terms far below
+ * the float32 resolution of its sums.  Tap steps (2x2 blocks of taps) whose weights are all below
+ * relative_weight x (sum of the 36 weights) are not sampled.  Default 2^-24; 0 samples everything (bit-identical to the
+ * unpruned evaluation).  The reference-side sums and the `sum_bw < 1e-6` exit (ACMMP.cu:497) always use all 36 taps.
+ * Measured effect on the cost: see tests/test_gpu_parity.py::test_sphere_tap_pruning_*. */
+int acmmp_set_sphere_tap_pruning(acmmp_ctx *ctx, float relative_weight);
+
 /* 0: plane_now is the current plane unless a neighbour is accepted (what the source intends);
  * 1 (default): what the reference BINARY does -- `float4 plane_hypotheses_now` is uninitialised
  * (ACMMP.cu:1301) and nvcc 12.9 keeps the best neighbour's plane in it whenever that neighbour
@@ -259,6 +268,42 @@ int acmmp_last_timings(acmmp_ctx *ctx, float what[8]);
 
 /* How many kernels of this library were launched on the context since creation. */
 int64_t acmmp_launch_count(const acmmp_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depth-map fusion.  Replaces the device part of RunFusionCuda
+ * (ACMMP.cu:1817-2105): SimpleFusionKernel (:1664-1814) per reference view, the valid points
+ * compacted on the device in pixel order (the reference copies a 36-byte PointList + a flag for every
+ * pixel to the host and filters there, :2056-2076).
+ * --------------------------------------------------------------------------------------------- */
+/* reference `struct PointList`, main.h:71-75: world point, world normal, colour (written as b, g, r by the PLY writer) */
+typedef struct {
+    float coord[3];
+    float normal[3];
+    float color[3];
+} acmmp_point;
+
+typedef struct acmmp_fusion acmmp_fusion;
+
+int acmmp_fusion_create(int device, int n_views, acmmp_fusion **out);
+void acmmp_fusion_destroy(acmmp_fusion *f);
+const char *acmmp_fusion_last_error(const acmmp_fusion *f);
+/* One view of the scene: camera ALREADY scaled to the depth map's size (RescaleImageAndCamera,
+ * ACMMP.cpp:213-245), depth (w*h, depths_geom.dmb / depths.dmb), world-frame normals (w*h*3, normals.dmb)
+ * and grey levels 0..255 (w*h) at that size.  Host pointers; copied to the device. */
+int acmmp_fusion_set_view(acmmp_fusion *f, int index, const acmmp_camera *cam, int w, int h, const float *depth,
+                          const float *normals3, const float *gray);
+/* The same with DEVICE pointers that stay valid until the object is destroyed (resident chain: the depth /
+ * normal maps a PatchMatch context holds, acmmp_device_buffers): normals4 = float4 per pixel. */
+int acmmp_fusion_set_view_device(acmmp_fusion *f, int index, const acmmp_camera *cam, int w, int h, const float *depth_dev,
+                                 const void *normals4_dev, const float *gray_dev);
+/* Fuse reference view `ref` against the views src[0 .. n_src) (indices into the view table, -1 = not
+ * available; at most 32 like FusionProblem, ACMMP.cu:1656-1661).  points: room for `capacity` points (host);
+ * *n_points: how many the view produced (ACMMP_E_ARG when capacity was too small: call again).
+ * kernel_ms (optional): CUDA-event time of the three kernels. */
+int acmmp_fusion_run(acmmp_fusion *f, int ref, int n_src, const int32_t *src, acmmp_point *points, int capacity,
+                     int *n_points, float *kernel_ms);
+/* which pixels of the reference view fused LAST produced a point: w*h bytes (host), row-major */
+int acmmp_fusion_last_flags(acmmp_fusion *f, int ref, unsigned char *flags);
 
 #ifdef __cplusplus
 }

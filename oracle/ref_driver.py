@@ -36,6 +36,8 @@ def lib():
         l.ref_launch_pass.restype = C.c_float
         l.ref_launch_finalize.restype = C.c_float
         l.ref_set_seed.argtypes = [C.c_uint64]
+        l.ref_fusion_create.restype = C.c_void_p
+        l.ref_fusion_run.restype = C.c_float
         _lib = l
     return _lib
 
@@ -281,3 +283,39 @@ def run_jbu(image, coarse_depth, ref_image_id=0, with_ms=False):
     if k >= 0:
         ms = float(q.text[k + len(key):].split()[0]) * 1e3
     return out, ms
+
+
+class RefFusion:
+    """The reference's SimpleFusionKernel (ACMMP.cu:1664-1814) behind the texture set-up of RunFusionCuda (see ref_harness.cu);
+    run(ref, src) returns the points of one reference view filtered on the host in pixel order like ACMMP.cu:2069-2076."""
+
+    def __init__(self, cams, depths, normals, grays):
+        from acmmp_b200 import Camera
+        self._l = lib()
+        n = len(cams)
+        self.d = [_f32(x) for x in depths]
+        self.nm = [_f32(x) for x in normals]
+        self.g = [_f32(x) for x in grays]
+        self.sizes = [x.shape for x in self.d]
+        ws = (C.c_int * n)(*[s[1] for s in self.sizes])
+        hs = (C.c_int * n)(*[s[0] for s in self.sizes])
+        FP = C.POINTER(C.c_float)
+        self._h = C.c_void_p(self._l.ref_fusion_create(C.c_int(n), (Camera * n)(*cams), ws, hs, (FP * n)(*[_fp(x) for x in self.d]),
+                                                       (FP * n)(*[_fp(x) for x in self.nm]), (FP * n)(*[_fp(x) for x in self.g])))
+        self.kernel_ms = 0.0
+
+    def run(self, ref, src_indices):
+        h, w = self.sizes[ref]
+        pts = np.empty((h * w, 9), np.float32)
+        flags = np.empty(h * w, np.int32)
+        src = (C.c_int * len(src_indices))(*[int(s) for s in src_indices])
+        self.kernel_ms = float(self._l.ref_fusion_run(self._h, C.c_int(ref), C.c_int(len(src_indices)), src, _fp(pts),
+                                                      flags.ctypes.data_as(C.POINTER(C.c_int))))
+        if self._l.ref_last_error() != 0:
+            raise RuntimeError("reference fusion harness reported a CUDA error")
+        return pts[flags != 0], flags.reshape(h, w)
+
+    def close(self):
+        if self._h:
+            self._l.ref_fusion_destroy(self._h)
+            self._h = None

@@ -520,4 +520,126 @@ void ref_run_jbu(const float *image, int width, int height, const float *coarse_
     ref_check(cudaGetLastError(), "run_jbu");
 }
 
+
+// ---------------------------------------------------------------------------------
+// Fusion oracle: the reference's SimpleFusionKernel (ACMMP.cu:1664-1814), unmodified, fed through textures set up the way
+// RunFusionCuda sets them up (ACMMP.cu:1890-1973: float depth and float4 normal arrays with POINT filtering, float4 RGBA /
+// 255 colour arrays with LINEAR filtering, address modes Wrap / Clamp, unnormalised coordinates), launched with its grid
+// (:2040-2053).  RunFusionCuda itself needs cv::imread / cvtColor / resize and is bypassed: views arrive as arrays already at
+// the depth maps' size with cameras scaled accordingly, i.e. what RescaleImageAndCamera (ACMMP.cpp:213-245) leaves.
+// Output: the dense PointList + flag arrays the reference copies to the host (:2056-2066).
+// ---------------------------------------------------------------------------------
+struct RefFusion {
+    int n;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> depth_tex, normal_tex, image_tex;
+    std::vector<Camera> cams;
+    cudaTextureObject_t *depth_dev, *normal_dev, *image_dev;
+    Camera *cams_dev;
+};
+
+static cudaTextureObject_t ref_make_tex(RefFusion *f, const void *host, int w, int h, bool four, bool linear)
+{
+    cudaChannelFormatDesc desc = four ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
+    cudaArray_t arr = nullptr;
+    ref_check(cudaMallocArray(&arr, &desc, w, h), "fusion cudaMallocArray");
+    const size_t pitch = (size_t)w * (four ? sizeof(float4) : sizeof(float));
+    ref_check(cudaMemcpy2DToArray(arr, 0, 0, host, pitch, pitch, h, cudaMemcpyHostToDevice), "fusion cudaMemcpy2DToArray");
+    f->arrays.push_back(arr);
+    cudaResourceDesc res = {};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaTextureDesc tex = {};
+    tex.addressMode[0] = cudaAddressModeWrap;
+    tex.addressMode[1] = cudaAddressModeClamp;
+    tex.filterMode = linear ? cudaFilterModeLinear : cudaFilterModePoint;
+    tex.readMode = cudaReadModeElementType;
+    tex.normalizedCoords = false;
+    cudaTextureObject_t t = 0;
+    ref_check(cudaCreateTextureObject(&t, &res, &tex, NULL), "fusion cudaCreateTextureObject");
+    return t;
+}
+
+// depths[i]: w*h floats; normals3[i]: w*h*3; gray[i]: w*h grey levels 0..255 (the colour texture gets (g, g, g, 1) / 255)
+void *ref_fusion_create(int n, const Camera *cams, const int *ws, const int *hs, const float *const *depths,
+                        const float *const *normals3, const float *const *gray)
+{
+    RefFusion *f = new RefFusion();
+    f->n = n;
+    for (int i = 0; i < n; ++i) {
+        const size_t npx = (size_t)ws[i] * hs[i];
+        Camera c = cams[i];
+        c.width = ws[i];
+        c.height = hs[i];
+        f->cams.push_back(c);
+        f->depth_tex.push_back(ref_make_tex(f, depths[i], ws[i], hs[i], false, false));
+        std::vector<float> n4(4 * npx), rgba(4 * npx);
+        for (size_t k = 0; k < npx; ++k) {
+            n4[4 * k] = normals3[i][3 * k]; n4[4 * k + 1] = normals3[i][3 * k + 1]; n4[4 * k + 2] = normals3[i][3 * k + 2]; n4[4 * k + 3] = 1.0f;
+            const float g = (float)(gray[i][k] * (1.0 / 255.0));      // convertTo(CV_32FC4, 1.0 / 255.0), ACMMP.cu:1951
+            rgba[4 * k] = g; rgba[4 * k + 1] = g; rgba[4 * k + 2] = g; rgba[4 * k + 3] = 1.0f;
+        }
+        f->normal_tex.push_back(ref_make_tex(f, n4.data(), ws[i], hs[i], true, false));
+        f->image_tex.push_back(ref_make_tex(f, rgba.data(), ws[i], hs[i], true, true));
+    }
+    cudaMalloc(&f->depth_dev, n * sizeof(cudaTextureObject_t));
+    cudaMalloc(&f->normal_dev, n * sizeof(cudaTextureObject_t));
+    cudaMalloc(&f->image_dev, n * sizeof(cudaTextureObject_t));
+    cudaMalloc(&f->cams_dev, n * sizeof(Camera));
+    cudaMemcpy(f->depth_dev, f->depth_tex.data(), n * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice);
+    cudaMemcpy(f->normal_dev, f->normal_tex.data(), n * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice);
+    cudaMemcpy(f->image_dev, f->image_tex.data(), n * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice);
+    ref_check(cudaMemcpy(f->cams_dev, f->cams.data(), n * sizeof(Camera), cudaMemcpyHostToDevice), "fusion cameras");
+    return f;
+}
+
+// points: w*h PointList (9 floats each), flags: w*h ints -- the arrays of ACMMP.cu:2056-2066; returns kernel ms
+float ref_fusion_run(void *fv, int ref, int n_src, const int *src_indices, float *points, int *flags)
+{
+    RefFusion *f = (RefFusion *)fv;
+    const int width = f->cams[ref].width, height = f->cams[ref].height, total = width * height;
+    FusionProblem prob;
+    std::memset(&prob, 0, sizeof(prob));
+    prob.ref_image_id = ref;
+    prob.num_src_images = std::min(n_src, 32);
+    for (int j = 0; j < prob.num_src_images; ++j) {
+        prob.src_image_ids[j] = src_indices[j];
+        prob.src_image_indices[j] = src_indices[j];
+    }
+    PointList *out_dev = nullptr;
+    int *flags_dev = nullptr;
+    cudaMalloc(&out_dev, total * sizeof(PointList));
+    cudaMalloc(&flags_dev, total * sizeof(int));
+    cudaMemset(flags_dev, 0, total * sizeof(int));
+    dim3 block_size(16, 16);
+    dim3 grid_size((width + block_size.x - 1) / block_size.x, (height + block_size.y - 1) / block_size.y);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    SimpleFusionKernel<<<grid_size, block_size>>>(f->depth_dev, f->normal_dev, f->image_dev, f->cams_dev, ref, prob, out_dev, flags_dev, width, height);
+    cudaEventRecord(e1);
+    ref_check(cudaDeviceSynchronize(), "SimpleFusionKernel");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaMemcpy(points, out_dev, total * sizeof(PointList), cudaMemcpyDeviceToHost);
+    ref_check(cudaMemcpy(flags, flags_dev, total * sizeof(int), cudaMemcpyDeviceToHost), "fusion copy back");
+    cudaFree(out_dev);
+    cudaFree(flags_dev);
+    return ms;
+}
+
+void ref_fusion_destroy(void *fv)
+{
+    RefFusion *f = (RefFusion *)fv;
+    for (auto t : f->depth_tex) cudaDestroyTextureObject(t);
+    for (auto t : f->normal_tex) cudaDestroyTextureObject(t);
+    for (auto t : f->image_tex) cudaDestroyTextureObject(t);
+    for (auto a : f->arrays) cudaFreeArray(a);
+    cudaFree(f->depth_dev); cudaFree(f->normal_dev); cudaFree(f->image_dev); cudaFree(f->cams_dev);
+    delete f;
+}
+
 } // extern "C"

@@ -196,3 +196,27 @@ def test_cpu_planar_prior_stage_agrees_with_the_numpy_twin(host, model):
     theirs = p_ref[m_ref[both].astype(np.int64) - 1]
     same = np.all(np.abs(mine - theirs) <= 1e-4 + 1e-4 * np.abs(theirs), axis=1)
     assert same.mean() > 0.55, same.mean()
+
+
+def test_ply_writer_writes_the_references_binary_layout(tmp_path):
+    """StoreColorPlyFileBinaryPointCloud (reference ACMMP.cpp:481-534): header lines, 27-byte records (6 float + 3 uchar),
+    colour stored as (b, g, r) in PointList and written red-green-blue, non-finite coordinates zeroed."""
+    import ctypes as C
+    import struct
+    lib = C.CDLL(str(ROOT / "acmmp-spherical_b200" / "lib" / "libacmmp_host.so"))
+    pts = np.array([[1.0, 2.0, 3.0, 0.0, 0.0, 1.0, 10.7, 20.2, 30.9],
+                    [np.inf, 5.0, 6.0, 0.6, 0.0, 0.8, 255.0, 128.0, 0.0]], np.float32)
+    path = tmp_path / "cloud.ply"
+    assert lib.acmmp_host_write_ply(str(path).encode(), pts.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(len(pts))) == 0
+    raw = path.read_bytes()
+    head, body = raw.split(b"end_header\n", 1)
+    lines = head.decode().splitlines()
+    assert lines[:3] == ["ply", "format binary_little_endian 1.0", "element vertex 2"]
+    assert lines[3:] == ["property float x", "property float y", "property float z", "property float nx", "property float ny",
+                         "property float nz", "property uchar red", "property uchar green", "property uchar blue"]
+    assert len(body) == 2 * 27
+    a = struct.unpack("<6f3B", body[:27])
+    b = struct.unpack("<6f3B", body[27:])
+    assert a == (1.0, 2.0, 3.0, 0.0, 0.0, 1.0, 30, 20, 10)                    # truncation, r = color.z, b = color.x
+    assert b[:3] == (0.0, 0.0, 0.0) and b[6:] == (0, 128, 255)
+    assert abs(b[3] - 0.6) < 1e-6 and abs(b[5] - 0.8) < 1e-6

@@ -46,11 +46,31 @@ def test_cpp_driver_runs_the_reference_schedule_on_a_dense_folder(tmp_path):
         ok = np.abs(depth - gt) / gt <= 0.01
         res[f"view{v}_within_1pct_of_gt"] = float(ok[8:-8, 8:-8].mean())
         res[f"view{v}_unit_normals"] = float((np.abs(np.linalg.norm(normals, axis=-1) - 1) < 1e-3).mean())
+    # fusion (RunFusionCuda, main.cpp:478-479): ACMMP/ACMM_model_cuda_5.ply, 27 bytes per point after the header
+    ply = (tmp_path / "ACMMP" / "ACMM_model_cuda_5.ply").read_bytes()
+    head, body = ply.split(b"end_header\n", 1)
+    n_points = int([l for l in head.decode().splitlines() if l.startswith("element vertex")][0].split()[-1])
+    assert n_points == summary["fusion_points"] and len(body) == 27 * n_points
+    pts = np.frombuffer(body, np.dtype([("xyz", "<f4", 3), ("n", "<f4", 3), ("rgb", "u1", 3)]))
+    res["fusion_points"] = n_points
+    res["fusion_points_per_pixel"] = n_points / (4.0 * scene.depths_gt[0].size)
+    res["fusion_unit_normals"] = float((np.abs(np.linalg.norm(pts["n"], axis=-1) - 1) < 1e-3).mean())
+    # every fused point projects into view 0 at a depth that agrees with that view's ground-truth depth
+    R, t, K = scene.Rs[0], scene.ts[0], scene.Ks[0]
+    Xc = pts["xyz"].astype(np.float64) @ R.T + t
+    uv = (Xc @ K.T)[:, :2] / Xc[:, 2:3]
+    ui, vi = np.rint(uv[:, 0]).astype(int), np.rint(uv[:, 1]).astype(int)
+    gt0 = scene.depths_gt[0]
+    inside = (ui >= 8) & (ui < gt0.shape[1] - 8) & (vi >= 8) & (vi < gt0.shape[0] - 8) & (Xc[:, 2] > 0)
+    rel = np.abs(Xc[inside, 2] - gt0[vi[inside], ui[inside]]) / gt0[vi[inside], ui[inside]]
+    res["fusion_points_within_2pct_of_gt_surface"] = float((rel <= 0.02).mean())
     res.update(summary)
     util.dump("cpp_driver", res)
     for v in range(4):
         assert res[f"view{v}_within_1pct_of_gt"] > 0.85, res
         assert res[f"view{v}_unit_normals"] > 0.99, res
+    assert res["fusion_points_per_pixel"] > 0.3 and res["fusion_unit_normals"] > 0.99, res
+    assert res["fusion_points_within_2pct_of_gt_surface"] > 0.8, res      # occluded points excepted
 
 
 @pytest.mark.gpu
@@ -136,4 +156,56 @@ def test_cpp_driver_on_an_equirectangular_dense_folder(tmp_path):
         for d in ("depths_geom.dmb", "normals.dmb", "costs.dmb"):
             assert res[f"resident_view{v}_{d}_identical"], res
         assert res[f"gpu_prior_view{v}_within_1pct_of_files"] > 0.99, res
+        assert res[f"view{v}_within_1pct_of_gt"] > 0.85, res
+
+
+def _device_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("levels", [1, 2])
+def test_cpp_driver_multi_gpu_shards_views_and_exchanges_depth_maps(tmp_path, levels):
+    """`--gpus 2`: the reference views dealt round-robin to two devices, one host thread per device, the
+    neighbours' depth maps pulled over NVLink at the two exchange points of a level.  Photometric and prior stages are
+    per-view work: on a one-level scene a sharded run holds the SAME maps after them as the one-device run (depths.dmb
+    bit-identical).  The geometric rounds read other views' maps: round 1 is Gauss-Seidel inside a device and Jacobi across
+    devices, so the final maps (and everything a finer level builds on them) agree within the full-map tolerance, not bit
+    for bit.  Needs two GPUs (skipped otherwise)."""
+    import shutil
+    from acmmp_b200 import synth
+    if _device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    w, h, f = (900, 680, 780.0) if levels == 1 else (1100, 820, 950.0)
+    scene = synth.make_pinhole_scene(n_views=5, width=w, height=h, focal=f, seed=5)
+    one = tmp_path / "one"
+    one.mkdir()
+    synth.write_dense_folder(scene, str(one), pgm=True)
+    two = tmp_path / "two"
+    shutil.copytree(one, two)
+    out = {}
+    for name, folder, gpus in (("one", one, "1"), ("two", two, "2")):
+        r = subprocess.run([str(DRIVER), str(folder), "--seed", "11", "--resident", "1", "--gpu-prior", "1", "--gpus", gpus],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["one"]["gpus"] == 1 and out["two"]["gpus"] == 2, out
+    res = dict(out)
+    for v in range(5):
+        a = {d: _read_dmb(one / "ACMMP" / ("2333_%08d" % v) / d) for d in ("depths.dmb", "depths_geom.dmb", "normals.dmb")}
+        b = {d: _read_dmb(two / "ACMMP" / ("2333_%08d" % v) / d) for d in ("depths.dmb", "depths_geom.dmb", "normals.dmb")}
+        res[f"view{v}_prior_stage_depths_identical"] = bool(np.array_equal(a["depths.dmb"].view(np.uint32), b["depths.dmb"].view(np.uint32)))
+        rel = np.abs(a["depths_geom.dmb"] - b["depths_geom.dmb"]) / np.maximum(np.abs(a["depths_geom.dmb"]), 1e-9)
+        res[f"view{v}_final_depth_within_1pct"] = float((rel <= 0.01)[8:-8, 8:-8].mean())
+        gt = scene.depths_gt[v]
+        res[f"view{v}_within_1pct_of_gt"] = float((np.abs(b["depths_geom.dmb"] - gt) / gt <= 0.01)[8:-8, 8:-8].mean())
+    util.dump(f"cpp_driver_multi_gpu_{levels}_levels", res)
+    for v in range(5):
+        if levels == 1:
+            assert res[f"view{v}_prior_stage_depths_identical"], res
+        assert res[f"view{v}_final_depth_within_1pct"] > 0.97, res
         assert res[f"view{v}_within_1pct_of_gt"] > 0.85, res

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--model", default="pinhole")
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--tap-prune", type=float, default=None, help="SPHERE: acmmp_set_sphere_tap_pruning threshold (0 = sample every tap)")
     a = ap.parse_args()
     from acmmp_b200 import Context, synth
     t0 = time.time()
@@ -36,6 +37,8 @@ def main():
     ctx = Context(0)
     ctx.set_views(imgs, cams)
     ctx.set_seed(1234)
+    if a.tap_prune is not None:
+        ctx.set_sphere_tap_pruning(a.tap_prune)
     for rep in range(2):
         t0 = time.time()
         ctx.run_patch_match()
