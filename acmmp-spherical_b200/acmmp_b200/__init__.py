@@ -78,8 +78,8 @@ _EXPORTS = [
     "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
     "acmmp_get_params", "acmmp_reset_modes", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
-    "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_support_points",
-    "acmmp_planar_prior_from_triangles", "acmmp_set_seed",
+    "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_next_level_device", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_support_points",
+    "acmmp_planar_prior_from_triangles", "acmmp_download_prior", "acmmp_set_seed",
     "acmmp_set_plane_now_semantics", "acmmp_set_sphere_tap_pruning", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
     "acmmp_finalize", "acmmp_synchronize", "acmmp_get_result", "acmmp_width", "acmmp_height",
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_export_depth_device_sync", "acmmp_download_state", "acmmp_upload_state",
@@ -268,6 +268,13 @@ class Context:
         t = np.ascontiguousarray(tri_xy, np.int32).reshape(-1, 6)
         self._ck(self._l.acmmp_planar_prior_from_triangles(self._h, t.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(t.shape[0])),
                  "acmmp_planar_prior_from_triangles")
+
+    def download_prior(self):
+        """(prior planes [H, W, 4], triangle ids [H, W] uint32) as the device holds them."""
+        pp = np.empty((self.H, self.W, 4), np.float32)
+        mk = np.empty((self.H, self.W), np.uint32)
+        self._ck(self._l.acmmp_download_prior(self._h, _fp(pp), mk.ctypes.data_as(C.POINTER(C.c_uint32))), "acmmp_download_prior")
+        return pp, mk
 
     def set_seed(self, seed):
         self._ck(self._l.acmmp_set_seed(self._h, C.c_uint64(seed)), "acmmp_set_seed")

@@ -76,6 +76,10 @@ class GpuWorker:
         self.ctx.set_plane_now_semantics(as_compiled)
         self.first = True
 
+    def restart(self):
+        """The same view again from the coarsest level (benchmark steps): buffers and pools are kept."""
+        self.first = True
+
     def begin_level(self, images, cams):
         if self.first:
             self.ctx.reset_modes()
@@ -130,19 +134,19 @@ def delaunay_triangles_inside(points_xy, width, height):
     if _host_lib is None:
         from . import PKG_DIR
         _host_lib = C.CDLL(str(PKG_DIR / "lib" / "libacmmp_host.so"))
-        _host_lib.acmmp_host_delaunay.restype = C.c_int
+        _host_lib.acmmp_host_delaunay_rect.restype = C.c_int
     pts = np.ascontiguousarray(points_xy, np.int32)
     n = pts.shape[0]
     if n < 3:
         return np.zeros((0, 3, 2), np.int32)
     cap = 2 * n + 16
     idx = np.zeros((cap, 3), np.int32)
-    nt = _host_lib.acmmp_host_delaunay(pts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(n), idx.ctypes.data_as(C.POINTER(C.c_int32)),
-                                       C.c_int(cap))
+    nt = _host_lib.acmmp_host_delaunay_rect(pts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(n), C.c_int(width), C.c_int(height),
+                                            idx.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(cap))
     if nt > cap:
         idx = np.zeros((nt, 3), np.int32)
-        nt = _host_lib.acmmp_host_delaunay(pts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(n), idx.ctypes.data_as(C.POINTER(C.c_int32)),
-                                           C.c_int(nt))
+        nt = _host_lib.acmmp_host_delaunay_rect(pts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(n), C.c_int(width), C.c_int(height),
+                                                idx.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(nt))
     tri = pts[idx[:nt]]                                  # [nt, 3, 2]
     inside = ((tri[..., 0] >= 0) & (tri[..., 0] < width) & (tri[..., 1] >= 0) & (tri[..., 1] < height)).all(axis=1)
     return np.ascontiguousarray(tri[inside])
@@ -176,20 +180,36 @@ class DeviceTable:
 
 
 def run_scene(levels: SceneLevels, pairs, rank, world, make_worker, alloc, all_gather, finest_only_download=True,
-              on_result=None, overlap_delaunay=True):
+              on_result=None, overlap_delaunay=True, workers=None, tables=None):
     """Process every view this rank owns through every level and stage.
       pairs       : [(ref view, [source views])] for every view of the scene (view id == index)
       make_worker : () -> worker object (GpuWorker, or a CPU stand-in in the tests)
       alloc       : shape -> (keep-alive, device pointer) of a float32 device array
       all_gather  : (table: DeviceTable) -> device ms; fills table.all from every rank's table.mine
       on_result   : callable(view, planes, costs) for the final result of each owned view (finest level, last stage)
+      workers     : optional dict view -> worker kept from an earlier run of the same scene (their contexts keep their buffer
+                    pools: nothing is allocated again); the dict is filled when empty and the workers are then left open
+      tables      : optional list kept the same way for the two device tables
     Returns SceneTimes."""
     n_views = len(pairs)
     owned = shard.views_of(rank, n_views, world)
     rounds = shard.rounds(n_views, world)
     t = SceneTimes()
-    workers = {v: make_worker() for v in owned}
-    dtab, gtab = DeviceTable(world, rounds, alloc), DeviceTable(world, rounds, alloc)
+    keep_workers = workers is not None
+    if workers is None:
+        workers = {}
+    for v in owned:
+        if v not in workers:
+            workers[v] = make_worker()
+        elif hasattr(workers[v], "restart"):
+            workers[v].restart()
+    launches0 = {v: workers[v].launches() for v in owned}
+    if tables is not None and len(tables) == 2:
+        dtab, gtab = tables
+    else:
+        dtab, gtab = DeviceTable(world, rounds, alloc), DeviceTable(world, rounds, alloc)
+        if tables is not None:
+            tables[:] = [dtab, gtab]
     # the host part of a view's prior stage (the triangulation: 0.3 s for the 273 k support points of a 3200x2130 view) runs on
     # worker threads while this thread -- which issues ALL device work, in a fixed order -- goes on with the photometric stages
     # of the next views; a view is finished (prior upload, prior-stage PatchMatch, depth export) up to DEPTH views later
@@ -268,8 +288,9 @@ def run_scene(levels: SceneLevels, pairs, rank, world, make_worker, alloc, all_g
                 t.exchange_bytes += 4 * H * W * rounds * (world - 1)
     for v in owned:
         workers[v].sync()
-        t.launches += workers[v].launches()
-        workers[v].close()
+        t.launches += workers[v].launches() - launches0[v]
+        if not keep_workers:
+            workers[v].close()
     if pool:
         pool.shutdown()
     return t

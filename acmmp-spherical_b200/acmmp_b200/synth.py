@@ -133,7 +133,9 @@ def make_pinhole_scene(n_views=5, width=640, height=480, focal=500.0, seed=1, n_
     job only needs its own reference view and that view's sources."""
     rng = np.random.default_rng(seed)
     texel = 0.7 * depth0 / focal
-    halfw = 0.5 * width / focal * depth0 * 1.9 + baseline_ratio * depth0 * n_views
+    # arc: the background grows with the camera spread; ring: the cameras stay inside a fixed circle (a 64-view arc would
+    # need a background texture wider than cv2.remap's 32767-texel limit)
+    halfw = 0.5 * width / focal * depth0 * 1.9 + (0.0 if ring else baseline_ratio * depth0 * n_views)
     halfh = 0.5 * height / focal * depth0 * 1.9
     quads = [_make_quad(rng, (-halfw, -halfh, depth0 * 1.15), (1, 0, 0), (0, 1, 0), 2 * halfw, 2 * halfh, texel)]
     fw, fh = 0.45 * halfw, 0.5 * halfh

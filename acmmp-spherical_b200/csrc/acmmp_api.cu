@@ -1211,6 +1211,18 @@ int acmmp_support_points(acmmp_ctx *ctx, int32_t *xy, int capacity, int *n)
     return ACMMP_OK;
 }
 
+int acmmp_download_prior(acmmp_ctx *ctx, float *prior_planes4, uint32_t *plane_masks)
+{
+    if (!ctx || !ctx->prior_planes || !ctx->plane_masks || !prior_planes4 || !plane_masks)
+        return fail(ctx, ACMMP_E_ARG, "acmmp_download_prior: no prior on this context");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    CK(cudaMemcpyAsync(prior_planes4, ctx->prior_planes, sizeof(float4) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(plane_masks, ctx->plane_masks, sizeof(uint32_t) * npx, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ACMMP_OK;
+}
+
 int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int n_tri)
 {
     if (!ctx || !ctx->planes || n_tri < 0 || (n_tri > 0 && !tri_xy))
@@ -1249,8 +1261,23 @@ int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int
     return ACMMP_OK;
 }
 
+static int next_level_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_device, const int32_t *widths,
+                             const int32_t *heights, const acmmp_camera *cams);
+
 int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const int32_t *widths, const int32_t *heights,
                      const acmmp_camera *cams)
+{
+    return next_level_common(ctx, n, images, false, widths, heights, cams);
+}
+
+int acmmp_next_level_device(acmmp_ctx *ctx, int n, const float *const *images_dev, const int32_t *widths, const int32_t *heights,
+                            const acmmp_camera *cams)
+{
+    return next_level_common(ctx, n, images_dev, true, widths, heights, cams);
+}
+
+static int next_level_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_device, const int32_t *widths,
+                             const int32_t *heights, const acmmp_camera *cams)
 {
     if (!ctx || !ctx->planes) return fail(ctx, ACMMP_E_ARG, "acmmp_next_level: no previous level on this context");
     CK(cudaSetDevice(ctx->device));
@@ -1264,7 +1291,7 @@ int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const in
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     acmmp_reset_modes(ctx);
-    int rc = set_views_common(ctx, n, images, false, widths, heights, cams);      // re-allocates at the new size
+    int rc = set_views_common(ctx, n, images, on_device, widths, heights, cams);      // re-allocates at the new size
     if (rc) { ctx->pool.dfree(coarse); ctx->pool.dfree(coarse_depth); return rc; }
     const int npx = ctx->W * ctx->H;
     const int Imagescale = std::max(ctx->H / sh, ctx->W / sw);

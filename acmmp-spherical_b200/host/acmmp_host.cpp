@@ -171,6 +171,27 @@ void ACMMP::SetViewsHost(const std::vector<cv::Mat_<float>> &images, const std::
     }
 }
 
+void ACMMP::SetViewsDevice(const std::vector<const float *> &images_dev, const std::vector<int> &widths, const std::vector<int> &heights,
+                           const std::vector<Camera> &cameras, bool next_level, const cv::Mat_<float> *ref_host)
+{
+    const int n = (int)images_dev.size();
+    images_.assign((size_t)n, cv::Mat_<float>());
+    if (ref_host) images_[0] = *ref_host;
+    cameras_ = cameras;
+    std::vector<int32_t> ws(widths.begin(), widths.end()), hs(heights.begin(), heights.end());
+    params_.depth_min = cameras_[0].depth_min * 0.6f;
+    params_.depth_max = cameras_[0].depth_max * 1.2f;
+    params_.num_images = n;
+    if (next_level) {
+        check(acmmp_next_level_device(ctx_, n, images_dev.data(), ws.data(), hs.data(), cameras_.data()), "SetViewsDevice (next level)");
+        params_.geom_consistency = params_.multi_geometry = params_.planar_prior = 0;
+        params_.max_iterations = 3;
+        params_.hierarchy = 1;
+    } else {
+        check(acmmp_set_views_device(ctx_, n, images_dev.data(), ws.data(), hs.data(), cameras_.data()), "SetViewsDevice");
+    }
+}
+
 void ACMMP::ResetModes()
 {
     check(acmmp_reset_modes(ctx_), "ResetModes");
@@ -354,10 +375,11 @@ void ACMMP::GetSupportPoints(std::vector<cv::Point> &support2DPoints)
 // reference ACMMP.cpp:932-954 (cv::Subdiv2D there)
 std::vector<Triangle> ACMMP::DelaunayTriangulation(const cv::Rect boundRC, const std::vector<cv::Point> &points)
 {
-    (void)boundRC;
     std::vector<Triangle> results;
     if (points.empty()) return results;
-    const std::vector<int> idx = DelaunayIndices(points);
+    // cv::Subdiv2D subdiv2d(boundRC) (ACMMP.cpp:938): the same enclosing triangle when the rectangle starts at the origin
+    const bool at_origin = boundRC.x == 0 && boundRC.y == 0;
+    const std::vector<int> idx = DelaunayIndices(points, at_origin ? boundRC.width : 0, at_origin ? boundRC.height : 0);
     results.reserve(idx.size() / 3);
     for (size_t i = 0; i + 2 < idx.size(); i += 3) results.push_back(Triangle(points[idx[i]], points[idx[i + 1]], points[idx[i + 2]]));
     return results;
@@ -437,7 +459,7 @@ void PlanarPriorCpu(const Camera &cam, const cv::Mat_<float> &depths, const floa
     mask_tri = cv::Mat_<float>::zeros(height, width);
     planeParams_tri.clear();
     if (support2DPoints.empty()) return;
-    const std::vector<int> idx = DelaunayIndices(support2DPoints);
+    const std::vector<int> idx = DelaunayIndices(support2DPoints, width, height);
     uint32_t tri_idx = 0;
     for (size_t t = 0; t + 2 < idx.size(); t += 3) {
         const Triangle triangle(support2DPoints[idx[t]], support2DPoints[idx[t + 1]], support2DPoints[idx[t + 2]]);

@@ -78,7 +78,7 @@ float3 Get3DPointonRefCam(const int x, const int y, const float depth, const Cam
 
 // Delaunay triangulation of integer points inside `bound` (stands in for cv::Subdiv2D, ACMMP.cpp:932-954):
 // exact integer predicates, incremental insertion with walking point location.  Returns vertex index triples.
-std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points);
+std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points, int rect_w = 0, int rect_h = 0);
 
 // ---- the CPU planar-prior stage as free functions (what the ACMMP methods below and the driver use) -----------
 // GetSupportPoints, ACMMP.cpp:904-930, on a W x H cost map
@@ -132,6 +132,11 @@ public:
     //   SetViewsHost(next_level = true) : move to the next finer level: JBU of the current result on the device,
     //                                     hierarchy inputs, SetHierarchyParams (acmmp_next_level)
     void SetViewsHost(const std::vector<cv::Mat_<float>> &images, const std::vector<Camera> &cameras, bool next_level);
+    // the same with the level images already on this object's device (dense float32 W x H each): a driver uploads every
+    // view's image once per level and device instead of once per object that uses it.  ref_host (optional) is what
+    // GetReferenceImage returns.
+    void SetViewsDevice(const std::vector<const float *> &images_dev, const std::vector<int> &widths, const std::vector<int> &heights,
+                        const std::vector<Camera> &cameras, bool next_level, const cv::Mat_<float> *ref_host = nullptr);
     void ResetModes();                                   // flags of a freshly constructed object, views kept
     // depth maps of the SOURCE views for the geometric term (device pointers); the reference view's own map is the
     // state on the device (acmmp_set_depth_maps_device with maps[0] == NULL)

@@ -330,7 +330,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         std::vector<char> need(num_images, 0);
         for (size_t i = 0; i < num_images; ++i)
             if (device_of(i) == d)
-                for (int id : problems[i].src_image_ids) need[index_of[id]] = 1;
+                for (int id : problems[i].src_image_ids) need[index_of.at(id)] = 1;
         for (size_t v = 0; v < num_images; ++v)
             if (need[v] && device_of(v) != d) remote[d].push_back(v);
     }
@@ -361,6 +361,18 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (cudaStreamSynchronize(0) != cudaSuccess) throw std::runtime_error("peer copies of the depth maps failed");
             t_exchange += now_s() - t0;
         };
+        std::vector<std::future<void>> writers;             // .dmb output of finished views
+        std::vector<DeviceMap> pool(num_images);            // level images on this device
+        std::vector<size_t> needed;                         // my views and their source views
+        {
+            std::vector<char> need(num_images, 0);
+            for (size_t i : mine) {
+                need[i] = 1;
+                for (int id : problems[i].src_image_ids) need[index_of.at(id)] = 1;
+            }
+            for (size_t v = 0; v < num_images; ++v)
+                if (need[v]) needed.push_back(v);
+        }
         bool first_level = true;
         for (int level = 0; level < levels; ++level) {
             const int scale = max_num_downscale - level;
@@ -384,6 +396,16 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             }
             t_load += now_s() - tp;
             if (!barrier.wait()) return;
+            // Every image this device's views use (their own and their source views'), on the device ONCE per level: a view's
+            // image is a source image of ~10 other views, and uploading it with each of them was 0.3 s per 3200x2130 view
+            tp = now_s();
+            for (size_t v : needed) {
+                pool[v].fit(level_w[v], level_h[v], full_px[v]);
+                if (cudaMemcpyAsync(pool[v].ptr, level_image[v].ptr(), sizeof(float) * (size_t)level_w[v] * level_h[v], cudaMemcpyHostToDevice, 0) != cudaSuccess)
+                    throw std::runtime_error("upload of a level image failed");
+            }
+            if (cudaStreamSynchronize(0) != cudaSuccess) throw std::runtime_error("upload of the level images failed");
+            t_views += now_s() - tp;
 
             struct PriorJob {
                 std::future<void> done;
@@ -430,11 +452,15 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             for (size_t i : mine) {                                                  // photometric + prior stage
                 const Problem &problem = problems[i];
                 std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << "..." << std::endl;
-                std::vector<cv::Mat_<float>> images{level_image[i]};
+                std::vector<const float *> images{pool[i].ptr};
+                std::vector<int> ws{level_w[i]}, hs{level_h[i]};
                 std::vector<Camera> cameras{level_camera[i]};
                 for (int id : problem.src_image_ids) {
-                    images.push_back(level_image[index_of[id]]);
-                    cameras.push_back(level_camera[index_of[id]]);
+                    const size_t s = index_of.at(id);
+                    images.push_back(pool[s].ptr);
+                    ws.push_back(level_w[s]);
+                    hs.push_back(level_h[s]);
+                    cameras.push_back(level_camera[s]);
                 }
                 tp = now_s();
                 if (first_level) {
@@ -442,7 +468,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     objs[i]->SetSeed(g_seed);
                 }
                 ACMMP &acmmp = *objs[i];
-                acmmp.SetViewsHost(images, cameras, !first_level);
+                acmmp.SetViewsDevice(images, ws, hs, cameras, !first_level, &level_image[i]);
                 t_views += now_s() - tp;
                 tp = now_s();
                 acmmp.RunPatchMatchResident(!g_gpu_prior);                           // the CPU prior stage reads the result
@@ -500,7 +526,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     std::vector<const float *> maps;
                     std::vector<int> ws, hs;
                     for (int id : problem.src_image_ids) {
-                        const DeviceMap &m = multi_geometry ? gtab[d][index_of[id]] : dtab[d][index_of[id]];
+                        const DeviceMap &m = multi_geometry ? gtab[d][index_of.at(id)] : dtab[d][index_of.at(id)];
                         maps.push_back(m.ptr);
                         ws.push_back(m.w);
                         hs.push_back(m.h);
@@ -519,21 +545,28 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     t_export += now_s() - tg;
                     tg = now_s();
                     if (last) {
-                        const int width = acmmp.GetReferenceImageWidth(), height = acmmp.GetReferenceImageHeight();
-                        cv::Mat_<float> depths = cv::Mat_<float>::zeros(height, width), costs = cv::Mat_<float>::zeros(height, width);
-                        cv::Mat_<cv::Vec3f> normals = cv::Mat_<cv::Vec3f>::zeros(height, width);
-                        for (int k = 0; k < width * height; ++k) {
-                            const float4 ph = acmmp.GetPlaneHypothesis(k);
-                            depths.ptr()[k] = ph.w;
-                            normals.ptr()[k] = cv::Vec3f(ph.x, ph.y, ph.z);
-                            costs.ptr()[k] = acmmp.GetCost(k);
-                        }
-                        const std::string result_folder = result_folder_of(dense_folder, problem.ref_image_id);
-                        mkdir(result_folder.c_str(), 0777);
-                        writeDepthDmb(result_folder + "/depths.dmb", final_prior_depth[i]);
-                        writeDepthDmb(result_folder + "/depths_geom.dmb", depths);
-                        writeNormalDmb(result_folder + "/normals.dmb", normals);
-                        writeDepthDmb(result_folder + "/costs.dmb", costs);
+                        // the view's four .dmb files on a writer thread: the result sits in the object's host buffers, which
+                        // nothing touches any more (this was the view's last stage), and this thread goes on with the next view
+                        ACMMP *obj = &acmmp;
+                        const int ref_id = problem.ref_image_id;
+                        const cv::Mat_<float> *prior_depth = &final_prior_depth[i];
+                        writers.push_back(std::async(std::launch::async, [obj, ref_id, prior_depth, &dense_folder]() {
+                            const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
+                            cv::Mat_<float> depths = cv::Mat_<float>::zeros(height, width), costs = cv::Mat_<float>::zeros(height, width);
+                            cv::Mat_<cv::Vec3f> normals = cv::Mat_<cv::Vec3f>::zeros(height, width);
+                            for (int k = 0; k < width * height; ++k) {
+                                const float4 ph = obj->GetPlaneHypothesis(k);
+                                depths.ptr()[k] = ph.w;
+                                normals.ptr()[k] = cv::Vec3f(ph.x, ph.y, ph.z);
+                                costs.ptr()[k] = obj->GetCost(k);
+                            }
+                            const std::string result_folder = result_folder_of(dense_folder, ref_id);
+                            mkdir(result_folder.c_str(), 0777);
+                            writeDepthDmb(result_folder + "/depths.dmb", *prior_depth);
+                            writeDepthDmb(result_folder + "/depths_geom.dmb", depths);
+                            writeNormalDmb(result_folder + "/normals.dmb", normals);
+                            writeDepthDmb(result_folder + "/costs.dmb", costs);
+                        }));
                         std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << " done!" << std::endl;
                     }
                     t_output += now_s() - tg;
@@ -547,6 +580,11 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             t_geom += now_s() - t_g;
             first_level = false;
             if (!barrier.wait()) return;                                             // nobody overwrites a table somebody still reads
+        }
+        {
+            const double tw = now_s();
+            for (auto &w : writers) w.get();                 // rethrows a writer's exception
+            t_output += now_s() - tw;
         }
         std::lock_guard<std::mutex> lock(stats_mutex);
         g_gpu_ms += gpu_ms;

@@ -3,7 +3,8 @@
 // Incremental Bowyer-Watson with triangle adjacency, point location by walking from the last new triangle
 // (the support points arrive in scan order, so walks are a few steps), EXACT predicates in integer arithmetic
 // (orientation in int64, in-circle in __int128), co-circular points count as outside.  On co-circular quadruples
-// the diagonal may differ from OpenCV's -- both are Delaunay triangulations.
+// the diagonal may differ from OpenCV's -- both are Delaunay triangulations (on a 3200x2130 view's 272 640 near-grid
+// support points the two triangle sets come out identical, tests/test_cpu_cpp_host.py).
 #include <cstdint>
 #include <vector>
 
@@ -37,7 +38,11 @@ inline bool in_circle(const P2 &a, const P2 &b, const P2 &c, const P2 &d)
 
 } // namespace
 
-std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points)
+// rect_w / rect_h > 0: the enclosing triangle is the one cv::Subdiv2D::initDelaunay builds for Rect(0, 0, rect_w, rect_h)
+// -- (3M, 0), (0, 3M), (-3M, -3M) with M = max(w, h) -- so that the triangulation of the points TOGETHER WITH these three
+// virtual vertices, and with it the thin triangles along the convex hull that survive the reference's inside-the-image
+// filter (main.cpp:140-146), is the one the reference computes.
+std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points, int rect_w, int rect_h)
 {
     const int n = (int)points.size();
     std::vector<int> out;
@@ -51,9 +56,23 @@ std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points)
     std::vector<P2> pt(n + 3);
     for (int i = 0; i < n; ++i) pt[i] = P2{points[i].x, points[i].y};
     // enclosing triangle, counter-clockwise, far outside the points
-    pt[n + 0] = P2{lo_x - 20 * S, lo_y - 10 * S};
-    pt[n + 1] = P2{hi_x + 20 * S, lo_y - 10 * S};
-    pt[n + 2] = P2{(lo_x + hi_x) / 2, hi_y + 30 * S};
+    bool cv_triangle = rect_w > 0 && rect_h > 0;
+    if (cv_triangle) {
+        const int64_t big = 3 * (int64_t)std::max(rect_w, rect_h);
+        // every point must lie strictly inside it (true for pixels of the rectangle)
+        for (const auto &p : points)
+            if (p.x < 0 || p.y < 0 || p.x >= rect_w || p.y >= rect_h) cv_triangle = false;
+        if (cv_triangle) {
+            pt[n + 0] = P2{big, 0};
+            pt[n + 1] = P2{0, big};
+            pt[n + 2] = P2{-big, -big};
+        }
+    }
+    if (!cv_triangle) {
+        pt[n + 0] = P2{lo_x - 20 * S, lo_y - 10 * S};
+        pt[n + 1] = P2{hi_x + 20 * S, lo_y - 10 * S};
+        pt[n + 2] = P2{(lo_x + hi_x) / 2, hi_y + 30 * S};
+    }
 
     std::vector<Tri> tris;
     tris.reserve((size_t)2 * n + 16);

@@ -55,7 +55,18 @@ int acmmp_host_resize_linear(const float *src, int w, int h, float *dst, int nw,
     return 0;
 }
 
-// points: n x (x, y) int32; out: up to cap index triples; returns the number of triangles
+// points: n x (x, y) int32; out: up to cap index triples; returns the number of triangles.
+// acmmp_host_delaunay_rect: with the enclosing triangle cv::Subdiv2D builds for Rect(0, 0, w, h) (see delaunay.cpp).
+int acmmp_host_delaunay_rect(const int32_t *points, int n, int w, int h, int32_t *out, int cap)
+{
+    std::vector<cv::Point> pts(n);
+    for (int i = 0; i < n; ++i) pts[i] = cv::Point(points[2 * i], points[2 * i + 1]);
+    const std::vector<int> idx = DelaunayIndices(pts, w, h);
+    const int nt = (int)(idx.size() / 3);
+    for (int i = 0; i < std::min(nt, cap) * 3; ++i) out[i] = idx[i];
+    return nt;
+}
+
 int acmmp_host_delaunay(const int32_t *points, int n, int32_t *out, int cap)
 {
     std::vector<cv::Point> pts(n);

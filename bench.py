@@ -357,8 +357,11 @@ def run_c3(a, cfg, rank, local_rank, world, use_dist, json_fd):
         gt = gt_mine[v]
         results[v] = float((np.abs(planes[..., 3] - gt) / gt <= 0.01)[8:-8, 8:-8].mean())
 
+    workers, tables = {}, []          # one context per owned view and the two map tables live through all steps (warm pools)
+
     def step():
-        return sc.run_scene(levels, full.pairs, rank, world, lambda: sc.GpuWorker(local_rank, 1234), alloc, all_gather, on_result=on_result)
+        return sc.run_scene(levels, full.pairs, rank, world, lambda: sc.GpuWorker(local_rank, 1234), alloc, all_gather, on_result=on_result,
+                            workers=workers, tables=tables)
 
     def barrier():
         torch.cuda.synchronize()

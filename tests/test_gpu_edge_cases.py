@@ -165,3 +165,53 @@ def test_argument_errors_are_reported_not_fatal():
     ctx.reset_modes()
     ctx.run_patch_match()                          # and the context is still usable
     assert lib().acmmp_create(C.byref(C.c_void_p()), C.c_int(4096)) != 0      # no such device
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["pinhole", "sphere"])
+def test_device_planar_prior_against_the_numpy_twin(model):
+    """acmmp_support_points + acmmp_planar_prior_from_triangles (k_support_cells, k_tri_planes,
+    k_tri_raster[_long], k_prior_finish) against acmmp_b200/prior.py, which follows the reference's CPU stage
+    (ACMMP.cpp:904-1011, main.cpp:113-185) with cv2.Subdiv2D -- the reference's own triangulator -- on the SAME photometric
+    result: same support points, same triangles (tests/test_cpu_cpp_host.py pins the C++ triangulator to Subdiv2D), same
+    plane per triangle; per pixel the same prior plane except on triangle edges, where the twin's cv2.fillConvexPoly and the
+    reference's stepping rasteriser (reproduced on the device) assign the pixel to either neighbour."""
+    import cv2
+    from acmmp_b200 import Context, synth
+    from acmmp_b200 import prior as twin
+    from acmmp_b200.scene import delaunay_triangles_inside
+    scene = (synth.make_pinhole_scene(n_views=4, width=640, height=480, focal=500.0, seed=1) if model == "pinhole"
+             else synth.make_sphere_scene(n_views=4, width=1024, height=512, seed=4))
+    imgs, cams, _ = scene.problem(0)
+    ctx = Context(0)
+    ctx.set_views(imgs, cams)
+    ctx.set_seed(5)
+    ctx.run_patch_match()
+    planes, costs = (np.array(a) for a in ctx.get_result())
+    H, W = costs.shape
+    dmin = float(np.float32(cams[0].depth_min) * np.float32(0.6))
+    dmax = float(np.float32(cams[0].depth_max) * np.float32(1.2))
+    ctx.set_planar_prior()
+    pts = ctx.support_points()
+    pts_twin = twin.support_points(costs)
+    assert np.array_equal(pts, pts_twin)
+    ctx.planar_prior_from_triangles(delaunay_triangles_inside(pts, W, H))
+    pp, mk = ctx.download_prior()
+    p_ref, m_ref = twin.planar_prior(cams[0], np.ascontiguousarray(planes[..., 3]), costs, dmin, dmax)
+    both = (mk > 0) & (m_ref > 0)
+    mine = pp[both]
+    theirs = p_ref[m_ref[both].astype(np.int64) - 1]
+    same = np.all(np.abs(mine - theirs) <= 1e-4 + 1e-4 * np.abs(theirs), axis=1)
+    # the planes of the pixels that disagree belong to a NEIGHBOURING triangle of the twin: check against the twin's plane set
+    from scipy.spatial import cKDTree
+    scale = np.abs(p_ref).max(axis=0)
+    d, _ = cKDTree(p_ref / scale).query(mine[~same] / scale) if (~same).any() else (np.zeros(0), None)
+    res = dict(support_points=int(len(pts)), triangles=int(mk.max()), triangles_twin=int(len(p_ref)),
+               masked_mine=float((mk > 0).mean()), masked_twin=float((m_ref > 0).mean()), masked_both=float(both.mean()),
+               same_plane_where_both=float(same.mean()), disagreeing_planes_found_in_twin_set=float((d < 1e-4).mean()) if len(d) else 1.0)
+    util.dump(f"device_prior_vs_twin_{model}", res)
+    ctx.close()
+    assert res["triangles"] == res["triangles_twin"], res
+    assert abs(res["masked_mine"] - res["masked_twin"]) < 0.02 and res["masked_both"] > 0.9 * res["masked_twin"], res
+    assert res["same_plane_where_both"] > 0.6, res
+    assert res["disagreeing_planes_found_in_twin_set"] > 0.99, res
