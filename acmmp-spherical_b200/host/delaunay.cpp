@@ -39,9 +39,15 @@ inline bool in_circle(const P2 &a, const P2 &b, const P2 &c, const P2 &d)
 } // namespace
 
 // rect_w / rect_h > 0: the enclosing triangle is the one cv::Subdiv2D::initDelaunay builds for Rect(0, 0, rect_w, rect_h)
-// -- (3M, 0), (0, 3M), (-3M, -3M) with M = max(w, h) -- so that the triangulation of the points TOGETHER WITH these three
-// virtual vertices, and with it the thin triangles along the convex hull that survive the reference's inside-the-image
-// filter (main.cpp:140-146), is the one the reference computes.
+// -- (B, 0), (0, B), (-B, -B) with B = kSubdivBig * max(w, h) -- so that the triangulation of the points TOGETHER WITH
+// these three virtual vertices, and with it the thin triangles along the convex hull that survive the reference's
+// inside-the-image filter (main.cpp:140-146), is the one the reference computes.  The factor is OpenCV's and depends on
+// its version: 6 in OpenCV 4.13 (the cv2 of this image, which the parity tests compare with: getVertex(1..3) of a fresh
+// Subdiv2D((0, 0, 640, 480)) = (3840, 0), (0, 3840), (-3840, -3840)), 3 in older releases; the reference pins no version
+// (README: OpenCV >= 2.4).  Only hull triangles a few pixels thin depend on it.
+#ifndef ACMMP_SUBDIV_BIG
+#define ACMMP_SUBDIV_BIG 6
+#endif
 std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points, int rect_w, int rect_h)
 {
     const int n = (int)points.size();
@@ -58,7 +64,7 @@ std::vector<int> DelaunayIndices(const std::vector<cv::Point> &points, int rect_
     // enclosing triangle, counter-clockwise, far outside the points
     bool cv_triangle = rect_w > 0 && rect_h > 0;
     if (cv_triangle) {
-        const int64_t big = 3 * (int64_t)std::max(rect_w, rect_h);
+        const int64_t big = (int64_t)ACMMP_SUBDIV_BIG * (int64_t)std::max(rect_w, rect_h);
         // every point must lie strictly inside it (true for pixels of the rectangle)
         for (const auto &p : points)
             if (p.x < 0 || p.y < 0 || p.x >= rect_w || p.y >= rect_h) cv_triangle = false;

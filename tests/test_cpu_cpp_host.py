@@ -222,8 +222,8 @@ def test_ply_writer_writes_the_references_binary_layout(tmp_path):
     assert abs(b[3] - 0.6) < 1e-6 and abs(b[5] - 0.8) < 1e-6
 
 
-@pytest.mark.parametrize("full_grid", [True, False])
-def test_delaunay_triangle_set_equals_cv2_subdiv2d_at_full_resolution(host, full_grid):
+@pytest.mark.parametrize("kind", ["grid", "ragged", "clustered"])
+def test_delaunay_triangle_set_equals_cv2_subdiv2d_at_full_resolution(host, kind):
     """SURVEY.md 8(f) N2, the parity question: the reference triangulates the support points with cv::Subdiv2D
     (ACMMP.cpp:932-954); this library with host/delaunay.cpp.  cv2.Subdiv2D is the same OpenCV implementation, so the
     comparison below pins the stand-in to what the reference would compute, at the size that matters: one support point
@@ -236,10 +236,16 @@ def test_delaunay_triangle_set_equals_cv2_subdiv2d_at_full_resolution(host, full
     W, H = 3200, 2130
     cx, cy = np.meshgrid(np.arange(W // 5), np.arange(H // 5), indexing="ij")
     pts = np.stack([5 * cx.ravel() + rng.integers(0, 5, cx.size), 5 * cy.ravel() + rng.integers(0, 5, cx.size)], 1).astype(np.int32)
-    if not full_grid:
+    if kind == "ragged":
         # real support sets have holes (cells whose best cost is >= 0.1) and a ragged hull: keep 85 % of the cells and cut
         # two corners away
         keep = (rng.random(len(pts)) < 0.85) & (pts[:, 0] + pts[:, 1] > 400) & (pts[:, 0] - pts[:, 1] < 2900)
+        pts = np.ascontiguousarray(pts[keep])
+    elif kind == "clustered":
+        # holes in clusters (texture-less regions) reaching the image border: long thin triangles along the hull, whose
+        # existence depends on the virtual enclosing triangle (delaunay.cpp: the one of this image's OpenCV)
+        field = cv2.GaussianBlur(rng.random((H // 5, W // 5)).astype(np.float32), (0, 0), 6)
+        keep = field[np.minimum(pts[:, 1] // 5, H // 5 - 1), np.minimum(pts[:, 0] // 5, W // 5 - 1)] > np.quantile(field, 0.25)
         pts = np.ascontiguousarray(pts[keep])
     out = np.zeros((2 * len(pts) + 16, 3), np.int32)
     nt = host.acmmp_host_delaunay_rect(pts.ctypes.data_as(C.POINTER(C.c_int32)), len(pts), W, H, out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
@@ -293,7 +299,7 @@ def test_delaunay_triangle_set_equals_cv2_subdiv2d_at_full_resolution(host, full
     import sys
     sys.path.insert(0, str(ROOT / "tests"))
     import util
-    util.dump("delaunay_vs_subdiv2d_c2" + ("" if full_grid else "_ragged"), res)
+    util.dump("delaunay_vs_subdiv2d_c2_" + kind, res)
     # measured: 544 859 triangles on both sides, every one of them in common (the two implementations even break the
     # co-circular ties the same way on this input)
     assert frac_common >= 0.999, res
