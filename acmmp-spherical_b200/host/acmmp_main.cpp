@@ -38,6 +38,7 @@ int g_gpu_prior = 0;
 double g_gpu_ms = 0.0, g_prior_s = 0.0;
 // wall-clock attribution of the resident schedule (printed in the summary): image load + scaling, view upload / level
 // change (incl. context creation), stage runs (kernels + waits + downloads), depth-map export, result output
+double g_t_ctx = 0.0, g_t_upload = 0.0, g_t_support = 0.0, g_t_prior_dev = 0.0;
 double g_t_load = 0.0, g_t_views = 0.0, g_t_run = 0.0, g_t_export = 0.0, g_t_output = 0.0, g_t_join = 0.0;
 double g_t_sweep1 = 0.0, g_t_geom = 0.0;   // totals: first sweep, geometric sweeps
 double g_t_exchange = 0.0;                 // --gpus N: peer copies of the depth maps
@@ -344,6 +345,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
 
     auto device_main = [&](const int d) {
         // per-thread wall-clock attribution, merged into the globals at the end
+        double t_ctx = 0, t_upload = 0, t_support = 0, t_prior_dev = 0;
         double t_load = 0, t_views = 0, t_run = 0, t_export = 0, t_output = 0, t_join = 0, t_sweep1 = 0, t_geom = 0, t_exchange = 0, gpu_ms = 0;
         cudaSetDevice(g_device + d);
         std::vector<size_t> mine;
@@ -406,6 +408,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             }
             if (cudaStreamSynchronize(0) != cudaSuccess) throw std::runtime_error("upload of the level images failed");
             t_views += now_s() - tp;
+            t_upload += now_s() - tp;
 
             struct PriorJob {
                 std::future<void> done;
@@ -424,6 +427,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 tw = now_s();
                 if (g_gpu_prior) {
                     a.CudaPlanarPriorFromTriangles(pending[v]->inside);
+                    t_prior_dev += now_s() - tw;
                     add_prior_s(pending[v]->host_s + (now_s() - tw));
                 } else {
                     a.CudaPlanarPriorInitialization(pending[v]->planeParams_tri, pending[v]->mask_tri);
@@ -466,6 +470,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 if (first_level) {
                     objs[i].reset(new ACMMP(g_device + d));
                     objs[i]->SetSeed(g_seed);
+                    t_ctx += now_s() - tp;
                 }
                 ACMMP &acmmp = *objs[i];
                 acmmp.SetViewsDevice(images, ws, hs, cameras, !first_level, &level_image[i]);
@@ -488,6 +493,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     const double t0 = now_s();
                     acmmp.SetPlanarPriorParams();
                     acmmp.GetSupportPointsDevice(job->support);
+                    t_support += now_s() - t0;
                     add_prior_s(now_s() - t0);
                     job->done = std::async(std::launch::async, [job, obj]() {
                         const double t1 = now_s();
@@ -588,6 +594,8 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         }
         std::lock_guard<std::mutex> lock(stats_mutex);
         g_gpu_ms += gpu_ms;
+        g_t_ctx = std::max(g_t_ctx, t_ctx); g_t_upload = std::max(g_t_upload, t_upload); g_t_support = std::max(g_t_support, t_support);
+        g_t_prior_dev = std::max(g_t_prior_dev, t_prior_dev);
         g_t_load = std::max(g_t_load, t_load); g_t_views = std::max(g_t_views, t_views); g_t_run = std::max(g_t_run, t_run);
         g_t_export = std::max(g_t_export, t_export); g_t_output = std::max(g_t_output, t_output); g_t_join = std::max(g_t_join, t_join);
         g_t_sweep1 = std::max(g_t_sweep1, t_sweep1); g_t_geom = std::max(g_t_geom, t_geom); g_t_exchange = std::max(g_t_exchange, t_exchange);
@@ -710,7 +718,8 @@ int main(int argc, char **argv)
     }
     std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << wall_patchmatch << ", \"kernel_ms\": " << g_gpu_ms
               << ", \"prior_cpu_s\": " << g_prior_s << ", \"load_s\": " << g_t_load << ", \"views_s\": " << g_t_views << ", \"run_s\": " << g_t_run
-              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"sweep1_s\": " << g_t_sweep1 << ", \"geom_s\": " << g_t_geom
+              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"ctx_s\": " << g_t_ctx << ", \"upload_s\": " << g_t_upload
+              << ", \"support_s\": " << g_t_support << ", \"prior_dev_s\": " << g_t_prior_dev << ", \"sweep1_s\": " << g_t_sweep1 << ", \"geom_s\": " << g_t_geom
               << ", \"gpus\": " << (resident ? g_devices_used : 1) << ", \"exchange_s\": " << g_t_exchange
               << ", \"fusion_s\": " << fusion_s << ", \"fusion_kernel_ms\": " << fusion_kernel_ms << ", \"fusion_points\": " << fusion_points << "}" << std::endl;
     return 0;

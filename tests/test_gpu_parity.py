@@ -535,4 +535,7 @@ def test_full_stage_statistical(model):
     dump(f"full_stage_{model}", res)
     # both converge to the same surface; the quality of mine must not be below the reference's
     assert res["mine_vs_gt_1pct"] >= res["ref_vs_gt_1pct"] - 0.02, res
-    assert res["depth_within_1pct"] >= 0.90, res
+    # measured (B200): pinhole 99.96 % of the pixels within 1 % depth / 98.3 % of the normals within 5 deg, sphere 99.6 % / 95.6 %;
+    # the reference against itself on a single photometric stage: tests/test_gpu_pipeline_parity.py (C1)
+    assert res["depth_within_1pct"] >= 0.99, res
+    assert res["normal_within_5deg"] >= (0.97 if model == "pinhole" else 0.94), res
