@@ -77,7 +77,7 @@ _EXPORTS = [
     "acmmp_default_params", "acmmp_version", "acmmp_abi_sizeof_camera", "acmmp_abi_sizeof_params",
     "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
-    "acmmp_get_params", "acmmp_reset_modes", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
+    "acmmp_get_params", "acmmp_reset_modes", "acmmp_park", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
     "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_next_level_device", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_support_points",
     "acmmp_planar_prior_from_triangles", "acmmp_download_prior", "acmmp_set_seed",
     "acmmp_set_plane_now_semantics", "acmmp_set_sphere_tap_pruning", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
@@ -195,6 +195,11 @@ class Context:
 
     def reset_modes(self):
         self._ck(self._l.acmmp_reset_modes(self._h), "acmmp_reset_modes")
+
+    def park(self, keep_prior=False, keep_host_result=False):
+        """Give everything but the stage state (planes, costs, coarse planes) back to the device's pool; go on with
+        set_views / set_views_device of the same shapes (include/acmmp_b200.h: acmmp_park)."""
+        self._ck(self._l.acmmp_park(self._h, C.c_int(int(keep_prior)), C.c_int(int(keep_host_result))), "acmmp_park")
 
     def params(self) -> Params:
         p = Params()

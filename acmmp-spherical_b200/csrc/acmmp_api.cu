@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <mutex>
 #include <string>
@@ -154,41 +155,103 @@ inline M3 kproj(const float K[9])
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
+// ACMMP_TRACE=1: host wall clock per entry point / phase / allocator call, summed over the process and printed to
+// stderr at exit (a development aid for the driver's end-to-end time; off by default, two clock reads per scope)
+// ---------------------------------------------------------------------------------------------
+struct TraceTable {
+    std::mutex m;
+    std::map<std::string, std::pair<double, long>> acc;
+    const bool on = std::getenv("ACMMP_TRACE") != nullptr;
+    void add(const std::string &k, double dt)
+    {
+        std::lock_guard<std::mutex> lock(m);
+        auto &e = acc[k];
+        e.first += dt;
+        e.second++;
+    }
+    ~TraceTable()
+    {
+        if (!on) return;
+        for (auto &kv : acc) std::fprintf(stderr, "[acmmp trace] %-44s %9.3f ms  %6ld calls\n", kv.first.c_str(), kv.second.first * 1e3, kv.second.second);
+    }
+};
+static TraceTable g_trace;
+static inline double trace_now()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+struct Trace {
+    const char *name;
+    double t0, tp;
+    explicit Trace(const char *n) : name(n), t0(g_trace.on ? trace_now() : 0.0), tp(t0) {}
+    void mark(const char *phase)
+    {
+        if (!g_trace.on) return;
+        const double t = trace_now();
+        g_trace.add(std::string(name) + ":" + phase, t - tp);
+        tp = t;
+    }
+    ~Trace()
+    {
+        if (g_trace.on) g_trace.add(name, trace_now() - t0);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-// Size-keyed free lists for device memory, pinned host memory and CUDA arrays.  A view walks through the
-// same three pyramid-level shapes over and over (and a context is re-used for consecutive views), so after
-// the first level visit nothing is cudaMalloc'ed / cudaMallocHost'ed again (the reference allocates and
-// frees everything per ProcessProblem call, ACMMP.cpp:685-724 / :101-143).
+// Size-keyed free lists for device memory, pinned host memory and CUDA arrays, in two tiers.  Every context has its
+// own (unsynchronised) pool: a view walks through the same three pyramid-level shapes over and over, and a block freed
+// by a context is handed back to that context in stream order.  Behind it sits one pool per DEVICE, shared by the
+// contexts of that device (mutex): a context that parks (acmmp_park) or is destroyed synchronises its stream and moves
+// its free blocks there, and a context that misses in its own lists looks there before it calls cudaMalloc /
+// cudaMallocHost / cudaMallocArray.  A resident scene keeps one context per view alive (the stage state lives in it);
+// with every context allocating its own ~1.1 GB of scratch per level, the allocator calls were 6 of 16 s of an
+// 11-view 3200x2130 scene (ACMMP_TRACE).  (The reference allocates and frees everything per ProcessProblem call,
+// ACMMP.cpp:685-724 / :101-143.)
 struct MemPool {
     std::multimap<size_t, void *> dev_free, host_free;
-    std::unordered_map<void *, size_t> dev_size, host_size;
+    std::unordered_map<void *, size_t> dev_size, host_size;      // every block this pool owns, free or handed out
     typedef std::tuple<int, int, int> ArrKey;
     std::multimap<ArrKey, cudaArray_t> arr_free;
     std::map<cudaArray_t, ArrKey> arr_key;
+    struct DeviceShared *shared = nullptr;                        // second tier (null for the shared pool itself)
 
-    cudaError_t dmalloc(void **p, size_t bytes)
+    bool take_dev(size_t bytes, void **p)
     {
         auto it = dev_free.find(bytes);
-        if (it != dev_free.end()) { *p = it->second; dev_free.erase(it); return cudaSuccess; }
-        cudaError_t e = cudaMalloc(p, bytes);
-        if (e == cudaSuccess) dev_size[*p] = bytes;
-        return e;
+        if (it == dev_free.end()) return false;
+        *p = it->second;
+        dev_free.erase(it);
+        return true;
     }
+    bool take_host(size_t bytes, void **p)
+    {
+        auto it = host_free.find(bytes);
+        if (it == host_free.end()) return false;
+        *p = it->second;
+        host_free.erase(it);
+        return true;
+    }
+    bool take_arr(const ArrKey &k, cudaArray_t *a)
+    {
+        auto it = arr_free.find(k);
+        if (it == arr_free.end()) return false;
+        *a = it->second;
+        arr_free.erase(it);
+        return true;
+    }
+    cudaError_t dmalloc(void **p, size_t bytes);
+    cudaError_t hmalloc(void **p, size_t bytes);
+    cudaError_t amalloc(cudaArray_t *a, const cudaChannelFormatDesc *desc, int w, int h, int layers);
     void dfree(void *p)
     {
         if (!p) return;
         auto it = dev_size.find(p);
         if (it == dev_size.end()) { cudaFree(p); return; }
         dev_free.insert(std::make_pair(it->second, p));
-    }
-    cudaError_t hmalloc(void **p, size_t bytes)
-    {
-        auto it = host_free.find(bytes);
-        if (it != host_free.end()) { *p = it->second; host_free.erase(it); return cudaSuccess; }
-        cudaError_t e = cudaMallocHost(p, bytes);
-        if (e == cudaSuccess) host_size[*p] = bytes;
-        return e;
     }
     void hfree(void *p)
     {
@@ -197,22 +260,28 @@ struct MemPool {
         if (it == host_size.end()) { cudaFreeHost(p); return; }
         host_free.insert(std::make_pair(it->second, p));
     }
-    cudaError_t amalloc(cudaArray_t *a, const cudaChannelFormatDesc *desc, int w, int h, int layers)
-    {
-        const ArrKey k(w, h, layers);
-        auto it = arr_free.find(k);
-        if (it != arr_free.end()) { *a = it->second; arr_free.erase(it); return cudaSuccess; }
-        cudaError_t e = layers > 0 ? cudaMalloc3DArray(a, desc, make_cudaExtent(w, h, layers), cudaArrayLayered)
-                                   : cudaMallocArray(a, desc, w, h);
-        if (e == cudaSuccess) arr_key[*a] = k;
-        return e;
-    }
     void afree(cudaArray_t a)
     {
         if (!a) return;
         auto it = arr_key.find(a);
         if (it == arr_key.end()) { cudaFreeArray(a); return; }
         arr_free.insert(std::make_pair(it->second, a));
+    }
+    // hand one block (free or not) over to another pool's registry
+    void disown_dev(void *p, MemPool &to)
+    {
+        auto it = dev_size.find(p);
+        if (it == dev_size.end()) return;
+        to.dev_size[p] = it->second;
+        dev_size.erase(it);
+    }
+    // every FREE block changes owner (the caller has synchronised the stream that last used them)
+    void give_free_to(MemPool &to)
+    {
+        for (auto &kv : dev_free) { to.dev_size[kv.second] = kv.first; to.dev_free.insert(kv); dev_size.erase(kv.second); }
+        for (auto &kv : host_free) { to.host_size[kv.second] = kv.first; to.host_free.insert(kv); host_size.erase(kv.second); }
+        for (auto &kv : arr_free) { to.arr_key[kv.second] = kv.first; to.arr_free.insert(kv); arr_key.erase(kv.second); }
+        dev_free.clear(); host_free.clear(); arr_free.clear();
     }
     void release_all()
     {
@@ -222,6 +291,61 @@ struct MemPool {
         dev_free.clear(); host_free.clear(); dev_size.clear(); host_size.clear(); arr_free.clear(); arr_key.clear();
     }
 };
+
+// per device: the shared pool, the curand_init states per (seed, W, H) (read-only once built; 164 MB at 3200x2130, one
+// copy per device instead of one per view) and the number of live contexts (the last one out frees everything)
+struct DeviceShared {
+    std::mutex m;
+    MemPool pool;
+    std::map<std::tuple<uint64_t, int, int>, uint2 *> seeded_cache;
+    int live = 0;
+};
+static DeviceShared &device_shared(int device)
+{
+    static std::mutex m;
+    static std::map<int, DeviceShared> table;          // node-based: references stay valid
+    std::lock_guard<std::mutex> lock(m);
+    return table[device];
+}
+
+cudaError_t MemPool::dmalloc(void **p, size_t bytes)
+{
+    if (take_dev(bytes, p)) return cudaSuccess;
+    if (shared) {
+        std::lock_guard<std::mutex> lock(shared->m);
+        if (shared->pool.take_dev(bytes, p)) { shared->pool.dev_size.erase(*p); dev_size[*p] = bytes; return cudaSuccess; }
+    }
+    Trace tr("pool.cudaMalloc");
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) dev_size[*p] = bytes;
+    return e;
+}
+cudaError_t MemPool::hmalloc(void **p, size_t bytes)
+{
+    if (take_host(bytes, p)) return cudaSuccess;
+    if (shared) {
+        std::lock_guard<std::mutex> lock(shared->m);
+        if (shared->pool.take_host(bytes, p)) { shared->pool.host_size.erase(*p); host_size[*p] = bytes; return cudaSuccess; }
+    }
+    Trace tr("pool.cudaMallocHost");
+    cudaError_t e = cudaMallocHost(p, bytes);
+    if (e == cudaSuccess) host_size[*p] = bytes;
+    return e;
+}
+cudaError_t MemPool::amalloc(cudaArray_t *a, const cudaChannelFormatDesc *desc, int w, int h, int layers)
+{
+    const ArrKey k(w, h, layers);
+    if (take_arr(k, a)) return cudaSuccess;
+    if (shared) {
+        std::lock_guard<std::mutex> lock(shared->m);
+        if (shared->pool.take_arr(k, a)) { shared->pool.arr_key.erase(*a); arr_key[*a] = k; return cudaSuccess; }
+    }
+    Trace tr("pool.cudaMallocArray");
+    cudaError_t e = layers > 0 ? cudaMalloc3DArray(a, desc, make_cudaExtent(w, h, layers), cudaArrayLayered)
+                               : cudaMallocArray(a, desc, w, h);
+    if (e == cudaSuccess) arr_key[*a] = k;
+    return e;
+}
 
 struct acmmp_ctx {
     MemPool pool;
@@ -235,7 +359,7 @@ struct acmmp_ctx {
     int num_sms = 148;
     uint64_t seed = 0;
     bool have_seeded = false;
-    std::map<std::tuple<uint64_t, int, int>, uint2 *> seeded_cache;   // curand_init states per (seed, W, H), kept across levels
+    bool parked = false;                  // acmmp_park: only the stage state is held, the scratch went to the device pool
     uint64_t seeded_seed = 0;
     int seeded_w = 0, seeded_h = 0;
 
@@ -359,7 +483,8 @@ int make_tmap(acmmp_ctx *ctx, CUtensorMap *tm, int box_w, int box_h)
     return ACMMP_OK;
 }
 
-void free_views(acmmp_ctx *ctx)
+// everything a stage needs besides its state: textures, padded reference, ping-pong and per-stage buffers, RNG states
+void free_scratch(acmmp_ctx *ctx, bool host_result)
 {
     if (ctx->src_tex) cudaDestroyTextureObject(ctx->src_tex);
     if (ctx->src_array) ctx->pool.afree(ctx->src_array);
@@ -372,19 +497,36 @@ void free_views(acmmp_ctx *ctx)
     ctx->pool.dfree(ctx->ref_dense); ctx->ref_dense = nullptr;
     ctx->pool.dfree(ctx->ref_padded); ctx->ref_padded = nullptr;
     ctx->pool.dfree(ctx->views_dev); ctx->views_dev = nullptr;
-    ctx->pool.dfree(ctx->planes); ctx->pool.dfree(ctx->planes_alt); ctx->pool.dfree(ctx->costs); ctx->pool.dfree(ctx->costs_alt);
+    ctx->pool.dfree(ctx->planes_alt); ctx->pool.dfree(ctx->costs_alt);
     ctx->pool.dfree(ctx->pre_costs); ctx->pool.dfree(ctx->selected_views); ctx->pool.dfree(ctx->rng);
-    ctx->pool.dfree(ctx->prior_planes); ctx->pool.dfree(ctx->plane_masks); ctx->pool.dfree(ctx->coarse_planes);
-    ctx->planes = ctx->planes_alt = nullptr;
-    ctx->costs = ctx->costs_alt = ctx->pre_costs = nullptr;
+    ctx->planes_alt = nullptr;
+    ctx->costs_alt = ctx->pre_costs = nullptr;
     ctx->selected_views = nullptr;
     ctx->rng = ctx->rng_seeded = nullptr;
-    ctx->prior_planes = nullptr; ctx->plane_masks = nullptr; ctx->coarse_planes = nullptr;
-    if (ctx->planes_host) ctx->pool.hfree(ctx->planes_host);
-    if (ctx->costs_host) ctx->pool.hfree(ctx->costs_host);
-    ctx->planes_host = nullptr; ctx->costs_host = nullptr;
     ctx->have_seeded = false;
-    ctx->have_result = false;
+    if (host_result) {
+        if (ctx->planes_host) ctx->pool.hfree(ctx->planes_host);
+        if (ctx->costs_host) ctx->pool.hfree(ctx->costs_host);
+        ctx->planes_host = nullptr; ctx->costs_host = nullptr;
+        ctx->have_result = false;
+    }
+}
+
+void free_prior(acmmp_ctx *ctx)
+{
+    ctx->pool.dfree(ctx->prior_planes); ctx->pool.dfree(ctx->plane_masks);
+    ctx->prior_planes = nullptr; ctx->plane_masks = nullptr;
+}
+
+void free_views(acmmp_ctx *ctx)
+{
+    free_scratch(ctx, true);
+    free_prior(ctx);
+    ctx->pool.dfree(ctx->planes); ctx->pool.dfree(ctx->costs); ctx->pool.dfree(ctx->coarse_planes);
+    ctx->planes = nullptr;
+    ctx->costs = nullptr;
+    ctx->coarse_planes = nullptr;
+    ctx->parked = false;
 }
 
 void free_depths(acmmp_ctx *ctx)
@@ -569,8 +711,14 @@ int ensure_seeded(acmmp_ctx *ctx)
 {
     if (ctx->have_seeded && ctx->seeded_seed == ctx->seed && ctx->seeded_w == ctx->W && ctx->seeded_h == ctx->H) return ACMMP_OK;
     const auto key = std::make_tuple(ctx->seed, ctx->W, ctx->H);
-    auto it = ctx->seeded_cache.find(key);
-    if (it == ctx->seeded_cache.end()) {
+    DeviceShared &sh = *ctx->pool.shared;
+    uint2 *cached = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(sh.m);
+        auto it = sh.seeded_cache.find(key);
+        if (it != sh.seeded_cache.end()) cached = it->second;
+    }
+    if (!cached) {
         uint2 *buf = nullptr;
         CK(pmalloc(ctx, &buf, sizeof(uint2) * 3 * (size_t)ctx->W * ctx->H));
         std::vector<uint32_t> rows;
@@ -583,9 +731,15 @@ int ensure_seeded(acmmp_ctx *ctx)
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->pool.dfree(rows_dev);
-        it = ctx->seeded_cache.insert(std::make_pair(key, buf)).first;
+        // complete and read-only from here on: the device's table owns it (two contexts racing to build the same key:
+        // the loser's copy goes back to the pool)
+        std::lock_guard<std::mutex> lock(sh.m);
+        auto ins = sh.seeded_cache.insert(std::make_pair(key, buf));
+        if (ins.second) ctx->pool.disown_dev(buf, sh.pool);
+        else ctx->pool.dfree(buf);
+        cached = ins.first->second;
     }
-    ctx->rng_seeded = it->second;
+    ctx->rng_seeded = cached;
     ctx->have_seeded = true;
     ctx->seeded_seed = ctx->seed;
     ctx->seeded_w = ctx->W;
@@ -597,6 +751,7 @@ int check_ready(acmmp_ctx *ctx)
 {
     if (!ctx) return ACMMP_E_ARG;
     if (ctx->n < 2 || !ctx->planes) return fail(ctx, ACMMP_E_ARG, "acmmp_set_views has not been called (need >= 1 source view)");
+    if (ctx->parked) return fail(ctx, ACMMP_E_ARG, "the context is parked: call acmmp_set_views[_device] with the same shapes first");
     if (ctx->params.geom_consistency && (int)ctx->depth_ptrs.size() != ctx->n)
         return fail(ctx, ACMMP_E_ARG, "geom_consistency is set but acmmp_set_depth_maps was not called with one map per view");
     if (ctx->params.planar_prior && !ctx->prior_planes)
@@ -609,6 +764,7 @@ int check_ready(acmmp_ctx *ctx)
 int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_device, const int32_t *widths,
                      const int32_t *heights, const acmmp_camera *cams)
 {
+    Trace tr("set_views");
     if (!ctx || n < 2 || n > kMaxSrc + 1 || !images || !widths || !heights || !cams)
         return fail(ctx, ACMMP_E_ARG, "acmmp_set_views: need 2..33 images");
     for (int i = 0; i < n; ++i) {
@@ -622,8 +778,12 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
     bool same_all = same_shape;
     if (same_shape)
         for (int i = 0; i < n; ++i) same_all = same_all && ctx->widths[i] == widths[i] && ctx->heights[i] == heights[i];
-    if (!same_all) {
-        free_views(ctx);
+    // a parked context re-activated with the shapes it was parked with keeps its stage state (planes, costs, prior,
+    // coarse planes) and only takes scratch again; anything else starts the view from nothing, like a new context
+    const bool resume = ctx->parked && same_all && ctx->planes;
+    if (!same_all || ctx->parked) {
+        if (!resume) free_views(ctx);
+        ctx->parked = false;
         ctx->n = n;
         ctx->W = widths[0];
         ctx->H = heights[0];
@@ -668,15 +828,17 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
         ctx->ref_pitch = (ctx->W + 2 * kRefPad + 3) & ~3;
         CK(pmalloc(ctx, &ctx->ref_dense, sizeof(float) * npx));
         CK(pmalloc(ctx, &ctx->ref_padded, sizeof(float) * (size_t)ctx->ref_pitch * (ctx->H + 2 * kRefPad)));
-        CK(pmalloc(ctx, &ctx->planes, sizeof(float4) * npx));
+        if (!resume) {
+            CK(pmalloc(ctx, &ctx->planes, sizeof(float4) * npx));
+            CK(pmalloc(ctx, &ctx->costs, sizeof(float) * npx));
+            CK(cudaMemsetAsync(ctx->planes, 0, sizeof(float4) * npx, ctx->stream));
+            CK(cudaMemsetAsync(ctx->costs, 0, sizeof(float) * npx, ctx->stream));
+        }
         CK(pmalloc(ctx, &ctx->planes_alt, sizeof(float4) * npx));
-        CK(pmalloc(ctx, &ctx->costs, sizeof(float) * npx));
         CK(pmalloc(ctx, &ctx->costs_alt, sizeof(float) * npx));
         CK(pmalloc(ctx, &ctx->pre_costs, sizeof(float) * npx));
         CK(pmalloc(ctx, &ctx->selected_views, sizeof(uint32_t) * npx));
         CK(pmalloc(ctx, &ctx->rng, sizeof(uint2) * 3 * npx));
-        CK(cudaMemsetAsync(ctx->planes, 0, sizeof(float4) * npx, ctx->stream));
-        CK(cudaMemsetAsync(ctx->costs, 0, sizeof(float) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->pre_costs, 0, sizeof(float) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->selected_views, 0, sizeof(uint32_t) * npx, ctx->stream));
         // the pinned result buffers are allocated on the first download (ensure_host_result): a resident chain that
@@ -688,6 +850,7 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
         rc = make_tmap(ctx, &ctx->tmap_tp, TGt::PW, TGt::RH);
         if (rc) return rc;
     }
+    tr.mark("alloc");
     ctx->cams.assign(cams, cams + n);
     for (int i = 0; i < n; ++i) {
         ctx->cams[i].width = widths[i];
@@ -742,14 +905,18 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
     ctx->params.disparity_min = ctx->cams[0].K[0] * ctx->params.baseline / ctx->params.depth_max;
     ctx->params.disparity_max = ctx->cams[0].K[0] * ctx->params.baseline / ctx->params.depth_min;
     ctx->ncc = ncc_table(ctx);
+    tr.mark("enqueue");
     int rc = upload_view_consts(ctx);
     if (rc) return rc;
-    return configure_kernels(ctx);
+    rc = configure_kernels(ctx);
+    tr.mark("consts");
+    return rc;
 }
 
 int set_depths_common(acmmp_ctx *ctx, int n, const float *const *maps, bool on_device, const int32_t *widths,
                       const int32_t *heights)
 {
+    Trace tr("set_depths");
     if (!ctx || n != ctx->n || !maps || !widths || !heights)
         return fail(ctx, ACMMP_E_ARG, "acmmp_set_depth_maps: one map per view (after acmmp_set_views)");
     // A null / empty neighbour map would make geom_address clamp to texel -1 of a null base (the file-chained host
@@ -992,6 +1159,7 @@ int acmmp_abi_sizeof_params(void) { return (int)sizeof(acmmp_params); }
 
 int acmmp_create(acmmp_ctx **out, int device)
 {
+    Trace tr("create");
     if (!out) return ACMMP_E_ARG;
     *out = nullptr;
     int count = 0;
@@ -1005,10 +1173,19 @@ int acmmp_create(acmmp_ctx **out, int device)
     if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
     acmmp_ctx *ctx = new acmmp_ctx();
     ctx->device = device;
+    ctx->pool.shared = &device_shared(device);
+    {
+        std::lock_guard<std::mutex> lock(ctx->pool.shared->m);
+        ctx->pool.shared->live++;
+    }
     ctx->num_sms = prop.multiProcessorCount;
     acmmp_default_params(&ctx->params);
     if (const char *e = std::getenv("ACMMP_NO_TMA")) ctx->use_tma = (e[0] == '1') ? 0 : 1;   // debug aid
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        {
+            std::lock_guard<std::mutex> lock(ctx->pool.shared->m);
+            ctx->pool.shared->live--;
+        }
         delete ctx;
         return ACMMP_E_CUDA;
     }
@@ -1026,7 +1203,18 @@ int acmmp_destroy(acmmp_ctx *ctx)
     free_depths(ctx);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
     for (auto &pe : ctx->pass_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
-    ctx->pool.release_all();
+    {
+        // the stream is idle: the free blocks go to the device's pool for the other contexts; the last context of a
+        // device returns everything to the driver
+        DeviceShared &sh = *ctx->pool.shared;
+        std::lock_guard<std::mutex> lock(sh.m);
+        ctx->pool.give_free_to(sh.pool);
+        if (--sh.live == 0) {
+            sh.pool.release_all();
+            sh.seeded_cache.clear();
+        }
+    }
+    ctx->pool.release_all();               // anything still registered here was not returned by its owner
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ACMMP_OK;
@@ -1092,6 +1280,28 @@ int acmmp_reset_modes(acmmp_ctx *ctx)
     ctx->params.hierarchy = 0;
     ctx->params.upsample = 0;
     ctx->params.max_iterations = 3;
+    return ACMMP_OK;
+}
+
+int acmmp_park(acmmp_ctx *ctx, int keep_prior, int keep_host_result)
+{
+    if (!ctx) return ACMMP_E_ARG;
+    if (!ctx->planes) return fail(ctx, ACMMP_E_ARG, "acmmp_park: no views on this context");
+    Trace tr("park");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_scratch(ctx, !keep_host_result);
+    if (!keep_prior) {
+        free_prior(ctx);
+        ctx->params.planar_prior = 0;
+    }
+    free_depths(ctx);
+    ctx->params.geom_consistency = ctx->params.multi_geometry = 0;
+    ctx->parked = true;
+    {
+        std::lock_guard<std::mutex> lock(ctx->pool.shared->m);
+        ctx->pool.give_free_to(ctx->pool.shared->pool);
+    }
     return ACMMP_OK;
 }
 
@@ -1185,6 +1395,7 @@ PriorCam prior_cam(const acmmp_ctx *ctx)
 
 int acmmp_support_points(acmmp_ctx *ctx, int32_t *xy, int capacity, int *n)
 {
+    Trace tr("support_points");
     if (!ctx || !ctx->planes || !xy || !n) return fail(ctx, ACMMP_E_ARG, "acmmp_support_points: bad arguments");
     CK(cudaSetDevice(ctx->device));
     const int cells_x = (ctx->W + 4) / 5, cells_y = (ctx->H + 4) / 5, ncell = cells_x * cells_y;
@@ -1225,6 +1436,7 @@ int acmmp_download_prior(acmmp_ctx *ctx, float *prior_planes4, uint32_t *plane_m
 
 int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int n_tri)
 {
+    Trace tr("prior_from_triangles");
     if (!ctx || !ctx->planes || n_tri < 0 || (n_tri > 0 && !tri_xy))
         return fail(ctx, ACMMP_E_ARG, "acmmp_planar_prior_from_triangles: bad arguments");
     for (int i = 0; i < 6 * n_tri; i += 2) {
@@ -1232,31 +1444,41 @@ int acmmp_planar_prior_from_triangles(acmmp_ctx *ctx, const int32_t *tri_xy, int
             return fail(ctx, ACMMP_E_ARG, "acmmp_planar_prior_from_triangles: triangle vertex outside the image");
     }
     CK(cudaSetDevice(ctx->device));
+    tr.mark("check");
     const int npx = ctx->W * ctx->H;
     const PriorCam cam = prior_cam(ctx);
-    int *tri_dev = nullptr;
+    // temporaries sized by the shape, not by this call's triangle count (support points sit one per 5x5 cell, a
+    // triangulation of n points has < 2 n triangles): the pool hands the same blocks back for every view of a level
+    const size_t cap = std::max((size_t)n_tri, 2 * (size_t)((ctx->W + 4) / 5) * (size_t)((ctx->H + 4) / 5));
+    int *tri_dev = nullptr, *long_list = nullptr, *long_items = nullptr;
     float4 *params_dev = nullptr;
     uint32_t *mask_dev = nullptr;
-    CK(pmalloc(ctx, &tri_dev, sizeof(int) * 6 * (size_t)std::max(n_tri, 1)));
-    CK(pmalloc(ctx, &params_dev, sizeof(float4) * (size_t)std::max(n_tri, 1)));
-    CK(pmalloc(ctx, &mask_dev, sizeof(uint32_t) * (size_t)npx));
+    PoolTemps tmp(ctx);
+    CK(tmp.d(&tri_dev, sizeof(int) * 6 * cap));
+    CK(tmp.d(&params_dev, sizeof(float4) * cap));
+    CK(tmp.d(&mask_dev, sizeof(uint32_t) * (size_t)npx));
+    const int list_capacity = (int)cap + 65536;
+    CK(tmp.d(&long_list, sizeof(int) * (size_t)list_capacity));
+    CK(tmp.d(&long_items, sizeof(int)));
     if (!ctx->prior_planes) CK(pmalloc(ctx, &ctx->prior_planes, sizeof(float4) * (size_t)npx));
     if (!ctx->plane_masks) CK(pmalloc(ctx, &ctx->plane_masks, sizeof(uint32_t) * (size_t)npx));
+    tr.mark("alloc");
     CK(cudaMemsetAsync(mask_dev, 0, sizeof(uint32_t) * (size_t)npx, ctx->stream));
+    CK(cudaMemsetAsync(long_items, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(long_list, 0xFF, sizeof(int) * (size_t)list_capacity, ctx->stream));
     if (n_tri > 0) {
         CK(cudaMemcpyAsync(tri_dev, tri_xy, sizeof(int) * 6 * (size_t)n_tri, cudaMemcpyHostToDevice, ctx->stream));
         k_tri_planes<<<(n_tri + 255) / 256, 256, 0, ctx->stream>>>(tri_dev, n_tri, ctx->planes, cam, params_dev);
-        k_tri_raster<<<(n_tri + 127) / 128, 128, 0, ctx->stream>>>(tri_dev, n_tri, ctx->W, mask_dev);
-        k_tri_raster_long<<<(n_tri + 3) / 4, 128, 0, ctx->stream>>>(tri_dev, n_tri, ctx->W, mask_dev);
+        k_tri_raster<<<(n_tri + 127) / 128, 128, 0, ctx->stream>>>(tri_dev, n_tri, ctx->W, mask_dev, long_list, list_capacity, long_items);
+        k_tri_raster_long<<<148 * 8, kRasterChunk, 0, ctx->stream>>>(tri_dev, ctx->W, mask_dev, long_list, list_capacity, long_items);
         ctx->launches += 3;
     }
     k_prior_finish<<<(npx + 255) / 256, 256, 0, ctx->stream>>>(mask_dev, params_dev, cam, ctx->prior_planes, ctx->plane_masks);
     ctx->launches++;
     CK(cudaGetLastError());
+    tr.mark("enqueue");
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->pool.dfree(tri_dev);
-    ctx->pool.dfree(params_dev);
-    ctx->pool.dfree(mask_dev);
+    tr.mark("wait");
     ctx->params.planar_prior = 1;
     return ACMMP_OK;
 }
@@ -1279,6 +1501,7 @@ int acmmp_next_level_device(acmmp_ctx *ctx, int n, const float *const *images_de
 static int next_level_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_device, const int32_t *widths,
                              const int32_t *heights, const acmmp_camera *cams)
 {
+    Trace tr("next_level");
     if (!ctx || !ctx->planes) return fail(ctx, ACMMP_E_ARG, "acmmp_next_level: no previous level on this context");
     CK(cudaSetDevice(ctx->device));
     const int sw = ctx->W, sh = ctx->H, snpx = sw * sh;
@@ -1290,8 +1513,10 @@ static int next_level_common(acmmp_ctx *ctx, int n, const float *const *images, 
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    tr.mark("coarse");
     acmmp_reset_modes(ctx);
     int rc = set_views_common(ctx, n, images, on_device, widths, heights, cams);      // re-allocates at the new size
+    tr.mark("set_views");
     if (rc) { ctx->pool.dfree(coarse); ctx->pool.dfree(coarse_depth); return rc; }
     const int npx = ctx->W * ctx->H;
     const int Imagescale = std::max(ctx->H / sh, ctx->W / sw);
@@ -1314,6 +1539,7 @@ static int next_level_common(acmmp_ctx *ctx, int n, const float *const *images, 
         cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ctx->t_jbu, e0, e1);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
+        tr.mark("jbu_wait");
         ctx->launches++;
         if (rc) { ctx->pool.dfree(coarse); ctx->pool.dfree(coarse_depth); ctx->pool.dfree(fine_depth); return fail(ctx, rc, "JBU failed"); }
     }
@@ -1375,6 +1601,7 @@ int acmmp_finalize(acmmp_ctx *ctx) { return do_finalize(ctx); }
 
 int acmmp_synchronize(acmmp_ctx *ctx)
 {
+    Trace tr("synchronize");
     if (!ctx) return ACMMP_E_ARG;
     CK(cudaSetDevice(ctx->device));
     return collect_timings(ctx);
@@ -1417,6 +1644,7 @@ int acmmp_run_patch_match_resident(acmmp_ctx *ctx) { return ctx ? run_stage(ctx,
 
 int acmmp_download_result(acmmp_ctx *ctx)
 {
+    Trace tr("download_result");
     if (!ctx || !ctx->planes) return ACMMP_E_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)ctx->W * ctx->H;
@@ -1450,6 +1678,7 @@ int acmmp_device_buffers(acmmp_ctx *ctx, void **planes4_dev, void **costs_dev)
 
 int acmmp_export_depth_device(acmmp_ctx *ctx, float *depth_dev)
 {
+    Trace tr("export_depth");
     if (!ctx || !ctx->planes || !depth_dev) return ACMMP_E_ARG;
     CK(cudaSetDevice(ctx->device));
     const int npx = ctx->W * ctx->H;
@@ -1470,6 +1699,7 @@ int acmmp_export_depth_device_sync(acmmp_ctx *ctx, float *depth_dev)
 int acmmp_download_state(acmmp_ctx *ctx, float *planes4, float *costs, uint32_t *selected_views, uint32_t *rand6,
                          float *pre_costs)
 {
+    if (ctx && ctx->parked) return fail(ctx, ACMMP_E_ARG, "the context is parked");
     if (!ctx || !ctx->planes) return ACMMP_E_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)ctx->W * ctx->H;
@@ -1485,6 +1715,7 @@ int acmmp_download_state(acmmp_ctx *ctx, float *planes4, float *costs, uint32_t 
 int acmmp_upload_state(acmmp_ctx *ctx, const float *planes4, const float *costs, const uint32_t *selected_views,
                        const uint32_t *rand6, const float *pre_costs)
 {
+    if (ctx && ctx->parked) return fail(ctx, ACMMP_E_ARG, "the context is parked");
     if (!ctx || !ctx->planes) return ACMMP_E_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)ctx->W * ctx->H;

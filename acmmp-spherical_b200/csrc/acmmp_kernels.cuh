@@ -1532,10 +1532,12 @@ k_tri_planes(const int *__restrict__ tri, const int n_tri, const float4 *__restr
 
 // The reference's barycentric stepping rasteriser (main.cpp:153-159); the sequential loop lets a later triangle
 // overwrite an earlier one, i.e. the largest id wins: atomicMax.  Triangles up to kRasterSmall pixels of longest edge
-// (the bulk: support points sit on a 5-pixel grid) take one thread each; the few long ones along image borders and
-// across texture-less regions (10^5 .. 10^6 steps each -- on one thread they dominated the stage) take a warp each:
-// lane l walks the outer-loop iterations l, l + 32, ...  The outer variable is the reference's running float sum
-// (p += step), so a lane reaches its iteration by the same sequence of additions.
+// (the bulk: support points sit on a 5-pixel grid) take one thread each and the pass appends the others to a list: the
+// long ones along image borders and across texture-less regions are 10^5 .. 10^7 steps each (L^2 / 2 for a longest
+// edge of L pixels) -- on one thread, and then on one warp, they WERE the stage (66 ms per 3200x2130 view).  They are
+// now spread over the whole grid: work item = (long triangle, chunk of kRasterChunk consecutive outer-loop iterations),
+// one thread per outer iteration, items dealt to the blocks round-robin.  The outer variable is the reference's running
+// float sum (p += step), so a thread reaches its iteration by the same sequence of additions.
 constexpr float kRasterSmall = 48.0f;
 
 struct RasterTri {
@@ -1569,28 +1571,44 @@ __device__ __forceinline__ void raster_row(const RasterTri &r, const float p, co
     }
 }
 
+constexpr int kRasterChunk = 256;          // outer iterations per work item = threads per block of k_tri_raster_long
+
+// long_list: cleared to -1 by the caller; long_items: 0.  A triangle whose items do not fit the list any more (thousands
+// of image-sized slivers) is rasterised by its own thread, its reserved slots stay -1.
 __global__ void __launch_bounds__(128)
-k_tri_raster(const int *__restrict__ tri, const int n_tri, const int W, uint32_t *__restrict__ mask)
+k_tri_raster(const int *__restrict__ tri, const int n_tri, const int W, uint32_t *__restrict__ mask, int *__restrict__ long_list,
+             const int list_capacity, int *__restrict__ long_items)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tri) return;
     const RasterTri r = raster_setup(tri, t);
-    if (r.max_edge > kRasterSmall) return;               // k_tri_raster_long
+    if (r.max_edge > kRasterSmall) {
+        // outer iterations: p = 0, step, 2 step, ... < 1  =>  at most ceil(max_edge) + 1 of them (step = 1 / max_edge in
+        // float; the running sum may undershoot 1 once more); an item past the end finds nothing to do
+        const int chunks = ((int)r.max_edge + 2 + kRasterChunk - 1) / kRasterChunk;
+        const int first = atomicAdd(long_items, chunks);
+        if (chunks <= 64 && first + chunks <= list_capacity) {
+            for (int c = 0; c < chunks; ++c) long_list[first + c] = t * 64 + c;
+            return;
+        }
+    }
     for (float p = 0; (double)p < 1.0; p = __fadd_rn(p, r.step)) raster_row(r, p, W, (uint32_t)(t + 1), mask);
 }
 
-__global__ void __launch_bounds__(128)
-k_tri_raster_long(const int *__restrict__ tri, const int n_tri, const int W, uint32_t *__restrict__ mask)
+__global__ void __launch_bounds__(kRasterChunk)
+k_tri_raster_long(const int *__restrict__ tri, const int W, uint32_t *__restrict__ mask, const int *__restrict__ long_list,
+                  const int list_capacity, const int *__restrict__ long_items)
 {
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (t >= n_tri) return;
-    const RasterTri r = raster_setup(tri, t);
-    if (!(r.max_edge > kRasterSmall)) return;
-    float p = 0;
-    for (int i = 0; i < lane && (double)p < 1.0; ++i) p = __fadd_rn(p, r.step);
-    while ((double)p < 1.0) {
-        raster_row(r, p, W, (uint32_t)(t + 1), mask);
-        for (int i = 0; i < 32 && (double)p < 1.0; ++i) p = __fadd_rn(p, r.step);
+    const int n_items = min(*long_items, list_capacity);
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int item = long_list[w];
+        if (item < 0) continue;
+        const int t = item >> 6, chunk = item & 63;
+        const RasterTri r = raster_setup(tri, t);
+        const int it = chunk * kRasterChunk + threadIdx.x;
+        float p = 0;
+        for (int i = 0; i < it && (double)p < 1.0; ++i) p = __fadd_rn(p, r.step);
+        if ((double)p < 1.0) raster_row(r, p, W, (uint32_t)(t + 1), mask);
     }
 }
 

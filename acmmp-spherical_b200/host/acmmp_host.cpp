@@ -175,8 +175,12 @@ void ACMMP::SetViewsDevice(const std::vector<const float *> &images_dev, const s
                            const std::vector<Camera> &cameras, bool next_level, const cv::Mat_<float> *ref_host)
 {
     const int n = (int)images_dev.size();
+    // (ref_host == nullptr: the host copy of the reference image stays what it was -- a re-activation after Park())
+    cv::Mat_<float> ref_image;
+    if (ref_host) ref_image = *ref_host;
+    else if (!images_.empty()) ref_image = std::move(images_[0]);
     images_.assign((size_t)n, cv::Mat_<float>());
-    if (ref_host) images_[0] = *ref_host;
+    images_[0] = std::move(ref_image);
     cameras_ = cameras;
     std::vector<int32_t> ws(widths.begin(), widths.end()), hs(heights.begin(), heights.end());
     params_.depth_min = cameras_[0].depth_min * 0.6f;
@@ -197,6 +201,14 @@ void ACMMP::ResetModes()
     check(acmmp_reset_modes(ctx_), "ResetModes");
     params_.geom_consistency = params_.multi_geometry = params_.planar_prior = params_.hierarchy = 0;
     params_.max_iterations = 3;
+}
+
+void ACMMP::Park(bool keep_prior, bool keep_host_result)
+{
+    check(acmmp_park(ctx_, keep_prior ? 1 : 0, keep_host_result ? 1 : 0), "Park");
+    params_.geom_consistency = params_.multi_geometry = 0;
+    if (!keep_prior) params_.planar_prior = 0;
+    if (!keep_host_result) planes_host_ = costs_host_ = nullptr;
 }
 
 void ACMMP::SetNeighbourDepthMapsDevice(const std::vector<const float *> &maps_dev, const std::vector<int> &widths,

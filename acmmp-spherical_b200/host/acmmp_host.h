@@ -138,6 +138,10 @@ public:
     void SetViewsDevice(const std::vector<const float *> &images_dev, const std::vector<int> &widths, const std::vector<int> &heights,
                         const std::vector<Camera> &cameras, bool next_level, const cv::Mat_<float> *ref_host = nullptr);
     void ResetModes();                                   // flags of a freshly constructed object, views kept
+    // Between two stages of a resident view: everything but the stage state (planes, costs, coarse planes) goes back to
+    // the device's pool for the next view's stage (acmmp_park); SetViewsDevice(..., next_level = false) with the same
+    // shapes takes it up again.  keep_host_result: GetPlaneHypothesis / GetCost stay readable (a writer thread's input).
+    void Park(bool keep_prior = false, bool keep_host_result = false);
     // depth maps of the SOURCE views for the geometric term (device pointers); the reference view's own map is the
     // state on the device (acmmp_set_depth_maps_device with maps[0] == NULL)
     void SetNeighbourDepthMapsDevice(const std::vector<const float *> &maps_dev, const std::vector<int> &widths,

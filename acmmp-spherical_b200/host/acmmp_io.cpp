@@ -14,6 +14,7 @@
 
 #ifdef ACMMP_WITH_NVJPEG
 #include <cuda_runtime.h>
+#include <mutex>
 #include <nvjpeg.h>
 #endif
 
@@ -219,6 +220,9 @@ bool jpeg_size(const std::vector<unsigned char> &b, int &w, int &h)
 #ifdef ACMMP_WITH_NVJPEG
 bool decode_jpeg_luma(const std::vector<unsigned char> &b, cv::Mat_<float> &image)
 {
+    // one decoder state for the process: the device threads of a multi-GPU run load their views at the same time
+    static std::mutex decoder_mutex;
+    std::lock_guard<std::mutex> lock(decoder_mutex);
     static nvjpegHandle_t handle = nullptr;
     static nvjpegJpegState_t state = nullptr;
     if (!handle) {

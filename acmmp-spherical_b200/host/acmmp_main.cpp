@@ -335,8 +335,8 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         for (size_t v = 0; v < num_images; ++v)
             if (need[v] && device_of(v) != d) remote[d].push_back(v);
     }
-    std::vector<cv::Mat_<float>> level_image(num_images);
-    std::vector<Camera> level_camera(num_images);
+    std::vector<cv::Mat_<float>> level_image(num_images), next_image(num_images);
+    std::vector<Camera> level_camera(num_images), next_camera(num_images);
     std::vector<int> level_w(num_images, 0), level_h(num_images, 0);
     PhaseBarrier barrier(ndev);
     std::mutex stats_mutex;
@@ -364,6 +364,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             t_exchange += now_s() - t0;
         };
         std::vector<std::future<void>> writers;             // .dmb output of finished views
+        std::future<void> prefetch;                         // the next level's images of this thread's views
         std::vector<DeviceMap> pool(num_images);            // level images on this device
         std::vector<size_t> needed;                         // my views and their source views
         {
@@ -391,8 +392,16 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (!barrier.wait()) return;
             // every view of this level, read and scaled once (each thread its share, all of them shared afterwards)
             double tp = now_s();
+            if (prefetch.valid()) {
+                prefetch.get();                                // read and scaled beside the previous level's kernels
+                for (size_t i : mine) {
+                    level_image[i] = std::move(next_image[i]);
+                    level_camera[i] = next_camera[i];
+                }
+            } else {
+                for (size_t i : mine) LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].cur_image_size, level_image[i], level_camera[i]);
+            }
             for (size_t i : mine) {
-                LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].cur_image_size, level_image[i], level_camera[i]);
                 level_w[i] = level_image[i].cols;
                 level_h[i] = level_image[i].rows;
             }
@@ -409,7 +418,31 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (cudaStreamSynchronize(0) != cudaSuccess) throw std::runtime_error("upload of the level images failed");
             t_views += now_s() - tp;
             t_upload += now_s() - tp;
+            if (level + 1 < levels) {
+                // the next level's images of this thread's views: file read / decode / bilinear scaling on a host thread
+                // while this one drives the device (every view has the same number of levels here, see the top)
+                const int next_shift = max_num_downscale - level - 1;
+                prefetch = std::async(std::launch::async, [&, next_shift]() {
+                    for (size_t i : mine)
+                        LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].max_image_size / (1 << next_shift), next_image[i], next_camera[i]);
+                });
+            }
 
+            // (re-)activate view i on its context: its image and its source views' images out of the level pool
+            auto activate = [&](const size_t i, const bool next_level, const bool fresh = false) {
+                const Problem &problem = problems[i];
+                std::vector<const float *> images{pool[i].ptr};
+                std::vector<int> ws{level_w[i]}, hs{level_h[i]};
+                std::vector<Camera> cameras{level_camera[i]};
+                for (int id : problem.src_image_ids) {
+                    const size_t s = index_of.at(id);
+                    images.push_back(pool[s].ptr);
+                    ws.push_back(level_w[s]);
+                    hs.push_back(level_h[s]);
+                    cameras.push_back(level_camera[s]);
+                }
+                objs[i]->SetViewsDevice(images, ws, hs, cameras, next_level, fresh ? &level_image[i] : nullptr);
+            };
             struct PriorJob {
                 std::future<void> done;
                 std::vector<cv::Point> support;
@@ -424,6 +457,9 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 double tw = now_s();
                 pending[v]->done.get();                        // rethrows a worker exception
                 t_join += now_s() - tw;
+                tw = now_s();
+                activate(v, false);                            // parked after its photometric stage
+                t_views += now_s() - tw;
                 tw = now_s();
                 if (g_gpu_prior) {
                     a.CudaPlanarPriorFromTriangles(pending[v]->inside);
@@ -449,6 +485,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 tw = now_s();
                 dtab[d][v].fit(width, height, full_px[v]);
                 a.ExportDepthDevice(dtab[d][v].ptr);
+                a.Park();                                      // the next view's stage runs in this one's scratch
                 t_export += now_s() - tw;
             };
             const double t_s1 = now_s();
@@ -456,16 +493,6 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             for (size_t i : mine) {                                                  // photometric + prior stage
                 const Problem &problem = problems[i];
                 std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << "..." << std::endl;
-                std::vector<const float *> images{pool[i].ptr};
-                std::vector<int> ws{level_w[i]}, hs{level_h[i]};
-                std::vector<Camera> cameras{level_camera[i]};
-                for (int id : problem.src_image_ids) {
-                    const size_t s = index_of.at(id);
-                    images.push_back(pool[s].ptr);
-                    ws.push_back(level_w[s]);
-                    hs.push_back(level_h[s]);
-                    cameras.push_back(level_camera[s]);
-                }
                 tp = now_s();
                 if (first_level) {
                     objs[i].reset(new ACMMP(g_device + d));
@@ -473,7 +500,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     t_ctx += now_s() - tp;
                 }
                 ACMMP &acmmp = *objs[i];
-                acmmp.SetViewsDevice(images, ws, hs, cameras, !first_level, &level_image[i]);
+                activate(i, !first_level, true);
                 t_views += now_s() - tp;
                 tp = now_s();
                 acmmp.RunPatchMatchResident(!g_gpu_prior);                           // the CPU prior stage reads the result
@@ -513,6 +540,8 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                         PlanarPriorStage(*obj, depths, job->mask_tri, job->planeParams_tri);        // adds its time to g_prior_s
                     });
                 }
+                // only the stage state stays with the view (CPU prior stage: and the host copy its worker reads)
+                acmmp.Park(false, !g_gpu_prior);
                 if (previous != (size_t)-1) finish_view(previous);
                 previous = i;
             }
@@ -527,6 +556,9 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 for (size_t i : mine) {
                     const Problem &problem = problems[i];
                     ACMMP &acmmp = *objs[i];
+                    double ta = now_s();
+                    activate(i, false);
+                    t_views += now_s() - ta;
                     acmmp.ResetModes();
                     acmmp.SetGeomConsistencyParams(multi_geometry);
                     std::vector<const float *> maps;
@@ -548,6 +580,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     tg = now_s();
                     gtab[d][i].fit(acmmp.GetReferenceImageWidth(), acmmp.GetReferenceImageHeight(), full_px[i]);
                     acmmp.ExportDepthDevice(gtab[d][i].ptr);
+                    acmmp.Park(false, last);                   // the writer below reads the host copy, then lets it go too
                     t_export += now_s() - tg;
                     tg = now_s();
                     if (last) {
@@ -572,6 +605,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                             writeDepthDmb(result_folder + "/depths_geom.dmb", depths);
                             writeNormalDmb(result_folder + "/normals.dmb", normals);
                             writeDepthDmb(result_folder + "/costs.dmb", costs);
+                            obj->Park();                       // the pinned result buffers serve the next view's download
                         }));
                         std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << " done!" << std::endl;
                     }

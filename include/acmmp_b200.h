@@ -109,6 +109,17 @@ int acmmp_get_params(const acmmp_ctx *ctx, acmmp_params *out);
  * keeping the uploaded views: lets one context serve consecutive stages of the same view and level
  * (the reference constructs a new ACMMP object per stage and re-uploads everything, main.cpp:83-93). */
 int acmmp_reset_modes(acmmp_ctx *ctx);
+/* Between two stages of a view that stays resident: give every buffer except the stage state back to the device's pool
+ * (textures, padded reference, ping-pong / per-stage buffers, RNG states, neighbour depth-map table -- ~1 GB of the
+ * ~1.15 GB a 3200x2130 view with 10 source views holds) so that the NEXT view's stage takes the same blocks instead of
+ * allocating its own.  What stays: planes + costs, the coarse planes of the hierarchy hand-over, with keep_prior != 0 the
+ * planar prior (planes + mask) and with keep_host_result != 0 the pinned result buffers acmmp_result_host points into.
+ * Waits for the context's stream.  The reference's counterpart is ~ACMMP() between stages (ACMMP.cpp:101-143), which
+ * frees everything because the state travels through .dmb files.  To go on: acmmp_set_views[_device] with the same shapes
+ * (re-uploads the images, keeps the state; other shapes start the view afresh), then the mode setters, neighbour depth
+ * maps and acmmp_run_patch_match* as usual.  acmmp_support_points, acmmp_planar_prior_from_triangles,
+ * acmmp_export_depth_device, acmmp_download_result and acmmp_next_level* work on a parked context. */
+int acmmp_park(acmmp_ctx *ctx, int keep_prior, int keep_host_result);
 
 /* Geometric consistency inputs: the n depth maps (index 0 = reference view, 1.. = source views)
  * that InuputInitialization reads from depths.dmb / depths_geom.dmb (ACMMP.cpp:653-678) and

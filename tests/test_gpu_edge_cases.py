@@ -215,3 +215,60 @@ def test_device_planar_prior_against_the_numpy_twin(model):
     assert abs(res["masked_mine"] - res["masked_twin"]) < 0.02 and res["masked_both"] > 0.9 * res["masked_twin"], res
     assert res["same_plane_where_both"] > 0.6, res
     assert res["disagreeing_planes_found_in_twin_set"] > 0.99, res
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("stage", ["geom", "prior"])
+def test_parked_context_resumes_bit_identically(stage):
+    """acmmp_park between two stages of a resident view (the scratch goes to the device's pool, another context runs in it,
+    the view is re-activated with acmmp_set_views of the same shapes): the second stage gives the bits it gives on a
+    context that never let go of anything."""
+    from acmmp_b200 import Context, synth
+    scene = synth.make_pinhole_scene(n_views=4, width=320, height=240, focal=260.0, seed=5)
+    imgs, cams, ids = scene.problem(0)
+    other_imgs, other_cams, _ = scene.problem(1)
+    neighbours = [None] + [scene.depths_gt[i] for i in ids[1:]]
+    H, W = imgs[0].shape
+
+    def second_stage(ctx, pts=None):
+        if stage == "geom":
+            ctx.reset_modes()
+            ctx.set_geom_consistency(False)
+            ctx.set_depth_maps(neighbours)
+        else:
+            ctx.set_planar_prior()
+            pts = ctx.support_points() if pts is None else pts
+            assert len(pts) > 50
+            from acmmp_b200.scene import delaunay_triangles_inside
+            ctx.planar_prior_from_triangles(delaunay_triangles_inside(pts, W, H))
+        ctx.run_patch_match()
+        return ctx.get_result()
+
+    plain = Context(0)
+    plain.set_seed(SEED)
+    plain.set_views(imgs, cams)
+    plain.run_patch_match(download=False)
+    p0, c0 = second_stage(plain)
+    plain.close()
+
+    a = Context(0)
+    a.set_seed(SEED)
+    a.set_views(imgs, cams)
+    a.run_patch_match(download=False)
+    a.park()
+    with pytest.raises(RuntimeError):
+        a.run_patch_match(download=False)                       # parked: no scratch to run in
+    pts = a.support_points() if stage == "prior" else None      # reads the state only: works on a parked context
+    b = Context(0)                                              # another view takes the blocks a let go of
+    b.set_seed(SEED + 1)
+    b.set_views(other_imgs, other_cams)
+    b.run_patch_match(download=False)
+    b.park()
+    a.set_views(imgs, cams)                                     # same shapes: the state is kept
+    p1, c1 = second_stage(a, pts)
+    a.close()
+    b.close()
+    assert np.array_equal(_bits(p0), _bits(p1)) and np.array_equal(_bits(c0), _bits(c1))

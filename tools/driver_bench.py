@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--focal", type=float, default=2800.0)
     ap.add_argument("--out", default="")
     ap.add_argument("--skip-files", action="store_true", help="only the resident schedules (no bit comparison)")
+    ap.add_argument("--no-fusion", action="store_true", help="pass --fusion 0 to the driver")
+    ap.add_argument("--trace", default="", help="prefix: the driver's stderr (ACMMP_TRACE=1 table) goes to <prefix>_<variant>.txt")
     a = ap.parse_args()
     from acmmp_b200 import synth
     scene = synth.make_pinhole_scene(n_views=a.views, width=a.width, height=a.height, focal=a.focal, seed=2)
@@ -50,8 +52,10 @@ def main():
         if name != "files":
             shutil.copytree(base, folders[name])
         t0 = time.time()
-        r = subprocess.run([str(DRIVER), str(folders[name]), "--seed", "11", "--resident", resident, "--gpu-prior", gpu_prior],
-                           capture_output=True, text=True)
+        r = subprocess.run([str(DRIVER), str(folders[name]), "--seed", "11", "--resident", resident, "--gpu-prior", gpu_prior]
+                           + (["--fusion", "0"] if a.no_fusion else []), capture_output=True, text=True)
+        if a.trace:
+            open(f"{a.trace}_{name}.txt", "w").write(r.stderr)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         res[name] = json.loads(r.stdout.strip().splitlines()[-1])
         res[name]["process_wall_s"] = time.time() - t0
