@@ -498,9 +498,9 @@ void free_scratch(acmmp_ctx *ctx, bool host_result)
     ctx->pool.dfree(ctx->ref_padded); ctx->ref_padded = nullptr;
     ctx->pool.dfree(ctx->views_dev); ctx->views_dev = nullptr;
     ctx->pool.dfree(ctx->planes_alt); ctx->pool.dfree(ctx->costs_alt);
-    ctx->pool.dfree(ctx->pre_costs); ctx->pool.dfree(ctx->selected_views); ctx->pool.dfree(ctx->rng);
+    ctx->pool.dfree(ctx->selected_views); ctx->pool.dfree(ctx->rng);
     ctx->planes_alt = nullptr;
-    ctx->costs_alt = ctx->pre_costs = nullptr;
+    ctx->costs_alt = nullptr;
     ctx->selected_views = nullptr;
     ctx->rng = ctx->rng_seeded = nullptr;
     ctx->have_seeded = false;
@@ -522,9 +522,12 @@ void free_views(acmmp_ctx *ctx)
 {
     free_scratch(ctx, true);
     free_prior(ctx);
-    ctx->pool.dfree(ctx->planes); ctx->pool.dfree(ctx->costs); ctx->pool.dfree(ctx->coarse_planes);
+    // the stage state: planes + costs, and what a stage leaves for the NEXT stage of the same reference object -- the
+    // costs of the uploaded planes that the hierarchy's acceptance test reads (pre_costs_cuda: written by the photometric
+    // stage's initialisation, read by its passes AND by the prior stage's, ACMMP.cu:770-771, :1318-1322), the coarse planes
+    ctx->pool.dfree(ctx->planes); ctx->pool.dfree(ctx->costs); ctx->pool.dfree(ctx->pre_costs); ctx->pool.dfree(ctx->coarse_planes);
     ctx->planes = nullptr;
-    ctx->costs = nullptr;
+    ctx->costs = ctx->pre_costs = nullptr;
     ctx->coarse_planes = nullptr;
     ctx->parked = false;
 }
@@ -831,15 +834,15 @@ int set_views_common(acmmp_ctx *ctx, int n, const float *const *images, bool on_
         if (!resume) {
             CK(pmalloc(ctx, &ctx->planes, sizeof(float4) * npx));
             CK(pmalloc(ctx, &ctx->costs, sizeof(float) * npx));
+            CK(pmalloc(ctx, &ctx->pre_costs, sizeof(float) * npx));
             CK(cudaMemsetAsync(ctx->planes, 0, sizeof(float4) * npx, ctx->stream));
             CK(cudaMemsetAsync(ctx->costs, 0, sizeof(float) * npx, ctx->stream));
+            CK(cudaMemsetAsync(ctx->pre_costs, 0, sizeof(float) * npx, ctx->stream));
         }
         CK(pmalloc(ctx, &ctx->planes_alt, sizeof(float4) * npx));
         CK(pmalloc(ctx, &ctx->costs_alt, sizeof(float) * npx));
-        CK(pmalloc(ctx, &ctx->pre_costs, sizeof(float) * npx));
         CK(pmalloc(ctx, &ctx->selected_views, sizeof(uint32_t) * npx));
         CK(pmalloc(ctx, &ctx->rng, sizeof(uint2) * 3 * npx));
-        CK(cudaMemsetAsync(ctx->pre_costs, 0, sizeof(float) * npx, ctx->stream));
         CK(cudaMemsetAsync(ctx->selected_views, 0, sizeof(uint32_t) * npx, ctx->stream));
         // the pinned result buffers are allocated on the first download (ensure_host_result): a resident chain that
         // never brings a level's result to the host does not pay 136 MB of cudaMallocHost per level

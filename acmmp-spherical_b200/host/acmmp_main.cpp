@@ -533,11 +533,20 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                         job->host_s = now_s() - t1;
                     });
                 } else {
+                    // (the worker only READS the object -- its host copy of the result, camera, depth range -- while this
+                    // thread parks it; CudaPlanarPriorInitialization sets the mode flag when the view is taken up again)
                     job->done = std::async(std::launch::async, [job, obj]() {
+                        const double t0 = now_s();
                         const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
                         cv::Mat_<float> depths(height, width);
-                        for (int k = 0; k < width * height; ++k) depths.ptr()[k] = obj->GetPlaneHypothesis(k).w;
-                        PlanarPriorStage(*obj, depths, job->mask_tri, job->planeParams_tri);        // adds its time to g_prior_s
+                        std::vector<float> costs((size_t)width * height);
+                        for (int k = 0; k < width * height; ++k) {
+                            depths.ptr()[k] = obj->GetPlaneHypothesis(k).w;
+                            costs[k] = obj->GetCost(k);
+                        }
+                        PlanarPriorCpu(obj->GetReferenceCamera(), depths, costs.data(), obj->GetMinDepth(), obj->GetMaxDepth(), job->mask_tri,
+                                       job->planeParams_tri);
+                        add_prior_s(now_s() - t0);
                     });
                 }
                 // only the stage state stays with the view (CPU prior stage: and the host copy its worker reads)

@@ -209,3 +209,33 @@ def test_cpp_driver_multi_gpu_shards_views_and_exchanges_depth_maps(tmp_path, le
             assert res[f"view{v}_prior_stage_depths_identical"], res
         assert res[f"view{v}_final_depth_within_1pct"] > 0.97, res
         assert res[f"view{v}_within_1pct_of_gt"] > 0.85, res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("colour", [False, True])
+def test_jpeg_views_are_decoded_on_the_device_like_imread_grayscale(tmp_path, colour):
+    """The reference reads images/%08d.jpg with cv::imread(IMREAD_GRAYSCALE) (ACMMP.cpp:578); the host side decodes the luma
+    plane with nvJPEG.  Both are the JPEG's Y channel: equal up to the IDCT's rounding (libjpeg vs nvJPEG: a grey level or
+    two on a few pixels).  Grey and colour files, odd sizes (chroma subsampling with partial blocks)."""
+    import ctypes as C
+    import cv2
+    from acmmp_b200 import synth
+    lib = C.CDLL(str(ROOT / "acmmp-spherical_b200" / "lib" / "libacmmp_host.so"))
+    scene = synth.make_pinhole_scene(n_views=2, width=397, height=251, focal=300.0, seed=8)
+    (tmp_path / "images").mkdir()
+    res = {}
+    for i, img in enumerate(scene.images):
+        g = img.astype(np.uint8)
+        src = np.stack([g, np.roll(g, 3, axis=1), 255 - g], axis=-1) if colour else g
+        path = str(tmp_path / "images" / ("%08d.jpg" % i))
+        assert cv2.imwrite(path, src, [cv2.IMWRITE_JPEG_QUALITY, 92])
+        want = cv2.imread(path, cv2.IMREAD_GRAYSCALE).astype(np.float32)
+        got = np.zeros(want.shape, np.float32)
+        w, h = C.c_int(0), C.c_int(0)
+        rc = lib.acmmp_host_load_grey(str(tmp_path).encode(), C.c_int(i), got.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(got.size),
+                                      C.byref(w), C.byref(h))
+        assert rc == 0 and (h.value, w.value) == want.shape
+        d = np.abs(got - want)
+        res[f"view{i}"] = dict(max_abs=float(d.max()), mean_abs=float(d.mean()), equal=float((d == 0).mean()))
+        assert d.max() <= 3 and d.mean() < 0.35
+    util.dump("jpeg_decode_" + ("colour" if colour else "grey"), res)

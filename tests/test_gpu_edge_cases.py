@@ -221,53 +221,59 @@ def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-@pytest.mark.parametrize("stage", ["geom", "prior"])
+@pytest.mark.parametrize("stage", ["geom", "prior", "hierarchy_prior"])
 def test_parked_context_resumes_bit_identically(stage):
-    """acmmp_park between two stages of a resident view (the scratch goes to the device's pool, another context runs in it,
-    the view is re-activated with acmmp_set_views of the same shapes): the second stage gives the bits it gives on a
-    context that never let go of anything."""
+    """acmmp_park between two stages of a resident view (the scratch goes to the device's pool, another context with the
+    same seed and shapes runs in it, the view is re-activated with acmmp_set_views of the same shapes): the second stage
+    gives the bits it gives on a context that never let go of anything.  hierarchy_prior: the prior stage of the SECOND
+    pyramid level, whose passes read what the photometric stage's initialisation left (pre_costs, ACMMP.cu:1318-1322)."""
     from acmmp_b200 import Context, synth
-    scene = synth.make_pinhole_scene(n_views=4, width=320, height=240, focal=260.0, seed=5)
-    imgs, cams, ids = scene.problem(0)
-    other_imgs, other_cams, _ = scene.problem(1)
-    neighbours = [None] + [scene.depths_gt[i] for i in ids[1:]]
-    H, W = imgs[0].shape
+    from acmmp_b200.scene import delaunay_triangles_inside
+    scene = synth.make_pinhole_scene(n_views=4, width=640, height=480, focal=520.0, seed=5)
+    full, full_cams, ids = scene.problem(0)
+    other_full, other_full_cams, _ = scene.problem(1)
+    imgs, cams = synth.scale_problem(full, full_cams, 320)
+    other_imgs, other_cams = synth.scale_problem(other_full, other_full_cams, 320)
+    two_levels = stage == "hierarchy_prior"
+
+    def first_stage(ctx, im0, cm0, im1, cm1):
+        ctx.set_seed(SEED)
+        ctx.set_views(im0, cm0)
+        ctx.run_patch_match(download=False)
+        if two_levels:
+            ctx.next_level(im1, cm1)
+            ctx.run_patch_match(download=False)
 
     def second_stage(ctx, pts=None):
+        H, W = ctx.H, ctx.W
         if stage == "geom":
+            import cv2
             ctx.reset_modes()
             ctx.set_geom_consistency(False)
-            ctx.set_depth_maps(neighbours)
+            ctx.set_depth_maps([None] + [cv2.resize(scene.depths_gt[i], (W, H), interpolation=cv2.INTER_NEAREST) for i in ids[1:]])
         else:
             ctx.set_planar_prior()
             pts = ctx.support_points() if pts is None else pts
             assert len(pts) > 50
-            from acmmp_b200.scene import delaunay_triangles_inside
             ctx.planar_prior_from_triangles(delaunay_triangles_inside(pts, W, H))
         ctx.run_patch_match()
         return ctx.get_result()
 
     plain = Context(0)
-    plain.set_seed(SEED)
-    plain.set_views(imgs, cams)
-    plain.run_patch_match(download=False)
+    first_stage(plain, imgs, cams, full, full_cams)
     p0, c0 = second_stage(plain)
     plain.close()
 
     a = Context(0)
-    a.set_seed(SEED)
-    a.set_views(imgs, cams)
-    a.run_patch_match(download=False)
+    first_stage(a, imgs, cams, full, full_cams)
     a.park()
     with pytest.raises(RuntimeError):
         a.run_patch_match(download=False)                       # parked: no scratch to run in
-    pts = a.support_points() if stage == "prior" else None      # reads the state only: works on a parked context
+    pts = a.support_points() if stage != "geom" else None       # reads the state only: works on a parked context
     b = Context(0)                                              # another view takes the blocks a let go of
-    b.set_seed(SEED + 1)
-    b.set_views(other_imgs, other_cams)
-    b.run_patch_match(download=False)
+    first_stage(b, other_imgs, other_cams, other_full, other_full_cams)
     b.park()
-    a.set_views(imgs, cams)                                     # same shapes: the state is kept
+    a.set_views(full if two_levels else imgs, full_cams if two_levels else cams)      # same shapes: the state is kept
     p1, c1 = second_stage(a, pts)
     a.close()
     b.close()
