@@ -38,7 +38,7 @@ int g_gpu_prior = 0;
 double g_gpu_ms = 0.0, g_prior_s = 0.0;
 // wall-clock attribution of the resident schedule (printed in the summary): image load + scaling, view upload / level
 // change (incl. context creation), stage runs (kernels + waits + downloads), depth-map export, result output
-double g_t_ctx = 0.0, g_t_upload = 0.0, g_t_support = 0.0, g_t_prior_dev = 0.0;
+double g_t_setup = 0.0, g_t_ctx = 0.0, g_t_upload = 0.0, g_t_support = 0.0, g_t_prior_dev = 0.0;
 double g_t_load = 0.0, g_t_views = 0.0, g_t_run = 0.0, g_t_export = 0.0, g_t_output = 0.0, g_t_join = 0.0;
 double g_t_sweep1 = 0.0, g_t_geom = 0.0;   // totals: first sweep, geometric sweeps
 double g_t_exchange = 0.0;                 // --gpus N: peer copies of the depth maps
@@ -275,6 +275,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (it == index_of.end() || (size_t)it->second >= num_images) return false;    // a neighbour that is not processed
         }
     }
+    const double t_setup0 = now_s();
     int avail = 0;
     cudaGetDeviceCount(&avail);
     if (ndev < 1 || g_device + ndev > avail) {
@@ -284,22 +285,36 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
     ndev = (int)std::min<size_t>((size_t)ndev, std::max<size_t>(num_images, 1));
     const auto device_of = [&](size_t view) { return (int)(view % (size_t)ndev); };
     for (int d = 0; d < ndev; ++d) {
-        // One context per view stays alive: images of the view and its sources twice (layered + per-view textures), the
-        // padded reference, planes x 2, costs x 3, view masks, two RNG states, prior planes + masks, for all pyramid
-        // levels of the pool (1 + 1/4 + 1/16); plus two depth-map tables of all views.  Scenes that do not fit fall back
-        // to the file-chained schedule.
+        // What a device holds: per owned view the stage state of the current level (planes, costs, pre-costs: 24 bytes
+        // per pixel -- parked views keep nothing else); the level images of the views it needs (4 B/px); two depth-map tables
+        // of all views (8 B/px); and the scratch of the views in flight, which all views share through the device's pool
+        // (images twice -- layered + per-view textures --, padded reference, ping-pong planes and costs, view masks, two RNG
+        // states, prior planes + masks, pinned-result staging: 8 (n_src + 1) + 160 B/px, two sets in rotation plus the
+        // smaller sets of the coarser levels that stay in the pool).  Scenes that do not fit fall back to the file-chained
+        // schedule.
         cudaSetDevice(g_device + d);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        double need = 0.0;
+        double need = 0.0, scratch = 0.0;
+        std::vector<char> uses(num_images, 0);
+        for (size_t i = 0; i < num_images; ++i)
+            if (device_of(i) == d) {
+                uses[i] = 1;
+                for (int id : problems[i].src_image_ids) uses[index_of.at(id)] = 1;
+            }
         for (size_t i = 0; i < num_images; ++i) {
             int cols = 0, rows = 0;
             if (!ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) continue;
             const double scale = std::min(1.0, (double)problems[i].max_image_size / std::max(cols, rows));
             const double px = (double)cols * rows * scale * scale;
-            if (device_of(i) == d) need += px * (8.0 * (problems[i].src_image_ids.size() + 1) + 160.0) * 1.32;
-            need += px * 8.0 * (ndev > 1 ? 1.0 : 0.0);
+            if (device_of(i) == d) {
+                need += px * 24.0;
+                scratch = std::max(scratch, px * (8.0 * (problems[i].src_image_ids.size() + 1) + 160.0));
+            }
+            if (uses[i]) need += px * 4.0;
+            need += px * 8.0;
         }
+        need += 2.7 * scratch;
         if (need > 0.85 * (double)free_b) {
             std::cout << "resident schedule: device " << g_device + d << " needs about " << need / 1e9 << " GB of device memory, "
                       << free_b / 1e9 << " GB are free" << std::endl;
@@ -316,6 +331,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         std::cout << "resident schedule on " << ndev << " devices, views dealt round-robin" << std::endl;
     }
 
+    g_t_setup = now_s() - t_setup0;                    // CUDA initialisation (all GPUs of the box are enumerated), contexts, peer access
     std::vector<std::unique_ptr<ACMMP>> objs(num_images);
     // tab[d][v]: the map of view v on device d ("d" = what depths.dmb would hold, "g" = depths_geom.dmb)
     std::vector<std::vector<DeviceMap>> dtab(ndev, std::vector<DeviceMap>(num_images)), gtab(ndev, std::vector<DeviceMap>(num_images));
@@ -761,7 +777,7 @@ int main(int argc, char **argv)
     }
     std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << wall_patchmatch << ", \"kernel_ms\": " << g_gpu_ms
               << ", \"prior_cpu_s\": " << g_prior_s << ", \"load_s\": " << g_t_load << ", \"views_s\": " << g_t_views << ", \"run_s\": " << g_t_run
-              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"ctx_s\": " << g_t_ctx << ", \"upload_s\": " << g_t_upload
+              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"setup_s\": " << g_t_setup << ", \"ctx_s\": " << g_t_ctx << ", \"upload_s\": " << g_t_upload
               << ", \"support_s\": " << g_t_support << ", \"prior_dev_s\": " << g_t_prior_dev << ", \"sweep1_s\": " << g_t_sweep1 << ", \"geom_s\": " << g_t_geom
               << ", \"gpus\": " << (resident ? g_devices_used : 1) << ", \"exchange_s\": " << g_t_exchange
               << ", \"fusion_s\": " << fusion_s << ", \"fusion_kernel_ms\": " << fusion_kernel_ms << ", \"fusion_points\": " << fusion_points << "}" << std::endl;
