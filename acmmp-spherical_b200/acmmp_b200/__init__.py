@@ -77,7 +77,7 @@ _EXPORTS = [
     "acmmp_default_params", "acmmp_version", "acmmp_abi_sizeof_camera", "acmmp_abi_sizeof_params",
     "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
-    "acmmp_get_params", "acmmp_reset_modes", "acmmp_park", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
+    "acmmp_get_params", "acmmp_reset_modes", "acmmp_park", "acmmp_reserve_device_memory", "acmmp_pool_alloc", "acmmp_pool_free", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
     "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_next_level_device", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_support_points",
     "acmmp_planar_prior_from_triangles", "acmmp_download_prior", "acmmp_set_seed",
     "acmmp_set_plane_now_semantics", "acmmp_set_sphere_tap_pruning", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",
@@ -395,6 +395,27 @@ class Context:
 
     def launch_count(self):
         return int(self._l.acmmp_launch_count(self._h))
+
+
+def reserve_device_memory(device, nbytes):
+    """One allocation that the device's pool carves its blocks out of (acmmp_reserve_device_memory).  Returns the status
+    code: 0, or ACMMP_E_ARG when the device already has a reservation."""
+    return int(lib().acmmp_reserve_device_memory(C.c_int(device), C.c_size_t(int(nbytes))))
+
+
+def pool_alloc(device, nbytes):
+    """A device buffer out of the device's pool (acmmp_pool_alloc) -> device pointer (int)."""
+    p = C.c_void_p()
+    rc = lib().acmmp_pool_alloc(C.c_int(device), C.c_size_t(int(nbytes)), C.byref(p))
+    if rc != 0:
+        raise RuntimeError(f"acmmp_pool_alloc failed ({rc})")
+    return int(p.value)
+
+
+def pool_free(device, ptr):
+    rc = lib().acmmp_pool_free(C.c_int(device), C.c_void_p(int(ptr)))
+    if rc != 0:
+        raise RuntimeError(f"acmmp_pool_free failed ({rc})")
 
 
 def jbu(image, coarse_depth, device=0):

@@ -218,6 +218,7 @@ struct MemPool {
     std::multimap<ArrKey, cudaArray_t> arr_free;
     std::map<cudaArray_t, ArrKey> arr_key;
     struct DeviceShared *shared = nullptr;                        // second tier (null for the shared pool itself)
+    const struct DeviceShared *home = nullptr;                    // the device this pool belongs to (arena range)
 
     bool take_dev(size_t bytes, void **p)
     {
@@ -250,7 +251,7 @@ struct MemPool {
     {
         if (!p) return;
         auto it = dev_size.find(p);
-        if (it == dev_size.end()) { cudaFree(p); return; }
+        if (it == dev_size.end()) { if (!in_arena(p)) cudaFree(p); return; }
         dev_free.insert(std::make_pair(it->second, p));
     }
     void hfree(void *p)
@@ -283,9 +284,11 @@ struct MemPool {
         for (auto &kv : arr_free) { to.arr_key[kv.second] = kv.first; to.arr_free.insert(kv); arr_key.erase(kv.second); }
         dev_free.clear(); host_free.clear(); arr_free.clear();
     }
+    bool in_arena(const void *p) const;
     void release_all()
     {
-        for (auto &kv : dev_size) cudaFree(kv.first);
+        for (auto &kv : dev_size)
+            if (!in_arena(kv.first)) cudaFree(kv.first);
         for (auto &kv : host_size) cudaFreeHost(kv.first);
         for (auto &kv : arr_key) cudaFreeArray(kv.first);
         dev_free.clear(); host_free.clear(); dev_size.clear(); host_size.clear(); arr_free.clear(); arr_key.clear();
@@ -298,14 +301,42 @@ struct DeviceShared {
     std::mutex m;
     MemPool pool;
     std::map<std::tuple<uint64_t, int, int>, uint2 *> seeded_cache;
-    int live = 0;
+    int live = 0;                 // contexts + blocks handed out by acmmp_pool_alloc
+    int cc_major = 0, cc_minor = 0, sm_count = 0;      // asked once (acmmp_create)
+    // acmmp_reserve_device_memory: ONE cudaMalloc that new blocks are carved out of (bump pointer, 512-byte steps; a freed
+    // block goes to the size-keyed free lists like any other).  cudaMalloc on a device that already holds hundreds of
+    // allocations costs 1.5 - 12 ms per call (ACMMP_TRACE), and a resident scene needs three state blocks per view and level.
+    char *arena = nullptr;
+    size_t arena_size = 0, arena_used = 0;
+    bool carve(size_t bytes, void **p)          // caller holds m
+    {
+        const size_t step = (bytes + 511) & ~(size_t)511;
+        if (!arena || arena_used + step > arena_size) return false;
+        *p = arena + arena_used;
+        arena_used += step;
+        return true;
+    }
+    void release_everything()                   // caller holds m
+    {
+        pool.release_all();
+        seeded_cache.clear();
+        if (arena) cudaFree(arena);
+        arena = nullptr;
+        arena_size = arena_used = 0;
+    }
 };
+bool MemPool::in_arena(const void *p) const
+{
+    return home && home->arena && (const char *)p >= home->arena && (const char *)p < home->arena + home->arena_size;
+}
 static DeviceShared &device_shared(int device)
 {
     static std::mutex m;
     static std::map<int, DeviceShared> table;          // node-based: references stay valid
     std::lock_guard<std::mutex> lock(m);
-    return table[device];
+    DeviceShared &sh = table[device];
+    sh.pool.home = &sh;
+    return sh;
 }
 
 cudaError_t MemPool::dmalloc(void **p, size_t bytes)
@@ -314,6 +345,7 @@ cudaError_t MemPool::dmalloc(void **p, size_t bytes)
     if (shared) {
         std::lock_guard<std::mutex> lock(shared->m);
         if (shared->pool.take_dev(bytes, p)) { shared->pool.dev_size.erase(*p); dev_size[*p] = bytes; return cudaSuccess; }
+        if (shared->carve(bytes, p)) { dev_size[*p] = bytes; return cudaSuccess; }
     }
     Trace tr("pool.cudaMalloc");
     cudaError_t e = cudaMalloc(p, bytes);
@@ -1167,21 +1199,35 @@ int acmmp_create(acmmp_ctx **out, int device)
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ACMMP_E_CUDA;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ACMMP_E_CUDA;
-    if (prop.major != 10) {
-        std::fprintf(stderr, "acmmp_b200: device %d is sm_%d%d; this library only carries sm_100a code\n", device, prop.major, prop.minor);
+    DeviceShared &dsh = device_shared(device);
+    int cc_major = 0, cc_minor = 0, sm_count = 0;
+    {
+        // asked once per device: cudaGetDeviceProperties takes 5 - 40 ms, and a resident scene creates a context per view
+        std::lock_guard<std::mutex> lock(dsh.m);
+        if (dsh.sm_count == 0) {
+            if (cudaDeviceGetAttribute(&dsh.cc_major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+                cudaDeviceGetAttribute(&dsh.cc_minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess ||
+                cudaDeviceGetAttribute(&dsh.sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+                dsh.sm_count = 0;
+                return ACMMP_E_CUDA;
+            }
+        }
+        cc_major = dsh.cc_major; cc_minor = dsh.cc_minor; sm_count = dsh.sm_count;
+    }
+    if (cc_major != 10) {
+        std::fprintf(stderr, "acmmp_b200: device %d is sm_%d%d; this library only carries sm_100a code\n", device, cc_major, cc_minor);
         return ACMMP_E_UNSUPPORTED;
     }
     if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
     acmmp_ctx *ctx = new acmmp_ctx();
     ctx->device = device;
-    ctx->pool.shared = &device_shared(device);
+    ctx->pool.shared = &dsh;
+    ctx->pool.home = ctx->pool.shared;
     {
         std::lock_guard<std::mutex> lock(ctx->pool.shared->m);
         ctx->pool.shared->live++;
     }
-    ctx->num_sms = prop.multiProcessorCount;
+    ctx->num_sms = sm_count;
     acmmp_default_params(&ctx->params);
     if (const char *e = std::getenv("ACMMP_NO_TMA")) ctx->use_tma = (e[0] == '1') ? 0 : 1;   // debug aid
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1212,10 +1258,7 @@ int acmmp_destroy(acmmp_ctx *ctx)
         DeviceShared &sh = *ctx->pool.shared;
         std::lock_guard<std::mutex> lock(sh.m);
         ctx->pool.give_free_to(sh.pool);
-        if (--sh.live == 0) {
-            sh.pool.release_all();
-            sh.seeded_cache.clear();
-        }
+        if (--sh.live == 0) sh.release_everything();
     }
     ctx->pool.release_all();               // anything still registered here was not returned by its owner
     cudaStreamDestroy(ctx->stream);
@@ -1305,6 +1348,53 @@ int acmmp_park(acmmp_ctx *ctx, int keep_prior, int keep_host_result)
         std::lock_guard<std::mutex> lock(ctx->pool.shared->m);
         ctx->pool.give_free_to(ctx->pool.shared->pool);
     }
+    return ACMMP_OK;
+}
+
+int acmmp_reserve_device_memory(int device, size_t bytes)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ACMMP_E_CUDA;
+    DeviceShared &sh = device_shared(device);
+    std::lock_guard<std::mutex> lock(sh.m);
+    if (sh.arena) return ACMMP_E_ARG;                         // one reservation per device (until everything is released)
+    if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
+    Trace tr("reserve_device_memory");
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return ACMMP_E_CUDA; }
+    sh.arena = (char *)p;
+    sh.arena_size = bytes;
+    sh.arena_used = 0;
+    return ACMMP_OK;
+}
+
+int acmmp_pool_alloc(int device, size_t bytes, void **out)
+{
+    if (!out || bytes == 0) return ACMMP_E_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ACMMP_E_CUDA;
+    DeviceShared &sh = device_shared(device);
+    std::lock_guard<std::mutex> lock(sh.m);
+    void *p = nullptr;
+    if (!sh.pool.take_dev(bytes, &p) && !sh.carve(bytes, &p)) {
+        if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
+        Trace tr("pool.cudaMalloc");
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return ACMMP_E_CUDA; }
+    }
+    sh.pool.dev_size[p] = bytes;
+    sh.live++;
+    *out = p;
+    return ACMMP_OK;
+}
+
+int acmmp_pool_free(int device, void *p)
+{
+    if (!p) return ACMMP_OK;
+    DeviceShared &sh = device_shared(device);
+    std::lock_guard<std::mutex> lock(sh.m);
+    if (sh.pool.dev_size.find(p) == sh.pool.dev_size.end()) return ACMMP_E_ARG;
+    sh.pool.dfree(p);
+    if (--sh.live == 0) sh.release_everything();
     return ACMMP_OK;
 }
 

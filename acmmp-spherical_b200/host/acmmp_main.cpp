@@ -213,12 +213,16 @@ struct DeviceMap {
     size_t cap = 0;
     // `reserve`: pixels of the finest level, so that the buffer is allocated once (a cudaFree + cudaMalloc per level
     // cost 20 ms per export on a device that holds a few GB of pooled buffers)
-    void fit(int nw, int nh, size_t reserve = 0)
+    // The memory comes out of the library's pool of the device (acmmp_pool_alloc): with the reservation made at the start
+    // of the resident schedule it is a pointer bump.
+    void fit(int nw, int nh, size_t reserve, int device)
     {
         const size_t need = std::max((size_t)nw * nh, reserve);
         if (need > cap) {
-            if (ptr) cudaFree(ptr);
-            if (cudaMalloc(&ptr, need * sizeof(float)) != cudaSuccess) throw std::runtime_error("cudaMalloc of a depth map failed");
+            if (ptr) acmmp_pool_free(device, ptr);
+            void *p = nullptr;
+            if (acmmp_pool_alloc(device, need * sizeof(float), &p) != ACMMP_OK) throw std::runtime_error("device memory for a depth map / level image");
+            ptr = (float *)p;
             cap = need;
         }
         w = nw;
@@ -276,6 +280,13 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         }
     }
     const double t_setup0 = now_s();
+    // the coarsest level's images of all views: read, decoded and scaled on a host thread while CUDA comes up below
+    std::vector<cv::Mat_<float>> level_image(num_images), next_image(num_images);
+    std::vector<Camera> level_camera(num_images), next_camera(num_images);
+    std::shared_future<void> first_load = std::async(std::launch::async, [&]() {
+        for (size_t i = 0; i < num_images; ++i)
+            LoadScaledView(dense_folder, problems[i].ref_image_id, problems[i].max_image_size / (1 << max_num_downscale), next_image[i], next_camera[i]);
+    }).share();
     int avail = 0;
     cudaGetDeviceCount(&avail);
     if (ndev < 1 || g_device + ndev > avail) {
@@ -284,6 +295,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
     }
     ndev = (int)std::min<size_t>((size_t)ndev, std::max<size_t>(num_images, 1));
     const auto device_of = [&](size_t view) { return (int)(view % (size_t)ndev); };
+    std::vector<size_t> reserve_bytes;
     for (int d = 0; d < ndev; ++d) {
         // What a device holds: per owned view the stage state of the current level (planes, costs, pre-costs: 24 bytes
         // per pixel -- parked views keep nothing else); the level images of the views it needs (4 B/px); two depth-map tables
@@ -320,7 +332,13 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                       << free_b / 1e9 << " GB are free" << std::endl;
             return false;
         }
+        reserve_bytes.push_back((size_t)(need * 1.1) + ((size_t)256 << 20));
     }
+    // one allocation per device that the library's pool carves the state blocks, scratch sets, level images and depth-map
+    // tables out of (the texture arrays and pinned buffers are separate allocations); what does not fit falls back to cudaMalloc
+    for (int d = 0; d < ndev; ++d)
+        if (acmmp_reserve_device_memory(g_device + d, reserve_bytes[d]) != ACMMP_OK)
+            std::cout << "resident schedule: no " << reserve_bytes[d] / 1e9 << " GB reservation on device " << g_device + d << " (allocating block by block)" << std::endl;
     if (ndev > 1) {
         for (int a = 0; a < ndev; ++a)
             for (int b = 0; b < ndev; ++b)
@@ -351,8 +369,6 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         for (size_t v = 0; v < num_images; ++v)
             if (need[v] && device_of(v) != d) remote[d].push_back(v);
     }
-    std::vector<cv::Mat_<float>> level_image(num_images), next_image(num_images);
-    std::vector<Camera> level_camera(num_images), next_camera(num_images);
     std::vector<int> level_w(num_images, 0), level_h(num_images, 0);
     PhaseBarrier barrier(ndev);
     std::mutex stats_mutex;
@@ -372,7 +388,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             const double t0 = now_s();
             for (size_t v : remote[d]) {
                 const int o = device_of(v);
-                tab[d][v].fit(level_w[v], level_h[v], full_px[v]);
+                tab[d][v].fit(level_w[v], level_h[v], full_px[v], g_device + d);
                 if (cudaMemcpyPeerAsync(tab[d][v].ptr, g_device + d, tab[o][v].ptr, g_device + o, sizeof(float) * (size_t)level_w[v] * level_h[v], 0) != cudaSuccess)
                     throw std::runtime_error("peer copy of a depth map failed");
             }
@@ -408,8 +424,9 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (!barrier.wait()) return;
             // every view of this level, read and scaled once (each thread its share, all of them shared afterwards)
             double tp = now_s();
-            if (prefetch.valid()) {
-                prefetch.get();                                // read and scaled beside the previous level's kernels
+            if (level == 0 || prefetch.valid()) {
+                if (level == 0) first_load.get();              // started before CUDA was initialised
+                else prefetch.get();                           // read and scaled beside the previous level's kernels
                 for (size_t i : mine) {
                     level_image[i] = std::move(next_image[i]);
                     level_camera[i] = next_camera[i];
@@ -427,7 +444,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             // image is a source image of ~10 other views, and uploading it with each of them was 0.3 s per 3200x2130 view
             tp = now_s();
             for (size_t v : needed) {
-                pool[v].fit(level_w[v], level_h[v], full_px[v]);
+                pool[v].fit(level_w[v], level_h[v], full_px[v], g_device + d);
                 if (cudaMemcpyAsync(pool[v].ptr, level_image[v].ptr(), sizeof(float) * (size_t)level_w[v] * level_h[v], cudaMemcpyHostToDevice, 0) != cudaSuccess)
                     throw std::runtime_error("upload of a level image failed");
             }
@@ -487,22 +504,24 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 pending.erase(v);
                 const int width = a.GetReferenceImageWidth(), height = a.GetReferenceImageHeight();
                 tw = now_s();
-                a.RunPatchMatchResident(finest);                                     // finest level: depths.dmb is an output
+                a.RunPatchMatchResident(false);
                 t_run += now_s() - tw;
                 float tt[8];
                 a.GetTimings(tt);
                 gpu_ms += tt[0] + tt[1] + tt[2];
                 tw = now_s();
-                if (finest) {
-                    final_prior_depth[v] = cv::Mat_<float>(height, width);
-                    for (int k = 0; k < width * height; ++k) final_prior_depth[v].ptr()[k] = a.GetPlaneHypothesis(k).w;
-                }
-                t_output += now_s() - tw;
-                tw = now_s();
-                dtab[d][v].fit(width, height, full_px[v]);
+                dtab[d][v].fit(width, height, full_px[v], g_device + d);
                 a.ExportDepthDevice(dtab[d][v].ptr);
                 a.Park();                                      // the next view's stage runs in this one's scratch
                 t_export += now_s() - tw;
+                tw = now_s();
+                if (finest) {
+                    // depths.dmb is an output at the finest level: the exported map (27 MB) instead of the whole result (136 MB)
+                    final_prior_depth[v] = cv::Mat_<float>(height, width);
+                    if (cudaMemcpy(final_prior_depth[v].ptr(), dtab[d][v].ptr, sizeof(float) * (size_t)width * height, cudaMemcpyDeviceToHost) != cudaSuccess)
+                        throw std::runtime_error("download of a prior-stage depth map failed");
+                }
+                t_output += now_s() - tw;
             };
             const double t_s1 = now_s();
             size_t previous = (size_t)-1;
@@ -603,7 +622,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     acmmp.GetTimings(t);
                     gpu_ms += t[0] + t[1] + t[2];
                     tg = now_s();
-                    gtab[d][i].fit(acmmp.GetReferenceImageWidth(), acmmp.GetReferenceImageHeight(), full_px[i]);
+                    gtab[d][i].fit(acmmp.GetReferenceImageWidth(), acmmp.GetReferenceImageHeight(), full_px[i], g_device + d);
                     acmmp.ExportDepthDevice(gtab[d][i].ptr);
                     acmmp.Park(false, last);                   // the writer below reads the host copy, then lets it go too
                     t_export += now_s() - tg;

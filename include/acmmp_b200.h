@@ -12,6 +12,7 @@
 #ifndef ACMMP_B200_H_
 #define ACMMP_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -120,6 +121,15 @@ int acmmp_reset_modes(acmmp_ctx *ctx);
  * maps and acmmp_run_patch_match* as usual.  acmmp_support_points, acmmp_planar_prior_from_triangles,
  * acmmp_export_depth_device, acmmp_download_result and acmmp_next_level* work on a parked context. */
 int acmmp_park(acmmp_ctx *ctx, int keep_prior, int keep_host_result);
+/* The pool of a device, for hosts that keep many views resident (no reference counterpart: the reference allocates per
+ * ProcessProblem call, ACMMP.cpp:685-724).  acmmp_reserve_device_memory: one allocation of `bytes` that the pool carves
+ * new blocks out of before it falls back to cudaMalloc (cudaMalloc on a device that already holds hundreds of allocations
+ * costs milliseconds per call); one reservation per device, released with everything else when the last context of the
+ * device is destroyed.  acmmp_pool_alloc / acmmp_pool_free: device buffers of the host (image pool, depth-map tables) out
+ * of the same pool; a block handed out keeps the pool alive like a context does.  Thread-safe. */
+int acmmp_reserve_device_memory(int device, size_t bytes);
+int acmmp_pool_alloc(int device, size_t bytes, void **out);
+int acmmp_pool_free(int device, void *p);
 
 /* Geometric consistency inputs: the n depth maps (index 0 = reference view, 1.. = source views)
  * that InuputInitialization reads from depths.dmb / depths_geom.dmb (ACMMP.cpp:653-678) and

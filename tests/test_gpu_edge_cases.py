@@ -278,3 +278,45 @@ def test_parked_context_resumes_bit_identically(stage):
     a.close()
     b.close()
     assert np.array_equal(_bits(p0), _bits(p1)) and np.array_equal(_bits(c0), _bits(c1))
+
+
+def test_reserved_device_memory_serves_contexts_and_host_buffers():
+    """acmmp_reserve_device_memory: the device's pool carves blocks out of one reservation; results do not depend on where a
+    buffer lives; acmmp_pool_alloc hands the host buffers out of the same pool; a second reservation is refused while the
+    first one is alive; everything is returned when the last context / host block is gone."""
+    import gc
+    import acmmp_b200 as ab
+    from acmmp_b200 import Context, synth
+    gc.collect()                                                   # contexts other tests dropped without close()
+    scene = synth.make_pinhole_scene(n_views=3, width=200, height=150, focal=160.0, seed=6)
+    imgs, cams, _ = scene.problem(0)
+
+    def stage():
+        ctx = Context(0)
+        ctx.set_seed(SEED)
+        ctx.set_views(imgs, cams)
+        ctx.run_patch_match()
+        out = ctx.get_result()
+        return ctx, out
+
+    ctx, (p0, c0) = stage()
+    ctx.close()                                                    # last context of the device: the pool is empty again
+    assert ab.reserve_device_memory(0, 256 << 20) == 0
+    assert ab.reserve_device_memory(0, 1 << 20) == -1              # ACMMP_E_ARG: one reservation per device
+    ctx, (p1, c1) = stage()
+    planes_dev, _ = ctx.device_buffers()
+    host_block = ab.pool_alloc(0, 4 * 200 * 150)
+    ctx.export_depth_device(host_block)
+    ctx.synchronize()
+    ctx.close()                                                    # the host block keeps the pool (and the reservation) alive
+    assert ab.reserve_device_memory(0, 1 << 20) == -1
+    again = ab.pool_alloc(0, 4 * 200 * 150)
+    assert again != host_block
+    # both blocks lie inside one 256 MB range: carved out of the reservation, not separate allocations
+    assert abs(again - host_block) < (256 << 20) and abs(int(planes_dev) - host_block) < (256 << 20)
+    ab.pool_free(0, again)
+    ab.pool_free(0, host_block)                                    # last reference: reservation released
+    assert ab.reserve_device_memory(0, 1 << 20) == 0
+    ctx, _ = stage()
+    ctx.close()
+    assert np.array_equal(_bits(p0), _bits(p1)) and np.array_equal(_bits(c0), _bits(c1))
