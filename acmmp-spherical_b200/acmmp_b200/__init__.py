@@ -85,7 +85,7 @@ _EXPORTS = [
     "acmmp_device_buffers", "acmmp_export_depth_device", "acmmp_export_depth_device_sync", "acmmp_download_state", "acmmp_upload_state",
     "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_coords", "acmmp_probe_geom", "acmmp_probe_warp",
     "acmmp_probe_initcost", "acmmp_last_timings", "acmmp_launch_count",
-    "acmmp_fusion_create", "acmmp_fusion_destroy", "acmmp_fusion_last_error", "acmmp_fusion_set_view", "acmmp_fusion_set_view_device",
+    "acmmp_fusion_create", "acmmp_fusion_destroy", "acmmp_fusion_last_error", "acmmp_fusion_set_view", "acmmp_fusion_set_view_colour", "acmmp_fusion_set_view_device",
     "acmmp_fusion_run", "acmmp_fusion_last_flags",
 ]
 
@@ -462,6 +462,14 @@ class Fusion:
         self._ck(self._l.acmmp_fusion_set_view(self._h, C.c_int(index), C.byref(cam), C.c_int(w), C.c_int(h), _fp(d), _fp(n3), _fp(g)),
                  "acmmp_fusion_set_view")
         self.sizes[index] = (h, w)
+
+    def set_view_colour(self, index, bgr):
+        """Optional colour image of a view already set: uint8 [h, w, 3] in OpenCV's B, G, R order."""
+        c = np.ascontiguousarray(bgr, np.uint8)
+        h, w = self.sizes[index]
+        assert c.shape == (h, w, 3)
+        self._ck(self._l.acmmp_fusion_set_view_colour(self._h, C.c_int(index), c.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(w), C.c_int(h)),
+                 "acmmp_fusion_set_view_colour")
 
     def run(self, ref, src_indices):
         src = np.ascontiguousarray(src_indices, np.int32)

@@ -2004,6 +2004,7 @@ int acmmp_fusion_set_view_device(acmmp_fusion *f, int index, const acmmp_camera 
     v.depth = depth_dev;
     v.normal = static_cast<const float4 *>(normals4_dev);
     v.gray = gray_dev;
+    v.bgr = nullptr;
     f->table_dirty = true;
     return ACMMP_OK;
 }
@@ -2039,6 +2040,26 @@ int acmmp_fusion_set_view(acmmp_fusion *f, int index, const acmmp_camera *cam, i
     v.depth = d;
     v.normal = n4;
     v.gray = g;
+    v.bgr = nullptr;
+    f->table_dirty = true;
+    return ACMMP_OK;
+}
+
+int acmmp_fusion_set_view_colour(acmmp_fusion *f, int index, const uint8_t *bgr, int w, int h)
+{
+    if (!f || index < 0 || index >= f->n || !bgr) return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_set_view_colour: bad arguments");
+    acmmp::FusionViewDev &v = f->views[index];
+    if (!v.depth || v.cam.width != w || v.cam.height != h)
+        return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_set_view_colour: set the view first; the colour image must have the depth map's size");
+    FCK(cudaSetDevice(f->device));
+    const size_t npx = (size_t)w * h;
+    std::vector<uchar4> packed(npx);
+    for (size_t k = 0; k < npx; ++k) packed[k] = make_uchar4(bgr[3 * k], bgr[3 * k + 1], bgr[3 * k + 2], 255);
+    uchar4 *dev = nullptr;
+    FCK(cudaMalloc(&dev, sizeof(uchar4) * npx));
+    f->owned[index].push_back(dev);
+    FCK(cudaMemcpy(dev, packed.data(), sizeof(uchar4) * npx, cudaMemcpyHostToDevice));
+    v.bgr = dev;
     f->table_dirty = true;
     return ACMMP_OK;
 }

@@ -30,6 +30,7 @@ struct FusionViewDev {
     const float *depth;
     const float4 *normal;                // world-frame normal (normals.dmb), w unused
     const float *gray;                   // grey levels 0..255 at the depth map's size (colour = (g, g, g))
+    const uchar4 *bgr;                   // optional: the colour image at that size, (B, G, R, -) per pixel; null = use gray
 };
 
 struct FusionProblemDev {
@@ -89,15 +90,25 @@ __device__ __forceinline__ void fuse_project(const acmmp_camera &cam, const floa
 }
 
 // tex2D<float4>(image, c, r) of a linear-filtered texture at an integer coordinate (no half-texel offset): the mean of
-// the texels (c-1 .. c) x (r-1 .. r) with clamp addressing, as a grey level 0..255
-__device__ __forceinline__ float fuse_colour(const FusionViewDev &v, const int c, const int r)
+// the texels (c-1 .. c) x (r-1 .. r) with clamp addressing, as levels 0..255.  Returned in the order the reference sums
+// them into PointList::color (ACMMP.cu:1704-1708, :1769-1771): (B, G, R) -- its texels are RGBA after cvtColor(BGR2RGBA)
+// and it takes .z first; the PLY writer reads them back in that order (ACMMP.cpp:509-511).
+__device__ __forceinline__ float3 fuse_colour(const FusionViewDev &v, const int c, const int r)
 {
     const int w = v.cam.width, h = v.cam.height;
     const int c0 = min(max(c - 1, 0), w - 1), c1 = min(max(c, 0), w - 1);
     const int r0 = min(max(r - 1, 0), h - 1), r1 = min(max(r, 0), h - 1);
+    if (v.bgr) {
+        const uchar4 a = __ldg(v.bgr + (size_t)r0 * w + c0), b = __ldg(v.bgr + (size_t)r0 * w + c1);
+        const uchar4 d = __ldg(v.bgr + (size_t)r1 * w + c0), e = __ldg(v.bgr + (size_t)r1 * w + c1);
+        return make_float3(0.25f * (((float)a.x + (float)b.x) + ((float)d.x + (float)e.x)),
+                           0.25f * (((float)a.y + (float)b.y) + ((float)d.y + (float)e.y)),
+                           0.25f * (((float)a.z + (float)b.z) + ((float)d.z + (float)e.z)));
+    }
     const float a = __ldg(v.gray + (size_t)r0 * w + c0), b = __ldg(v.gray + (size_t)r0 * w + c1);
     const float d = __ldg(v.gray + (size_t)r1 * w + c0), e = __ldg(v.gray + (size_t)r1 * w + c1);
-    return 0.25f * ((a + b) + (d + e));
+    const float g = 0.25f * ((a + b) + (d + e));
+    return make_float3(g, g, g);
 }
 
 // One thread per pixel of the reference view, row-major blocks of kFuseBlock pixels.
@@ -116,10 +127,9 @@ k_fuse_view(const FusionViewDev *__restrict__ views, const int ref, const __grid
             const acmmp_camera ref_cam = rv.cam;
             const float3 PointX = fuse_lift(ref_cam, static_cast<float>(c), static_cast<float>(r), ref_depth);
             const float4 rn = __ldg(rv.normal + idx);
-            const float g = fuse_colour(rv, c, r);
             float3 point_sum = PointX;
             float3 normal_sum = make_float3(rn.x, rn.y, rn.z);
-            float3 colour_sum = make_float3(g, g, g);            // the reference's texels are x / 255, multiplied back by 255
+            float3 colour_sum = fuse_colour(rv, c, r);           // the reference's texels are x / 255, multiplied back by 255
             int num_consistent = 1;
             for (int j = 0; j < problem.num_src; ++j) {
                 const int s = problem.src[j];
@@ -147,8 +157,8 @@ k_fuse_view(const FusionViewDev *__restrict__ views, const int ref, const __grid
                 if (reproj_error < 1.0 && relative_depth_diff < 0.01f && angle < 0.149f) {
                     point_sum.x += Xs.x; point_sum.y += Xs.y; point_sum.z += Xs.z;
                     normal_sum.x += sn.x; normal_sum.y += sn.y; normal_sum.z += sn.z;
-                    const float gs = fuse_colour(sv, src_c, src_r);
-                    colour_sum.x += gs; colour_sum.y += gs; colour_sum.z += gs;
+                    const float3 cs = fuse_colour(sv, src_c, src_r);
+                    colour_sum.x += cs.x; colour_sum.y += cs.y; colour_sum.z += cs.z;
                     num_consistent++;
                 }
             }

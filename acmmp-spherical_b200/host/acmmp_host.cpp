@@ -539,6 +539,7 @@ size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem>
         Camera cam;
         cv::Mat_<float> depth, gray;
         cv::Mat_<cv::Vec3f> normal;
+        cv::Mat_<cv::Vec3b> colour;          // empty: no colour source, the grey level goes to all three channels
         Problem problem;
     };
     std::vector<View> views;
@@ -567,6 +568,11 @@ size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem>
         const int cols = v.depth.cols, rows = v.depth.rows;
         v.cam.width = cols;
         v.cam.height = rows;
+        cv::Mat_<cv::Vec3b> colour;
+        if (LoadColourImage(dense_folder, id, colour) && colour.cols == image.cols && colour.rows == image.rows) {
+            if (cols == colour.cols && rows == colour.rows) v.colour = colour;
+            else ResizeLinearBgr(colour, v.colour, cols, rows);
+        }
         if (cols == image.cols && rows == image.rows) {
             v.gray = image;
         } else {
@@ -602,6 +608,9 @@ size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem>
         if (acmmp_fusion_set_view(f, (int)i, &v.cam, v.depth.cols, v.depth.rows, v.depth.ptr(), reinterpret_cast<const float *>(v.normal.ptr()),
                                   v.gray.ptr()) != ACMMP_OK)
             fail("set_view");
+        if (!v.colour.empty() &&
+            acmmp_fusion_set_view_colour(f, (int)i, reinterpret_cast<const uint8_t *>(v.colour.ptr()), v.depth.cols, v.depth.rows) != ACMMP_OK)
+            fail("set_view_colour");
     }
     std::vector<PointList> all_points;
     double ms_sum = 0.0;

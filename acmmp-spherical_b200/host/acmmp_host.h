@@ -72,6 +72,9 @@ bool ImageSize(const std::string &dense_folder, int id, int &cols, int &rows);
 bool LoadScaledView(const std::string &dense_folder, int id, int max_image_size, cv::Mat_<float> &image, Camera &camera);
 // cv::resize(src, dst, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) on a float image
 void ResizeLinear(const cv::Mat_<float> &src, cv::Mat_<float> &dst, int new_cols, int new_rows);
+// the colour image of a view (B, G, R like cv::imread(IMREAD_COLOR)) and cv::resize INTER_LINEAR on it: the fusion's inputs
+bool LoadColourImage(const std::string &dense_folder, int id, cv::Mat_<cv::Vec3b> &image);
+void ResizeLinearBgr(const cv::Mat_<cv::Vec3b> &src, cv::Mat_<cv::Vec3b> &dst, int new_cols, int new_rows);
 
 // ---- host twins of the camera math the CPU prior stage uses (ACMMP.cpp:287-312) -------------------------
 float3 Get3DPointonRefCam(const int x, const int y, const float depth, const Camera &camera);

@@ -249,6 +249,34 @@ bool decode_jpeg_luma(const std::vector<unsigned char> &b, cv::Mat_<float> &imag
     for (size_t i = 0; i < host.size(); ++i) dst[i] = (float)host[i];
     return true;
 }
+
+// cv::imread(IMREAD_COLOR): interleaved B, G, R
+bool decode_jpeg_bgr(const std::vector<unsigned char> &b, cv::Mat_<cv::Vec3b> &image)
+{
+    static std::mutex decoder_mutex;
+    std::lock_guard<std::mutex> lock(decoder_mutex);
+    static nvjpegHandle_t handle = nullptr;
+    static nvjpegJpegState_t state = nullptr;
+    if (!handle) {
+        if (nvjpegCreateSimple(&handle) != NVJPEG_STATUS_SUCCESS) { handle = nullptr; return false; }
+        if (nvjpegJpegStateCreate(handle, &state) != NVJPEG_STATUS_SUCCESS) return false;
+    }
+    int ncomp = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+    nvjpegChromaSubsampling_t ss;
+    if (nvjpegGetImageInfo(handle, b.data(), b.size(), &ncomp, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) return false;
+    const int w = ws[0], h = hs[0];
+    unsigned char *dev = nullptr;
+    if (cudaMalloc(&dev, (size_t)w * h * 3) != cudaSuccess) return false;
+    nvjpegImage_t out;
+    std::memset(&out, 0, sizeof(out));
+    out.channel[0] = dev;
+    out.pitch[0] = (size_t)w * 3;
+    bool ok = nvjpegDecode(handle, state, b.data(), b.size(), NVJPEG_OUTPUT_BGRI, &out, nullptr) == NVJPEG_STATUS_SUCCESS;
+    image = cv::Mat_<cv::Vec3b>(h, w);
+    ok = ok && cudaMemcpy(image.ptr(), dev, (size_t)w * h * 3, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(dev);
+    return ok;
+}
 #endif
 
 } // namespace
@@ -275,6 +303,92 @@ bool LoadGreyImage(const std::string &dense_folder, int id, cv::Mat_<float> &ima
 #endif
     }
     return false;
+}
+
+// The colour image of a view for the fused points (reference: cv::imread(images/%08d.jpg, IMREAD_COLOR), ACMMP.cu:1861-1862):
+// images/%08d.ppm (P6, lossless twin like the .pgm for the grey path) or the .jpg through nvJPEG; a view that only has a
+// grey image gets (g, g, g).
+bool LoadColourImage(const std::string &dense_folder, int id, cv::Mat_<cv::Vec3b> &image)
+{
+    std::vector<unsigned char> bytes;
+    if (read_file(view_file(dense_folder + "/images", id, ".ppm"), bytes) && bytes.size() > 2 && bytes[0] == 'P' && bytes[1] == '6') {
+        bytes[1] = '5';                                     // same header grammar as P5
+        int w, h;
+        size_t off;
+        if (parse_pgm(bytes, w, h, off) && bytes.size() >= off + (size_t)w * h * 3) {
+            image = cv::Mat_<cv::Vec3b>(h, w);
+            for (size_t i = 0; i < (size_t)w * h; ++i)      // file: R, G, B
+                image.ptr()[i] = cv::Vec3b(bytes[off + 3 * i + 2], bytes[off + 3 * i + 1], bytes[off + 3 * i]);
+            return true;
+        }
+    }
+    if (read_file(view_file(dense_folder + "/images", id, ".pgm"), bytes)) {
+        int w, h;
+        size_t off;
+        if (parse_pgm(bytes, w, h, off)) {
+            image = cv::Mat_<cv::Vec3b>(h, w);
+            for (size_t i = 0; i < (size_t)w * h; ++i) image.ptr()[i] = cv::Vec3b(bytes[off + i], bytes[off + i], bytes[off + i]);
+            return true;
+        }
+    }
+#ifdef ACMMP_WITH_NVJPEG
+    if (read_file(view_file(dense_folder + "/images", id, ".jpg"), bytes) && decode_jpeg_bgr(bytes, image)) return true;
+#endif
+    return false;
+}
+
+// cv::resize INTER_LINEAR on an 8-bit 3-channel image (RescaleImageAndCamera, ACMMP.cpp:236): OpenCV's fixed-point scheme --
+// coefficients rounded to 1/2048, horizontal pass in integers, vertical pass
+// ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+void ResizeLinearBgr(const cv::Mat_<cv::Vec3b> &src, cv::Mat_<cv::Vec3b> &dst, int new_cols, int new_rows)
+{
+    const int sw = src.cols, sh = src.rows;
+    dst = cv::Mat_<cv::Vec3b>(new_rows, new_cols);
+    const double scale_x = (double)sw / new_cols, scale_y = (double)sh / new_rows;
+    auto coeff = [](float f) {
+        const float v = f * 2048.0f;
+        return (int)std::lrintf(v);
+    };
+    std::vector<int> xofs(new_cols), xa0(new_cols), xa1(new_cols);
+    for (int dx = 0; dx < new_cols; ++dx) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)std::floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0.f; sx = 0; }
+        if (sx >= sw - 1) { fx = 0.f; sx = sw - 1; }
+        xofs[dx] = sx;
+        xa0[dx] = coeff(1.f - fx);
+        xa1[dx] = coeff(fx);
+    }
+    std::vector<int> row0((size_t)new_cols * 3), row1((size_t)new_cols * 3);
+    int cached0 = -1, cached1 = -1;
+    auto hresize = [&](int sy, std::vector<int> &out) {
+        const cv::Vec3b *S = src.ptr() + (size_t)sy * sw;
+        for (int dx = 0; dx < new_cols; ++dx) {
+            const int sx = xofs[dx], sx1 = sx + 1 < sw ? sx + 1 : sx;
+            for (int k = 0; k < 3; ++k) out[3 * (size_t)dx + k] = S[sx][k] * xa0[dx] + S[sx1][k] * xa1[dx];
+        }
+    };
+    for (int dy = 0; dy < new_rows; ++dy) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)std::floor(fy);
+        fy -= sy;
+        if (sy < 0) { fy = 0.f; sy = 0; }
+        if (sy >= sh - 1) { fy = 0.f; sy = sh - 1; }
+        const int sy1 = sy + 1 < sh ? sy + 1 : sy;
+        if (cached0 != sy) {
+            if (cached1 == sy) { row0.swap(row1); cached0 = sy; cached1 = -1; }
+            else { hresize(sy, row0); cached0 = sy; }
+        }
+        if (cached1 != sy1) { hresize(sy1, row1); cached1 = sy1; }
+        const int b0 = coeff(1.f - fy), b1 = coeff(fy);
+        cv::Vec3b *D = dst.ptr() + (size_t)dy * new_cols;
+        for (int dx = 0; dx < new_cols; ++dx)
+            for (int k = 0; k < 3; ++k) {
+                const int v = (((b0 * (row0[3 * (size_t)dx + k] >> 4)) >> 16) + ((b1 * (row1[3 * (size_t)dx + k] >> 4)) >> 16) + 2) >> 2;
+                D[dx][k] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+    }
 }
 
 bool ImageSize(const std::string &dense_folder, int id, int &cols, int &rows)

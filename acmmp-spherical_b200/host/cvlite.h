@@ -29,6 +29,14 @@ struct Vec3f {
     const float &operator[](int i) const { return v[i]; }
 };
 
+struct Vec3b {
+    unsigned char v[3] = {0, 0, 0};
+    Vec3b() {}
+    Vec3b(unsigned char a, unsigned char b, unsigned char c) { v[0] = a; v[1] = b; v[2] = c; }
+    unsigned char &operator[](int i) { return v[i]; }
+    const unsigned char &operator[](int i) const { return v[i]; }
+};
+
 template <typename T>
 class Mat_ {
 public:

@@ -57,6 +57,28 @@ int acmmp_host_resize_linear(const float *src, int w, int h, float *dst, int nw,
 
 // points: n x (x, y) int32; out: up to cap index triples; returns the number of triangles.
 // acmmp_host_delaunay_rect: with the enclosing triangle cv::Subdiv2D builds for Rect(0, 0, w, h) (see delaunay.cpp).
+// cv::resize INTER_LINEAR on an 8-bit B, G, R image (tests compare it with cv2.resize)
+int acmmp_host_resize_linear_bgr(const unsigned char *src, int w, int h, unsigned char *dst, int nw, int nh)
+{
+    if (!src || !dst || w <= 0 || h <= 0 || nw <= 0 || nh <= 0) return -1;
+    cv::Mat_<cv::Vec3b> a(h, w), b;
+    std::memcpy(a.ptr(), src, (size_t)w * h * 3);
+    ResizeLinearBgr(a, b, nw, nh);
+    std::memcpy(dst, b.ptr(), (size_t)nw * nh * 3);
+    return 0;
+}
+
+// LoadColourImage: the B, G, R image of a view of a dense folder (w*h*3 bytes)
+int acmmp_host_load_colour(const char *dense_folder, int id, unsigned char *dst, int cap, int *w, int *h)
+{
+    cv::Mat_<cv::Vec3b> img;
+    if (!LoadColourImage(dense_folder, id, img)) return -1;
+    *w = img.cols; *h = img.rows;
+    if ((size_t)cap < img.total() * 3) return -2;
+    std::memcpy(dst, img.ptr(), img.total() * 3);
+    return 0;
+}
+
 int acmmp_host_delaunay_rect(const int32_t *points, int n, int w, int h, int32_t *out, int cap)
 {
     std::vector<cv::Point> pts(n);

@@ -320,6 +320,11 @@ const char *acmmp_fusion_last_error(const acmmp_fusion *f);
  * and grey levels 0..255 (w*h) at that size.  Host pointers; copied to the device. */
 int acmmp_fusion_set_view(acmmp_fusion *f, int index, const acmmp_camera *cam, int w, int h, const float *depth,
                           const float *normals3, const float *gray);
+/* Optional, after acmmp_fusion_set_view[_device] of that view: its colour image at the depth map's size, w*h*3 bytes in
+ * OpenCV's order (B, G, R per pixel: cv::imread(IMREAD_COLOR) + RescaleImageAndCamera, ACMMP.cu:1862-1872).  Without it
+ * the fused points carry the grey level in all three channels.  acmmp_point::color is (B, G, R) like PointList::color
+ * (ACMMP.cu:1704-1708; the PLY writer swaps back, ACMMP.cpp:509-511). */
+int acmmp_fusion_set_view_colour(acmmp_fusion *f, int index, const uint8_t *bgr, int w, int h);
 /* The same with DEVICE pointers that stay valid until the object is destroyed (resident chain: the depth /
  * normal maps a PatchMatch context holds, acmmp_device_buffers): normals4 = float4 per pixel. */
 int acmmp_fusion_set_view_device(acmmp_fusion *f, int index, const acmmp_camera *cam, int w, int h, const float *depth_dev,

@@ -289,7 +289,8 @@ class RefFusion:
     """The reference's SimpleFusionKernel (ACMMP.cu:1664-1814) behind the texture set-up of RunFusionCuda (see ref_harness.cu);
     run(ref, src) returns the points of one reference view filtered on the host in pixel order like ACMMP.cu:2069-2076."""
 
-    def __init__(self, cams, depths, normals, grays):
+    def __init__(self, cams, depths, normals, grays, colours=None):
+        """colours: optional list of uint8 [h, w, 3] images in OpenCV's B, G, R order (the reference's cv::imread(IMREAD_COLOR))."""
         from acmmp_b200 import Camera
         self._l = lib()
         n = len(cams)
@@ -300,8 +301,17 @@ class RefFusion:
         ws = (C.c_int * n)(*[s[1] for s in self.sizes])
         hs = (C.c_int * n)(*[s[0] for s in self.sizes])
         FP = C.POINTER(C.c_float)
-        self._h = C.c_void_p(self._l.ref_fusion_create(C.c_int(n), (Camera * n)(*cams), ws, hs, (FP * n)(*[_fp(x) for x in self.d]),
-                                                       (FP * n)(*[_fp(x) for x in self.nm]), (FP * n)(*[_fp(x) for x in self.g])))
+        if colours is None:
+            self._h = C.c_void_p(self._l.ref_fusion_create(C.c_int(n), (Camera * n)(*cams), ws, hs, (FP * n)(*[_fp(x) for x in self.d]),
+                                                           (FP * n)(*[_fp(x) for x in self.nm]), (FP * n)(*[_fp(x) for x in self.g])))
+        else:
+            self.c = [np.ascontiguousarray(x, np.uint8) for x in colours]
+            assert all(c.shape == s + (3,) for c, s in zip(self.c, self.sizes))
+            BP = C.POINTER(C.c_ubyte)
+            self._l.ref_fusion_create_bgr.restype = C.c_void_p
+            self._h = C.c_void_p(self._l.ref_fusion_create_bgr(C.c_int(n), (Camera * n)(*cams), ws, hs, (FP * n)(*[_fp(x) for x in self.d]),
+                                                               (FP * n)(*[_fp(x) for x in self.nm]), (FP * n)(*[_fp(x) for x in self.g]),
+                                                               (BP * n)(*[x.ctypes.data_as(BP) for x in self.c])))
         self.kernel_ms = 0.0
 
     def run(self, ref, src_indices):

@@ -560,9 +560,18 @@ static cudaTextureObject_t ref_make_tex(RefFusion *f, const void *host, int w, i
     return t;
 }
 
-// depths[i]: w*h floats; normals3[i]: w*h*3; gray[i]: w*h grey levels 0..255 (the colour texture gets (g, g, g, 1) / 255)
+// depths[i]: w*h floats; normals3[i]: w*h*3; gray[i]: w*h grey levels 0..255 (the colour texture gets (g, g, g, 1) / 255);
+// bgr (may be null) / bgr[i]: w*h*3 bytes in OpenCV's B, G, R order -- the texture then gets what cvtColor(BGR2RGBA) +
+// convertTo(CV_32FC4, 1 / 255) produce (ACMMP.cu:1951-1955): (R, G, B, 1) / 255
+void *ref_fusion_create_bgr(int n, const Camera *cams, const int *ws, const int *hs, const float *const *depths,
+                            const float *const *normals3, const float *const *gray, const unsigned char *const *bgr);
 void *ref_fusion_create(int n, const Camera *cams, const int *ws, const int *hs, const float *const *depths,
                         const float *const *normals3, const float *const *gray)
+{
+    return ref_fusion_create_bgr(n, cams, ws, hs, depths, normals3, gray, nullptr);
+}
+void *ref_fusion_create_bgr(int n, const Camera *cams, const int *ws, const int *hs, const float *const *depths,
+                            const float *const *normals3, const float *const *gray, const unsigned char *const *bgr)
 {
     RefFusion *f = new RefFusion();
     f->n = n;
@@ -576,6 +585,13 @@ void *ref_fusion_create(int n, const Camera *cams, const int *ws, const int *hs,
         std::vector<float> n4(4 * npx), rgba(4 * npx);
         for (size_t k = 0; k < npx; ++k) {
             n4[4 * k] = normals3[i][3 * k]; n4[4 * k + 1] = normals3[i][3 * k + 1]; n4[4 * k + 2] = normals3[i][3 * k + 2]; n4[4 * k + 3] = 1.0f;
+            if (bgr && bgr[i]) {
+                rgba[4 * k] = (float)(bgr[i][3 * k + 2] * (1.0 / 255.0));
+                rgba[4 * k + 1] = (float)(bgr[i][3 * k + 1] * (1.0 / 255.0));
+                rgba[4 * k + 2] = (float)(bgr[i][3 * k] * (1.0 / 255.0));
+                rgba[4 * k + 3] = 1.0f;
+                continue;
+            }
             const float g = (float)(gray[i][k] * (1.0 / 255.0));      // convertTo(CV_32FC4, 1.0 / 255.0), ACMMP.cu:1951
             rgba[4 * k] = g; rgba[4 * k + 1] = g; rgba[4 * k + 2] = g; rgba[4 * k + 3] = 1.0f;
         }

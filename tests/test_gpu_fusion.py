@@ -27,8 +27,18 @@ def _inputs(scene, noise=0.002, holes=0.02, seed=9):
     return depths, normals
 
 
+def _colour_images(scene):
+    """B, G, R images with three DIFFERENT channels (a swapped pair would show): grey, shifted grey, inverted grey."""
+    out = []
+    for img in scene.images:
+        g = np.clip(img, 0, 255).astype(np.uint8)
+        out.append(np.ascontiguousarray(np.stack([g, np.roll(g, 5, axis=1), 255 - g], axis=-1)))
+    return out
+
+
+@pytest.mark.parametrize("colour", [False, True])
 @pytest.mark.parametrize("model", ["pinhole", "sphere"])
-def test_fusion_matches_the_reference_kernel(model):
+def test_fusion_matches_the_reference_kernel(model, colour):
     from acmmp_b200 import Fusion, synth
     from oracle.ref_driver import RefFusion
     scene = (synth.make_pinhole_scene(n_views=5, width=640, height=480, focal=500.0, seed=1) if model == "pinhole"
@@ -36,9 +46,12 @@ def test_fusion_matches_the_reference_kernel(model):
     depths, normals = _inputs(scene)
     n = len(scene.images)
     mine = Fusion(n, 0)
+    bgr = _colour_images(scene) if colour else None
     for v in range(n):
         mine.set_view(v, scene.cams[v], depths[v], normals[v], scene.images[v])
-    ref = RefFusion(scene.cams, depths, normals, scene.images)
+        if colour:
+            mine.set_view_colour(v, bgr[v])
+    ref = RefFusion(scene.cams, depths, normals, scene.images, colours=bgr)
     res = {}
     for r in range(n):
         src = list(scene.pairs[r][1])
@@ -58,9 +71,10 @@ def test_fusion_matches_the_reference_kernel(model):
             coord_within_1e4=float((np.abs(A[:, :3] - B[:, :3]) <= 1e-4 * scale).all(axis=1).mean()),
             normal_within_1e4=float((np.abs(A[:, 3:6] - B[:, 3:6]) <= 1e-4).all(axis=1).mean()),
             colour_within_half_level=float((np.abs(A[:, 6:] - B[:, 6:]) <= 0.5).all(axis=1).mean()),
+            channels_differ=float((np.abs(B[:, 6] - B[:, 8]) > 1.0).mean()),
             kernel_ms_mine=mine.kernel_ms, kernel_ms_ref=ref.kernel_ms)
         assert len(pa) == int(fa.sum())
-    dump(f"fusion_{model}", res)
+    dump(f"fusion_{model}" + ("_colour" if colour else ""), res)
     mine.close()
     ref.close()
     for k, v in res.items():
@@ -68,6 +82,8 @@ def test_fusion_matches_the_reference_kernel(model):
         assert v["flags_equal"] >= 0.9995, (k, v)
         assert v["coord_within_1e4"] >= 0.9999 and v["normal_within_1e4"] >= 0.9999, (k, v)
         assert v["colour_within_half_level"] >= 0.999, (k, v)
+        if colour:
+            assert v["channels_differ"] > 0.5, (k, v)          # the test images really have three different channels
 
 
 def test_fusion_edge_cases():
