@@ -304,3 +304,39 @@ def test_delaunay_triangle_set_equals_cv2_subdiv2d_at_full_resolution(host, kind
     # co-circular ties the same way on this input)
     assert frac_common >= 0.999, res
     assert res["only_theirs_cocircular"] >= 0.98 and res["only_mine_cocircular"] >= 0.98, res
+
+
+@pytest.mark.parametrize("shape,new", [((205, 410), (160, 320)), ((64, 96), (100, 141)), ((300, 400), (150, 200)), ((33, 57), (33, 29))])
+def test_colour_resize_matches_cv_resize_on_8_bit_images(host, shape, new):
+    """ResizeLinearBgr = cv::resize INTER_LINEAR on an 8-bit 3-channel image (RescaleImageAndCamera, ACMMP.cpp:236; the
+    fusion's colour input): OpenCV's fixed-point scheme.  cv2 wheels may route 8-bit resizes through a SIMD / IPP path
+    that rounds differently by one level on a few pixels, hence <= 1 everywhere and equal almost everywhere."""
+    import cv2
+    rng = np.random.default_rng(4)
+    src = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+    src[: shape[0] // 2] = np.clip(np.cumsum(rng.integers(-3, 4, (shape[0] // 2, shape[1], 3)), axis=1) + 128, 0, 255).astype(np.uint8)
+    nh, nw = new
+    dst = np.zeros((nh, nw, 3), np.uint8)
+    u8 = C.POINTER(C.c_ubyte)
+    assert host.acmmp_host_resize_linear_bgr(src.ctypes.data_as(u8), shape[1], shape[0], dst.ctypes.data_as(u8), nw, nh) == 0
+    want = cv2.resize(src, (nw, nh), interpolation=cv2.INTER_LINEAR)
+    d = np.abs(dst.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1, d.max()
+    assert (d == 0).mean() >= 0.98, (d == 0).mean()
+
+
+def test_colour_image_loader_reads_ppm_twins_in_opencv_channel_order(host, tmp_path):
+    """images/%08d.ppm (P6: R, G, B) -> B, G, R like cv::imread(IMREAD_COLOR); a view with only a .pgm gets (g, g, g)."""
+    import cv2
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, (23, 31, 3), dtype=np.uint8)
+    (tmp_path / "images").mkdir()
+    assert cv2.imwrite(str(tmp_path / "images" / "00000000.ppm"), bgr)                 # cv2 takes B, G, R and writes R, G, B
+    grey = rng.integers(0, 256, (23, 31), dtype=np.uint8)
+    assert cv2.imwrite(str(tmp_path / "images" / "00000001.pgm"), grey)
+    u8 = C.POINTER(C.c_ubyte)
+    for view, want in ((0, bgr), (1, np.repeat(grey[..., None], 3, axis=-1))):
+        got = np.zeros((23, 31, 3), np.uint8)
+        w, h = C.c_int(), C.c_int()
+        assert host.acmmp_host_load_colour(str(tmp_path).encode(), view, got.ctypes.data_as(u8), got.size, C.byref(w), C.byref(h)) == 0
+        assert (w.value, h.value) == (31, 23) and np.array_equal(got, want)

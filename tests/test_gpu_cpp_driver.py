@@ -29,6 +29,11 @@ def test_cpp_driver_runs_the_reference_schedule_on_a_dense_folder(tmp_path):
     # 1100 px -> two pyramid levels (550 and 1100): JBU + hierarchy + prior + 2 geometric rounds per level
     scene = synth.make_pinhole_scene(n_views=4, width=1100, height=820, focal=950.0, seed=3)
     synth.write_dense_folder(scene, str(tmp_path), pgm=True)
+    # colour twins for the fused points (the reference reads the .jpg in colour, ACMMP.cu:1862): B = g, G = shifted g, R = 255 - g
+    import cv2
+    for v, img in enumerate(scene.images):
+        g = np.clip(img, 0, 255).astype(np.uint8)
+        assert cv2.imwrite(str(tmp_path / "images" / ("%08d.ppm" % v)), np.stack([g, np.roll(g, 5, axis=1), 255 - g], axis=-1))
     r = subprocess.run([str(DRIVER), str(tmp_path), "--seed", "7"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     summary = json.loads(r.stdout.strip().splitlines()[-1])
@@ -55,6 +60,10 @@ def test_cpp_driver_runs_the_reference_schedule_on_a_dense_folder(tmp_path):
     res["fusion_points"] = n_points
     res["fusion_points_per_pixel"] = n_points / (4.0 * scene.depths_gt[0].size)
     res["fusion_unit_normals"] = float((np.abs(np.linalg.norm(pts["n"], axis=-1) - 1) < 1e-3).mean())
+    # PLY order red, green, blue: red = mean of (255 - g), blue = mean of g over the consistent views => red + blue = 255
+    rb = pts["rgb"][:, 0].astype(int) + pts["rgb"][:, 2].astype(int)
+    res["fusion_red_plus_blue_is_255"] = float((np.abs(rb - 255) <= 2).mean())
+    res["fusion_colour_spread"] = float(np.abs(pts["rgb"][:, 0].astype(int) - pts["rgb"][:, 2].astype(int)).mean())
     # every fused point projects into view 0 at a depth that agrees with that view's ground-truth depth
     R, t, K = scene.Rs[0], scene.ts[0], scene.Ks[0]
     Xc = pts["xyz"].astype(np.float64) @ R.T + t
@@ -70,6 +79,7 @@ def test_cpp_driver_runs_the_reference_schedule_on_a_dense_folder(tmp_path):
         assert res[f"view{v}_within_1pct_of_gt"] > 0.85, res
         assert res[f"view{v}_unit_normals"] > 0.99, res
     assert res["fusion_points_per_pixel"] > 0.3 and res["fusion_unit_normals"] > 0.99, res
+    assert res["fusion_red_plus_blue_is_255"] > 0.99 and res["fusion_colour_spread"] > 10, res      # colours, in the right channels
     assert res["fusion_points_within_2pct_of_gt_surface"] > 0.8, res      # occluded points excepted
 
 
