@@ -86,7 +86,7 @@ _EXPORTS = [
     "acmmp_jbu", "acmmp_jbu_device", "acmmp_probe_ncc", "acmmp_probe_coords", "acmmp_probe_geom", "acmmp_probe_warp",
     "acmmp_probe_initcost", "acmmp_last_timings", "acmmp_launch_count",
     "acmmp_fusion_create", "acmmp_fusion_destroy", "acmmp_fusion_last_error", "acmmp_fusion_set_view", "acmmp_fusion_set_view_colour", "acmmp_fusion_set_view_device",
-    "acmmp_fusion_run", "acmmp_fusion_last_flags",
+    "acmmp_fusion_run", "acmmp_fusion_run_ply", "acmmp_fusion_last_flags",
 ]
 
 _lib = None
@@ -486,6 +486,17 @@ class Fusion:
             if n.value <= cap:
                 self._ck(rc, "acmmp_fusion_run")
             cap = n.value
+
+    def run_ply(self, ref, src_indices):
+        """The points of one reference view as the PLY file's 27-byte vertex records -> uint8 [n, 27]."""
+        src = np.ascontiguousarray(src_indices, np.int32)
+        h, w = self.sizes[ref]
+        rec = np.empty((h * w, 27), np.uint8)
+        n, ms = C.c_int(0), C.c_float(0)
+        self._ck(self._l.acmmp_fusion_run_ply(self._h, C.c_int(ref), C.c_int(len(src)), src.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              rec.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(h * w), C.byref(n), C.byref(ms)), "acmmp_fusion_run_ply")
+        self.kernel_ms = float(ms.value)
+        return rec[: n.value].copy()
 
     def last_flags(self, ref):
         h, w = self.sizes[ref]

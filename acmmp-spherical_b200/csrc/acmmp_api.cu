@@ -2064,12 +2064,13 @@ int acmmp_fusion_set_view_colour(acmmp_fusion *f, int index, const uint8_t *bgr,
     return ACMMP_OK;
 }
 
-int acmmp_fusion_run(acmmp_fusion *f, int ref, int n_src, const int32_t *src, acmmp_point *points, int capacity,
-                     int *n_points, float *kernel_ms)
+// fuse one reference view and bring its points to the host: PointList records (36 bytes) or PLY vertex records (27 bytes)
+static int fusion_run_common(acmmp_fusion *f, int ref, int n_src, const int32_t *src, void *host_out, int capacity, int *n_points,
+                             float *kernel_ms, bool ply, const char *what)
 {
-    if (!f || ref < 0 || ref >= f->n || n_src < 0 || (n_src > 0 && !src) || !n_points || capacity < 0 || (capacity > 0 && !points))
-        return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_run: bad arguments");
-    if (!f->views[ref].depth) return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_run: the reference view was not set");
+    if (!f || ref < 0 || ref >= f->n || n_src < 0 || (n_src > 0 && !src) || !n_points || capacity < 0 || (capacity > 0 && !host_out))
+        return fusion_fail(f, ACMMP_E_ARG, std::string(what) + ": bad arguments");
+    if (!f->views[ref].depth) return fusion_fail(f, ACMMP_E_ARG, std::string(what) + ": the reference view was not set");
     FCK(cudaSetDevice(f->device));
     acmmp::FusionProblemDev prob;
     prob.num_src = std::min(n_src, acmmp::kFuseMaxSrc);
@@ -2098,16 +2099,22 @@ int acmmp_fusion_run(acmmp_fusion *f, int ref, int n_src, const int32_t *src, ac
         FCK(cudaMalloc(&f->counts, sizeof(int) * (size_t)nblocks));
         f->count_cap = (size_t)nblocks;
     }
-    if ((size_t)capacity > f->out_cap) {
+    // the compacted output never exceeds one record per pixel: sized by the view, so that a host buffer that turns out too
+    // small costs a second copy, not a second run
+    const int dev_capacity = std::min(capacity, npx);
+    if ((size_t)dev_capacity > f->out_cap) {
         cudaFree(f->out);
         f->out = nullptr; f->out_cap = 0;
-        FCK(cudaMalloc(&f->out, sizeof(acmmp_point) * (size_t)capacity));
-        f->out_cap = (size_t)capacity;
+        FCK(cudaMalloc(&f->out, sizeof(acmmp_point) * (size_t)dev_capacity));
+        f->out_cap = (size_t)dev_capacity;
     }
     cudaEventRecord(f->ev[0], f->stream);
     acmmp::k_fuse_view<<<nblocks, acmmp::kFuseBlock, 0, f->stream>>>(f->views_dev, ref, prob, f->dense, f->flags, f->counts);
     acmmp::k_scan_blocks<<<1, 1024, 0, f->stream>>>(f->counts, nblocks, f->total);
-    if (capacity > 0) acmmp::k_compact_points<<<nblocks, acmmp::kFuseBlock, 0, f->stream>>>(f->dense, f->flags, f->counts, npx, f->out, capacity);
+    if (dev_capacity > 0) {
+        if (ply) acmmp::k_compact_ply<<<nblocks, acmmp::kFuseBlock, 0, f->stream>>>(f->dense, f->flags, f->counts, npx, reinterpret_cast<unsigned char *>(f->out), dev_capacity);
+        else acmmp::k_compact_points<<<nblocks, acmmp::kFuseBlock, 0, f->stream>>>(f->dense, f->flags, f->counts, npx, f->out, dev_capacity);
+    }
     cudaEventRecord(f->ev[1], f->stream);
     FCK(cudaGetLastError());
     int total = 0;
@@ -2115,9 +2122,21 @@ int acmmp_fusion_run(acmmp_fusion *f, int ref, int n_src, const int32_t *src, ac
     FCK(cudaStreamSynchronize(f->stream));
     *n_points = total;
     if (kernel_ms) cudaEventElapsedTime(kernel_ms, f->ev[0], f->ev[1]);
-    if (total > capacity) return fusion_fail(f, ACMMP_E_ARG, "acmmp_fusion_run: capacity too small (n_points holds the need)");
-    if (total > 0) FCK(cudaMemcpy(points, f->out, sizeof(acmmp_point) * (size_t)total, cudaMemcpyDeviceToHost));
+    if (total > capacity) return fusion_fail(f, ACMMP_E_ARG, std::string(what) + ": capacity too small (n_points holds the need)");
+    if (total > 0) FCK(cudaMemcpy(host_out, f->out, (ply ? (size_t)27 : sizeof(acmmp_point)) * (size_t)total, cudaMemcpyDeviceToHost));
     return ACMMP_OK;
+}
+
+int acmmp_fusion_run(acmmp_fusion *f, int ref, int n_src, const int32_t *src, acmmp_point *points, int capacity,
+                     int *n_points, float *kernel_ms)
+{
+    return fusion_run_common(f, ref, n_src, src, points, capacity, n_points, kernel_ms, false, "acmmp_fusion_run");
+}
+
+int acmmp_fusion_run_ply(acmmp_fusion *f, int ref, int n_src, const int32_t *src, uint8_t *records27, int capacity,
+                         int *n_points, float *kernel_ms)
+{
+    return fusion_run_common(f, ref, n_src, src, records27, capacity, n_points, kernel_ms, true, "acmmp_fusion_run_ply");
 }
 
 /* test / inspection hook: which pixels of the last fused reference view produced a point (w*h bytes, host) */

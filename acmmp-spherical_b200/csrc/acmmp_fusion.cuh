@@ -237,6 +237,49 @@ k_compact_points(const acmmp_point *__restrict__ dense, const unsigned char *__r
     }
 }
 
+// The same compaction straight into the PLY's 27-byte vertex records (StoreColorPlyFileBinaryPointCloud, ACMMP.cpp:481-534:
+// x y z nx ny nz as little-endian floats, then red green blue = (char)(int) of color.z, .y, .x; a point with a non-finite
+// coordinate is written at the origin, :505-508): the host appends the bytes to the file as they are.
+__global__ void __launch_bounds__(kFuseBlock)
+k_compact_ply(const acmmp_point *__restrict__ dense, const unsigned char *__restrict__ flags, const int *__restrict__ block_offsets,
+              const int npx, unsigned char *__restrict__ out, const int capacity)
+{
+    __shared__ int warp_base[kFuseBlock / 32];
+    const int idx = blockIdx.x * kFuseBlock + threadIdx.x;
+    const bool valid = idx < npx && flags[idx];
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_base[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < kFuseBlock / 32; ++w) {
+            const int c = warp_base[w];
+            warp_base[w] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    if (valid) {
+        const int pos = block_offsets[blockIdx.x] + warp_base[warp] + __popc(ballot & ((1u << lane) - 1u));
+        if (pos < capacity) {
+            const acmmp_point p = dense[idx];
+            float v[6] = {p.coord[0], p.coord[1], p.coord[2], p.normal[0], p.normal[1], p.normal[2]};
+            const float big = 3.402823466e+38f;
+            if (!(v[0] < big && v[0] > -big) || !(v[1] < big && v[1] > -big) || !(v[2] < big && v[2] >= -big)) v[0] = v[1] = v[2] = 0.0f;
+            unsigned char *o = out + (size_t)27 * pos;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const unsigned u = __float_as_uint(v[k]);
+                o[4 * k] = (unsigned char)u; o[4 * k + 1] = (unsigned char)(u >> 8); o[4 * k + 2] = (unsigned char)(u >> 16); o[4 * k + 3] = (unsigned char)(u >> 24);
+            }
+            o[24] = (unsigned char)(int)p.color[2];
+            o[25] = (unsigned char)(int)p.color[1];
+            o[26] = (unsigned char)(int)p.color[0];
+        }
+    }
+}
+
 // (H, W, 3) normals -> float4 per pixel
 __global__ void __launch_bounds__(256)
 k_pack_normals(const float *__restrict__ n3, const int npx, float4 *__restrict__ n4)

@@ -5,7 +5,10 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <chrono>
+#include <future>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <unordered_map>
 #include <stdexcept>
@@ -209,6 +212,13 @@ void ACMMP::Park(bool keep_prior, bool keep_host_result)
     params_.geom_consistency = params_.multi_geometry = 0;
     if (!keep_prior) params_.planar_prior = 0;
     if (!keep_host_result) planes_host_ = costs_host_ = nullptr;
+}
+
+const float *ACMMP::GetPlanesDevice()
+{
+    void *planes = nullptr, *costs = nullptr;
+    check(acmmp_device_buffers(ctx_, &planes, &costs), "GetPlanesDevice");
+    return static_cast<const float *>(planes);
 }
 
 void ACMMP::SetNeighbourDepthMapsDevice(const std::vector<const float *> &maps_dev, const std::vector<int> &widths,
@@ -530,54 +540,77 @@ void RunJBU(const cv::Mat_<float> &scaled_image_float, const cv::Mat_<float> &sr
 }
 
 // reference ACMMP.cu:1817-2105 (host part) over acmmp_fusion_* (device part)
-size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem> &problems, bool geom_consistency, int device, double *kernel_ms)
+size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem> &problems, bool geom_consistency, int device, double *kernel_ms,
+                     const std::vector<ResidentView> *resident)
 {
     static_assert(sizeof(PointList) == sizeof(acmmp_point), "PointList must mirror acmmp_point");
     const size_t N = problems.size();
     std::cout << "[CUDA Fusion] Starting simple fusion with " << N << " images..." << std::endl;
     struct View {
+        bool ok = false;
         Camera cam;
         cv::Mat_<float> depth, gray;
         cv::Mat_<cv::Vec3f> normal;
         cv::Mat_<cv::Vec3b> colour;          // empty: no colour source, the grey level goes to all three channels
+        const ResidentView *dev = nullptr;   // maps still on the device: nothing to read back
         Problem problem;
     };
-    std::vector<View> views;
-    std::map<int, int> id_to_index;
-    for (size_t i = 0; i < N; ++i) {
+    const auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    std::map<int, const ResidentView *> resident_of;
+    if (resident)
+        for (const ResidentView &r : *resident) resident_of[r.ref_image_id] = &r;
+    // one view: maps (from the device-resident table or the .dmb files), grey and colour image, camera at the map's size
+    auto load_view = [&](const size_t i, View &v) {
         const int id = problems[i].ref_image_id;
-        View v;
-        std::stringstream cam_path;
-        cam_path << dense_folder << "/cams/" << std::setw(8) << std::setfill('0') << id << "_cam.txt";
-        v.cam = ReadCamera(cam_path.str());
-        const std::string folder = result_folder_of(dense_folder, id);
-        if (readDepthDmb(folder + (geom_consistency ? "/depths_geom.dmb" : "/depths.dmb"), v.depth) != 0) {
-            std::cerr << "Warning: Could not load depth for image " << id << std::endl;
-            continue;
+        v.problem = problems[i];
+        const auto rit = resident_of.find(id);
+        int cols = 0, rows = 0;
+        if (rit != resident_of.end()) {
+            v.dev = rit->second;
+            v.cam = v.dev->cam;
+            cols = v.dev->width;
+            rows = v.dev->height;
+        } else {
+            std::stringstream cam_path;
+            cam_path << dense_folder << "/cams/" << std::setw(8) << std::setfill('0') << id << "_cam.txt";
+            v.cam = ReadCamera(cam_path.str());
+            const std::string folder = result_folder_of(dense_folder, id);
+            if (readDepthDmb(folder + (geom_consistency ? "/depths_geom.dmb" : "/depths.dmb"), v.depth) != 0) {
+                std::cerr << "Warning: Could not load depth for image " << id << std::endl;
+                return;
+            }
+            if (readNormalDmb(folder + "/normals.dmb", v.normal) != 0) {
+                std::cerr << "Warning: Could not load normals for image " << id << std::endl;
+                return;
+            }
+            cols = v.depth.cols;
+            rows = v.depth.rows;
         }
-        if (readNormalDmb(folder + "/normals.dmb", v.normal) != 0) {
-            std::cerr << "Warning: Could not load normals for image " << id << std::endl;
-            continue;
-        }
-        cv::Mat_<float> image;
-        if (!LoadGreyImage(dense_folder, id, image)) {
-            std::cerr << "Warning: Could not load image " << id << std::endl;
-            continue;
-        }
-        // RescaleImageAndCamera (ACMMP.cpp:213-245): image and intrinsics to the depth map's resolution
-        const int cols = v.depth.cols, rows = v.depth.rows;
-        v.cam.width = cols;
-        v.cam.height = rows;
         cv::Mat_<cv::Vec3b> colour;
-        if (LoadColourImage(dense_folder, id, colour) && colour.cols == image.cols && colour.rows == image.rows) {
+        const bool have_colour = LoadColourImage(dense_folder, id, colour);
+        int image_cols = have_colour ? colour.cols : 0, image_rows = have_colour ? colour.rows : 0;
+        if (!v.dev) {
+            cv::Mat_<float> image;
+            if (!LoadGreyImage(dense_folder, id, image)) {
+                std::cerr << "Warning: Could not load image " << id << std::endl;
+                return;
+            }
+            image_cols = image.cols;
+            image_rows = image.rows;
+            if (cols == image.cols && rows == image.rows) v.gray = image;
+            else ResizeLinear(image, v.gray, cols, rows);
+        }
+        if (have_colour && colour.cols == image_cols && colour.rows == image_rows) {
             if (cols == colour.cols && rows == colour.rows) v.colour = colour;
             else ResizeLinearBgr(colour, v.colour, cols, rows);
         }
-        if (cols == image.cols && rows == image.rows) {
-            v.gray = image;
-        } else {
-            const float scale_x = cols / static_cast<float>(image.cols), scale_y = rows / static_cast<float>(image.rows);
-            ResizeLinear(image, v.gray, cols, rows);
+        // RescaleImageAndCamera (ACMMP.cpp:213-245): image and intrinsics to the depth map's resolution (a resident view's
+        // camera already is the finest level's)
+        v.cam.width = cols;
+        v.cam.height = rows;
+        if (!v.dev && !(cols == image_cols && rows == image_rows)) {
+            const float scale_x = cols / static_cast<float>(image_cols), scale_y = rows / static_cast<float>(image_rows);
             if (v.cam.model == SPHERE) {
                 v.cam.params[1] *= scale_x;
                 v.cam.params[2] *= scale_y;
@@ -586,62 +619,107 @@ size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem>
                 v.cam.K[4] *= scale_y; v.cam.K[5] *= scale_y;
             }
         }
-        v.problem = problems[i];
-        id_to_index[id] = (int)views.size();
-        views.push_back(v);
+        v.ok = true;
+    };
+    // file reads, decoding and resampling of the views on a few host threads (the JPEG decoder serialises itself)
+    std::vector<View> loaded(N);
+    {
+        const size_t workers = std::min<size_t>(8, std::max<size_t>(1, N));
+        std::vector<std::future<void>> jobs;
+        for (size_t w = 0; w < workers; ++w)
+            jobs.push_back(std::async(std::launch::async, [&, w]() {
+                for (size_t i = w; i < N; i += workers) load_view(i, loaded[i]);
+            }));
+        for (auto &j : jobs) j.get();
     }
+    std::vector<View> views;
+    std::map<int, int> id_to_index;
+    for (size_t i = 0; i < N; ++i) {
+        if (!loaded[i].ok) continue;
+        id_to_index[problems[i].ref_image_id] = (int)views.size();
+        views.push_back(std::move(loaded[i]));
+    }
+    loaded.clear();
     const size_t num_valid = views.size();
     std::cout << "[CUDA Fusion] Successfully loaded " << num_valid << "/" << N << " images" << std::endl;
     if (num_valid == 0) {
         std::cerr << "Error: No valid images to process!" << std::endl;
         return 0;
     }
+    const double t_loaded = now();
     acmmp_fusion *f = nullptr;
     if (acmmp_fusion_create(device, (int)num_valid, &f) != ACMMP_OK) throw std::runtime_error("RunFusionCuda: no usable sm_100 device (there is no CPU fallback)");
+    unsigned char *staging[2] = {nullptr, nullptr};
     auto fail = [&](const char *what) {
         const std::string msg = std::string("RunFusionCuda (") + what + "): " + acmmp_fusion_last_error(f);
         acmmp_fusion_destroy(f);
+        for (unsigned char *p : staging)
+            if (p) cudaFreeHost(p);
         throw std::runtime_error(msg);
     };
+    size_t max_px = 0;
     for (size_t i = 0; i < num_valid; ++i) {
         const View &v = views[i];
-        if (acmmp_fusion_set_view(f, (int)i, &v.cam, v.depth.cols, v.depth.rows, v.depth.ptr(), reinterpret_cast<const float *>(v.normal.ptr()),
-                                  v.gray.ptr()) != ACMMP_OK)
-            fail("set_view");
-        if (!v.colour.empty() &&
-            acmmp_fusion_set_view_colour(f, (int)i, reinterpret_cast<const uint8_t *>(v.colour.ptr()), v.depth.cols, v.depth.rows) != ACMMP_OK)
+        const int cols = v.cam.width, rows = v.cam.height;
+        max_px = std::max(max_px, (size_t)cols * rows);
+        const int rc = v.dev ? acmmp_fusion_set_view_device(f, (int)i, &v.cam, cols, rows, v.dev->depth_dev, v.dev->planes4_dev, v.dev->gray_dev)
+                             : acmmp_fusion_set_view(f, (int)i, &v.cam, cols, rows, v.depth.ptr(), reinterpret_cast<const float *>(v.normal.ptr()), v.gray.ptr());
+        if (rc != ACMMP_OK) fail("set_view");
+        if (!v.colour.empty() && acmmp_fusion_set_view_colour(f, (int)i, reinterpret_cast<const uint8_t *>(v.colour.ptr()), cols, rows) != ACMMP_OK)
             fail("set_view_colour");
     }
-    std::vector<PointList> all_points;
+    const double t_uploaded = now();
+    // Pass 1: how many points every view yields (the kernel alone: 2 ms per 3200x2130 view) -- the PLY header carries the
+    // total.  Pass 2: the points leave the device as the file's 27-byte vertex records into a pinned buffer and go from there
+    // straight into the file, a writer thread taking view i while the device fuses view i + 1.  The reference copies 36 bytes
+    // + a flag per PIXEL to the host, filters there, collects a vector of PointList and issues nine fwrite calls per point
+    // (ACMMP.cu:2056-2076, ACMMP.cpp:481-534).
+    std::vector<std::vector<int32_t>> srcs(num_valid);
+    std::vector<int> counts(num_valid, 0);
+    size_t total_points = 0;
     double ms_sum = 0.0;
     for (size_t i = 0; i < num_valid; ++i) {
         const View &v = views[i];
-        const int width = v.cam.width, height = v.cam.height;
-        std::cout << "[CUDA Fusion] Processing image " << (i + 1) << "/" << num_valid << " (ID=" << v.problem.ref_image_id << ", " << width << "x"
-                  << height << ")" << std::endl;
-        std::vector<int32_t> src;
         for (size_t j = 0; j < std::min<size_t>(v.problem.src_image_ids.size(), 32); ++j) {
             const auto it = id_to_index.find(v.problem.src_image_ids[j]);
-            src.push_back(it != id_to_index.end() ? it->second : -1);
+            srcs[i].push_back(it != id_to_index.end() ? it->second : -1);
         }
-        int capacity = std::max(width * height / 2, 1024), count = 0;
-        std::vector<PointList> points((size_t)capacity);
         float ms = 0.f;
-        int rc = acmmp_fusion_run(f, (int)i, (int)src.size(), src.data(), reinterpret_cast<acmmp_point *>(points.data()), capacity, &count, &ms);
-        if (rc == ACMMP_E_ARG && count > capacity) {
-            capacity = count;
-            points.resize((size_t)capacity);
-            rc = acmmp_fusion_run(f, (int)i, (int)src.size(), src.data(), reinterpret_cast<acmmp_point *>(points.data()), capacity, &count, &ms);
-        }
-        if (rc != ACMMP_OK) fail("run");
-        ms_sum += ms;
-        all_points.insert(all_points.end(), points.begin(), points.begin() + count);
-        std::cout << "  -> Generated " << count << " points" << std::endl;
+        const int rc = acmmp_fusion_run_ply(f, (int)i, (int)srcs[i].size(), srcs[i].data(), nullptr, 0, &counts[i], &ms);
+        if (rc != ACMMP_OK && counts[i] <= 0) fail("count");          // "capacity too small" is the answer asked for
+        total_points += (size_t)counts[i];
     }
-    acmmp_fusion_destroy(f);
     const std::string output_path = dense_folder + "/ACMMP/ACMM_model_cuda_5.ply";
-    StoreColorPlyFileBinaryPointCloud(output_path, all_points);
-    std::cout << "[CUDA Fusion] Complete! Wrote " << all_points.size() << " points to " << output_path << std::endl;
+    FILE *ply = OpenPlyForVertexRecords(output_path, total_points);
+    for (auto &p : staging)
+        if (cudaMallocHost(reinterpret_cast<void **>(&p), 27 * max_px) != cudaSuccess) { p = nullptr; fclose(ply); fail("pinned staging buffer"); }
+    std::future<bool> writer;
+    bool write_ok = true;
+    for (size_t i = 0; i < num_valid; ++i) {
+        const View &v = views[i];
+        std::cout << "[CUDA Fusion] Processing image " << (i + 1) << "/" << num_valid << " (ID=" << v.problem.ref_image_id << ", " << v.cam.width
+                  << "x" << v.cam.height << ")" << std::endl;
+        unsigned char *buf = staging[i & 1];
+        int count = 0;
+        float ms = 0.f;
+        if (acmmp_fusion_run_ply(f, (int)i, (int)srcs[i].size(), srcs[i].data(), buf, counts[i], &count, &ms) != ACMMP_OK || count != counts[i]) {
+            if (writer.valid()) writer.get();
+            fclose(ply);
+            fail("run");
+        }
+        ms_sum += ms;
+        std::cout << "  -> Generated " << count << " points" << std::endl;
+        if (writer.valid()) write_ok = writer.get() && write_ok;          // the other buffer is free again after this
+        writer = std::async(std::launch::async, [ply, buf, count]() { return count == 0 || fwrite(buf, 27, (size_t)count, ply) == (size_t)count; });
+    }
+    if (writer.valid()) write_ok = writer.get() && write_ok;
+    fclose(ply);
+    acmmp_fusion_destroy(f);
+    for (unsigned char *p : staging) cudaFreeHost(p);
+    if (!write_ok) throw std::runtime_error("short write to " + output_path);
+    std::cout << "[CUDA Fusion] read maps + images " << t_loaded - t_begin << " s, upload " << t_uploaded - t_loaded << " s, fuse + write "
+              << now() - t_uploaded << " s" << std::endl;
+    std::cout << "[CUDA Fusion] Complete! Wrote " << total_points << " points to " << output_path << std::endl;
     if (kernel_ms) *kernel_ms = ms_sum;
-    return all_points.size();
+    return total_points;
 }

@@ -13,6 +13,7 @@
 //     returns up to the decoder's IDCT rounding), or from a lossless images/%08d.pgm twin when present.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -145,6 +146,8 @@ public:
     // the device's pool for the next view's stage (acmmp_park); SetViewsDevice(..., next_level = false) with the same
     // shapes takes it up again.  keep_host_result: GetPlaneHypothesis / GetCost stay readable (a writer thread's input).
     void Park(bool keep_prior = false, bool keep_host_result = false);
+    // the stage state on the device: float4 per pixel (world-frame normal, depth); stays valid while the object lives
+    const float *GetPlanesDevice();
     // depth maps of the SOURCE views for the geometric term (device pointers); the reference view's own map is the
     // state on the device (acmmp_set_depth_maps_device with maps[0] == NULL)
     void SetNeighbourDepthMapsDevice(const std::vector<const float *> &maps_dev, const std::vector<int> &widths,
@@ -174,14 +177,26 @@ private:
 // StoreColorPlyFileBinaryPointCloud (ACMMP.cpp:481-534): binary little-endian PLY, x y z nx ny nz (float) + red green blue
 // (uchar); non-finite coordinates are written as 0
 void StoreColorPlyFileBinaryPointCloud(const std::string &plyFilePath, const std::vector<PointList> &pc);
+void StorePlyVertexRecords(const std::string &plyFilePath, const unsigned char *records27, size_t n_points);       // the same file from packed records
+FILE *OpenPlyForVertexRecords(const std::string &plyFilePath, size_t n_points);     // header written, positioned at the first vertex record
 
 // RunFusionCuda (ACMMP.cu:1817-2105): fuse the depth / normal maps of every view (depths_geom.dmb when geom_consistency,
 // else depths.dmb; normals.dmb) into ACMMP/ACMM_model_cuda_5.ply.  The per-pixel consistency kernel and the compaction
 // of its points run on the device (acmmp_fusion_*).  Colours: the grey level of the image the PatchMatch stages read
 // (the reference decodes the JPEG in colour).  Returns the number of points written.  kernel_ms: optional, sum of the
 // CUDA-event kernel times.
+// `resident`: views whose final maps are still on `device` (the resident schedule leaves them there): their depth / normal
+// maps and grey image are taken from the device instead of the .dmb files and the image folder.
+struct ResidentView {
+    int ref_image_id = 0;
+    Camera cam;                      // at the map's size (the finest level's camera)
+    int width = 0, height = 0;
+    const float *depth_dev = nullptr;      // width * height
+    const float *planes4_dev = nullptr;    // float4 per pixel: world-frame normal xyz (w unused)
+    const float *gray_dev = nullptr;       // grey levels 0..255
+};
 size_t RunFusionCuda(const std::string &dense_folder, const std::vector<Problem> &problems, bool geom_consistency, int device = 0,
-                     double *kernel_ms = nullptr);
+                     double *kernel_ms = nullptr, const std::vector<ResidentView> *resident = nullptr);
 
 // RunJBU (ACMMP.cpp:1071-1122): joint-bilateral upsampling of depths_geom.dmb to the new level, written as depths.dmb
 void RunJBU(const cv::Mat_<float> &scaled_image_float, const cv::Mat_<float> &src_depthmap, const std::string &dense_folder,

@@ -448,14 +448,14 @@ void ResizeLinear(const cv::Mat_<float> &src, cv::Mat_<float> &dst, int new_cols
 }
 
 // reference ACMMP.cpp:481-534
-void StoreColorPlyFileBinaryPointCloud(const std::string &plyFilePath, const std::vector<PointList> &pc)
+FILE *OpenPlyForVertexRecords(const std::string &plyFilePath, size_t n_points)
 {
     std::cout << "store 3D points to ply file" << std::endl;
     FILE *outputPly = fopen(plyFilePath.c_str(), "wb");
     if (!outputPly) throw std::runtime_error("cannot write " + plyFilePath);
     fprintf(outputPly, "ply\n");
     fprintf(outputPly, "format binary_little_endian 1.0\n");
-    fprintf(outputPly, "element vertex %zu\n", pc.size());
+    fprintf(outputPly, "element vertex %zu\n", n_points);
     fprintf(outputPly, "property float x\n");
     fprintf(outputPly, "property float y\n");
     fprintf(outputPly, "property float z\n");
@@ -466,6 +466,22 @@ void StoreColorPlyFileBinaryPointCloud(const std::string &plyFilePath, const std
     fprintf(outputPly, "property uchar green\n");
     fprintf(outputPly, "property uchar blue\n");
     fprintf(outputPly, "end_header\n");
+    return outputPly;
+}
+
+// the same file from vertex records the device already packed (acmmp_fusion_run_ply)
+void StorePlyVertexRecords(const std::string &plyFilePath, const unsigned char *records27, size_t n_points)
+{
+    FILE *outputPly = OpenPlyForVertexRecords(plyFilePath, n_points);
+    const size_t bytes = 27 * n_points;
+    const bool ok = bytes == 0 || fwrite(records27, 1, bytes, outputPly) == bytes;
+    fclose(outputPly);
+    if (!ok) throw std::runtime_error("short write to " + plyFilePath);
+}
+
+void StoreColorPlyFileBinaryPointCloud(const std::string &plyFilePath, const std::vector<PointList> &pc)
+{
+    FILE *outputPly = OpenPlyForVertexRecords(plyFilePath, pc.size());
     // one 27-byte record per point, assembled in memory and written in one go (the reference issues nine fwrite calls per
     // point inside an omp critical section)
     std::vector<unsigned char> buf(pc.size() * 27);

@@ -268,7 +268,8 @@ private:
 // geometric round) with peer copies over NVLink -- what the reference passes through depths.dmb / depths_geom.dmb.
 // Inside a device the second geometric round stays Gauss-Seidel (a view reads the maps its own device rewrote earlier in
 // the round), across devices it is Jacobi (the maps of the first round); one device = the reference's order exactly.
-bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems, const size_t num_images, int max_num_downscale, int ndev)
+bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems, const size_t num_images, int max_num_downscale, int ndev,
+                 std::vector<ResidentView> *resident_out)
 {
     std::map<int, int> index_of;                      // image id -> position in `problems`
     for (size_t i = 0; i < problems.size(); ++i) index_of[problems[i].ref_image_id] = (int)i;
@@ -670,6 +671,21 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             for (auto &w : writers) w.get();                 // rethrows a writer's exception
             t_output += now_s() - tw;
         }
+        if (resident_out && ndev == 1) {
+            // what the fusion would read back from the .dmb files and the image folder is still on this device: final depth
+            // maps (the table the last sweep exported into), the contexts' planes (world normal + depth), the level images
+            for (size_t i : mine) {
+                ResidentView r;
+                r.ref_image_id = problems[i].ref_image_id;
+                r.cam = level_camera[i];
+                r.width = level_w[i];
+                r.height = level_h[i];
+                r.depth_dev = gtab[d][i].ptr;
+                r.planes4_dev = objs[i]->GetPlanesDevice();
+                r.gray_dev = pool[i].ptr;
+                resident_out->push_back(r);
+            }
+        }
         std::lock_guard<std::mutex> lock(stats_mutex);
         g_gpu_ms += gpu_ms;
         g_t_ctx = std::max(g_t_ctx, t_ctx); g_t_upload = std::max(g_t_upload, t_upload); g_t_support = std::max(g_t_support, t_support);
@@ -746,11 +762,12 @@ int main(int argc, char **argv)
         if (dropped) std::cout << "--max-views: dropped " << dropped << " source-view references to views that are not processed" << std::endl;
     }
     const double t_start = now_s();
+    std::vector<ResidentView> resident_views;          // --resident 1 on one device: the final maps stay there for the fusion
     try {
         int max_num_downscale = ComputeMultiScaleSettings(dense_folder, problems);
         if (resident) {
             std::vector<Problem> work = problems;
-            if (RunResident(dense_folder, work, num_images, max_num_downscale, g_gpus)) max_num_downscale = -1;     // done
+            if (RunResident(dense_folder, work, num_images, max_num_downscale, g_gpus, &resident_views)) max_num_downscale = -1;     // done
             else { std::cout << "resident schedule not applicable to this scene; running the file-chained schedule" << std::endl; resident = 0; }
         }
         int flag = 0;
@@ -787,7 +804,7 @@ int main(int argc, char **argv)
         try {
             const double t0 = now_s();
             std::vector<Problem> fused(problems.begin(), problems.begin() + num_images);
-            fusion_points = RunFusionCuda(dense_folder, fused, true, g_device, &fusion_kernel_ms);
+            fusion_points = RunFusionCuda(dense_folder, fused, true, g_device, &fusion_kernel_ms, resident_views.empty() ? nullptr : &resident_views);
             fusion_s = now_s() - t0;
         } catch (const std::exception &e) {
             std::cerr << "acmmp_b200: " << e.what() << std::endl;

@@ -335,6 +335,11 @@ int acmmp_fusion_set_view_device(acmmp_fusion *f, int index, const acmmp_camera 
  * kernel_ms (optional): CUDA-event time of the three kernels. */
 int acmmp_fusion_run(acmmp_fusion *f, int ref, int n_src, const int32_t *src, acmmp_point *points, int capacity,
                      int *n_points, float *kernel_ms);
+/* The same, with the points already in the PLY file's 27-byte vertex records (x y z nx ny nz as little-endian floats, then
+ * red green blue; what StoreColorPlyFileBinaryPointCloud writes per point, ACMMP.cpp:481-534, including the non-finite
+ * coordinate -> origin rule): the host appends `records27` to the file as it is.  capacity in points. */
+int acmmp_fusion_run_ply(acmmp_fusion *f, int ref, int n_src, const int32_t *src, uint8_t *records27, int capacity,
+                         int *n_points, float *kernel_ms);
 /* which pixels of the reference view fused LAST produced a point: w*h bytes (host), row-major */
 int acmmp_fusion_last_flags(acmmp_fusion *f, int ref, unsigned char *flags);
 

@@ -120,6 +120,10 @@ def test_cpp_driver_resident_schedule_and_gpu_prior_write_the_same_maps_as_the_f
                 assert x.shape == y.shape, (name, v, dmb)
                 # bit patterns: costs hold NaN where no view was selected (0 / 0, as in the reference), and NaN != NaN
                 res[f"{name}_view{v}_{dmb}_identical"] = bool(np.array_equal(x.view(np.uint32), y.view(np.uint32)))
+        # the fused point cloud: the resident schedules feed the fusion from the maps still on the device, the file-chained
+        # ones from the .dmb files -- the same maps, so the same bytes
+        res[f"{name}_ply_identical"] = bool((folders["files"] / "ACMMP" / "ACMM_model_cuda_5.ply").read_bytes()
+                                            == (folders[name] / "ACMMP" / "ACMM_model_cuda_5.ply").read_bytes())
     util.dump("cpp_driver_resident", res)
     bad = [k for k, v in res.items() if k.endswith("_identical") and not v]
     assert not bad, bad

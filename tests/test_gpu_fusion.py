@@ -105,3 +105,27 @@ def test_fusion_edge_cases():
     f.set_view(0, scene.cams[0], np.zeros_like(depths[0]), normals[0], scene.images[0])
     assert len(f.run(0, [1, 2, 3])) == 0
     f.close()
+
+
+def test_ply_records_from_the_device_equal_the_host_writers(tmp_path):
+    """acmmp_fusion_run_ply: the 27-byte vertex records packed on the device are byte for byte what the host writer
+    (StoreColorPlyFileBinaryPointCloud, reference ACMMP.cpp:481-534) makes of the same points."""
+    import ctypes as C
+    from acmmp_b200 import Fusion, PKG_DIR, synth
+    scene = synth.make_pinhole_scene(n_views=4, width=320, height=240, focal=250.0, seed=1)
+    depths, normals = _inputs(scene, holes=0.01)
+    bgr = _colour_images(scene)
+    f = Fusion(4, 0)
+    for v in range(4):
+        f.set_view(v, scene.cams[v], depths[v], normals[v], scene.images[v])
+        f.set_view_colour(v, bgr[v])
+    src = list(scene.pairs[0][1])
+    pts = f.run(0, src)
+    rec = f.run_ply(0, src)
+    f.close()
+    assert len(pts) > 1000 and rec.shape == (len(pts), 27)
+    host = C.CDLL(str(PKG_DIR / "lib" / "libacmmp_host.so"))
+    path = tmp_path / "points.ply"
+    assert host.acmmp_host_write_ply(str(path).encode(), np.ascontiguousarray(pts, np.float32).ctypes.data_as(C.POINTER(C.c_float)), len(pts)) == 0
+    body = path.read_bytes().split(b"end_header\n", 1)[1]
+    assert body == rec.tobytes()

@@ -58,6 +58,7 @@ def main():
             open(f"{a.trace}_{name}.txt", "w").write(r.stderr)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         res[name] = json.loads(r.stdout.strip().splitlines()[-1])
+        res[name]["fusion_phases"] = [l for l in r.stdout.splitlines() if l.startswith("[CUDA Fusion] read maps")]
         res[name]["process_wall_s"] = time.time() - t0
         res[name]["s_per_view"] = res[name]["wall_s"] / a.views
     for name in ("resident", "resident_gpu_prior"):
