@@ -316,7 +316,7 @@ def driver_leg(cfg, scene, ids, device):
         n = d["views"]
         trace = [l for l in r.stderr.splitlines() if l.startswith("[acmmp trace]")]          # ACMMP_TRACE=1 in the environment
         return {**({"trace": trace} if trace else {}),"views": n, "src_views": cfg["n_src"], "s_per_view": d["wall_s"] / n, "value": n / d["wall_s"], "unit": UNIT,
-                "kernel_s_per_view": d["kernel_ms"] / 1e3 / n,
+                "kernel_s_per_view": d["kernel_ms"] / 1e3 / n, "fusion_s": d.get("fusion_s"), "fusion_points": d.get("fusion_points"),
                 "s_per_view_after_cuda_startup": (d["wall_s"] - d.get("setup_s", 0.0)) / n, "prior_s_per_view": d["prior_cpu_s"] / n, "process_wall_s": wall,
                 "breakdown_s": {k: d[k] for k in ("setup_s", "load_s", "views_s", "ctx_s", "upload_s", "run_s", "support_s", "prior_dev_s", "export_s", "output_s", "join_s", "sweep1_s", "geom_s") if k in d},
                 "what": "lib/acmmp_b200 <dense_folder> --resident 1 --gpu-prior 1: wall clock inside the process from pair.txt to the "
