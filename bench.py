@@ -303,7 +303,9 @@ def driver_leg(cfg, scene, ids, device):
     sub = synth.Scene(scene.model, [scene.images[i] for i in ids], [scene.cams[i] for i in ids], [scene.depths_gt[i] for i in ids],
                       [(k, [j for j in range(len(ids)) if j != k][: cfg["n_src"]]) for k in range(len(ids))],
                       [scene.Rs[i] for i in ids], [scene.ts[i] for i in ids], [scene.Ks[i] for i in ids], scene.quads)
-    tmp = tempfile.mkdtemp(prefix="acmmp_bench_driver_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    # images + four .dmb files per view + the fused PLY: ~5 GB at C2; RAM-backed when there is room for it
+    shm_ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (12 << 30)
+    tmp = tempfile.mkdtemp(prefix="acmmp_bench_driver_", dir="/dev/shm" if shm_ok else None)
     try:
         synth.write_dense_folder(sub, tmp, pgm=True)
         t0 = time.perf_counter()
