@@ -371,6 +371,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             if (need[v] && device_of(v) != d) remote[d].push_back(v);
     }
     std::vector<int> level_w(num_images, 0), level_h(num_images, 0);
+    std::vector<std::vector<DeviceMap>> pools(ndev, std::vector<DeviceMap>(num_images));
     PhaseBarrier barrier(ndev);
     std::mutex stats_mutex;
     std::string failure;
@@ -398,7 +399,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         };
         std::vector<std::future<void>> writers;             // .dmb output of finished views
         std::future<void> prefetch;                         // the next level's images of this thread's views
-        std::vector<DeviceMap> pool(num_images);            // level images on this device
+        std::vector<DeviceMap> &pool = pools[d];            // level images on this device
         std::vector<size_t> needed;                         // my views and their source views
         {
             std::vector<char> need(num_images, 0);
@@ -671,21 +672,6 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             for (auto &w : writers) w.get();                 // rethrows a writer's exception
             t_output += now_s() - tw;
         }
-        if (resident_out && ndev == 1) {
-            // what the fusion would read back from the .dmb files and the image folder is still on this device: final depth
-            // maps (the table the last sweep exported into), the contexts' planes (world normal + depth), the level images
-            for (size_t i : mine) {
-                ResidentView r;
-                r.ref_image_id = problems[i].ref_image_id;
-                r.cam = level_camera[i];
-                r.width = level_w[i];
-                r.height = level_h[i];
-                r.depth_dev = gtab[d][i].ptr;
-                r.planes4_dev = objs[i]->GetPlanesDevice();
-                r.gray_dev = pool[i].ptr;
-                resident_out->push_back(r);
-            }
-        }
         std::lock_guard<std::mutex> lock(stats_mutex);
         g_gpu_ms += gpu_ms;
         g_t_ctx = std::max(g_t_ctx, t_ctx); g_t_upload = std::max(g_t_upload, t_upload); g_t_support = std::max(g_t_support, t_support);
@@ -709,6 +695,43 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
     for (int d = 1; d < ndev; ++d) threads.emplace_back(guarded, d);
     guarded(0);
     for (auto &t : threads) t.join();
+    if (resident_out && failure.empty()) {
+        // What the fusion would read back from the .dmb files and the image folder is still on the devices: final depth maps
+        // (the tables the last sweep exported into), the contexts' planes (world normal + depth), the level images.  The
+        // fusion runs on the first device; the maps of views another device owns come over with three peer copies each.
+        const double t0 = now_s();
+        cudaSetDevice(g_device);
+        bool ok = true;
+        for (size_t i = 0; i < num_images && ok; ++i) {
+            const int d = device_of(i);
+            const size_t npx = (size_t)level_w[i] * level_h[i];
+            ResidentView r;
+            r.ref_image_id = problems[i].ref_image_id;
+            r.cam = level_camera[i];
+            r.width = level_w[i];
+            r.height = level_h[i];
+            const float *src[3] = {gtab[d][i].ptr, objs[i]->GetPlanesDevice(), pools[d][i].ptr};
+            const size_t bytes[3] = {sizeof(float) * npx, 4 * sizeof(float) * npx, sizeof(float) * npx};
+            const float *dst[3] = {src[0], src[1], src[2]};
+            if (d != 0) {
+                for (int k = 0; k < 3 && ok; ++k) {
+                    void *p = nullptr;
+                    ok = acmmp_pool_alloc(g_device, bytes[k], &p) == ACMMP_OK &&
+                         cudaMemcpyPeer(p, g_device, src[k], g_device + d, bytes[k]) == cudaSuccess;
+                    dst[k] = (const float *)p;
+                }
+            }
+            r.depth_dev = dst[0];
+            r.planes4_dev = dst[1];
+            r.gray_dev = dst[2];
+            resident_out->push_back(r);
+        }
+        if (!ok) {
+            (void)cudaGetLastError();
+            resident_out->clear();                      // the fusion reads the files instead
+        }
+        g_t_exchange += now_s() - t0;
+    }
     // The process ends right after this schedule: the contexts (a few GB of pooled device and pinned buffers each)
     // are left to the driver's process teardown, which reclaims them much faster than hundreds of cudaFree /
     // cudaFreeHost calls would (measured: ~0.4 s per view at C2 size).
@@ -723,12 +746,12 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
 int main(int argc, char **argv)
 {
     if (argc < 2) {
-        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--gpus N] [--max-views N] [--resident 0|1] [--gpu-prior 0|1] [--fusion 0|1]" << std::endl;
+        std::cout << "USAGE: acmmp_b200 dense_folder [--seed S] [--device D] [--gpus N] [--max-views N] [--resident 0|1] [--gpu-prior 0|1] [--fusion 0|1] [--fusion-only 0|1]" << std::endl;
         return -1;
     }
     const std::string dense_folder = argv[1];
     size_t max_views = 0;
-    int resident = 0;
+    int resident = 0, fusion_only = 0;
     for (int i = 2; i + 1 < argc; i += 2) {
         if (!std::strcmp(argv[i], "--resident")) resident = std::atoi(argv[i + 1]);
         else if (!std::strcmp(argv[i], "--gpu-prior")) g_gpu_prior = std::atoi(argv[i + 1]);
@@ -737,6 +760,7 @@ int main(int argc, char **argv)
         else if (!std::strcmp(argv[i], "--max-views")) max_views = (size_t)std::atoi(argv[i + 1]);
         else if (!std::strcmp(argv[i], "--gpus")) { g_gpus = std::atoi(argv[i + 1]); resident = 1; }      // multi-GPU is a resident schedule
         else if (!std::strcmp(argv[i], "--fusion")) g_fusion = std::atoi(argv[i + 1]);
+        else if (!std::strcmp(argv[i], "--fusion-only")) fusion_only = std::atoi(argv[i + 1]);       // re-fuse the maps of an earlier run
     }
     std::vector<Problem> problems;
     GenerateSampleList(dense_folder, problems);
@@ -764,8 +788,8 @@ int main(int argc, char **argv)
     const double t_start = now_s();
     std::vector<ResidentView> resident_views;          // --resident 1 on one device: the final maps stay there for the fusion
     try {
-        int max_num_downscale = ComputeMultiScaleSettings(dense_folder, problems);
-        if (resident) {
+        int max_num_downscale = fusion_only ? -1 : ComputeMultiScaleSettings(dense_folder, problems);
+        if (resident && !fusion_only) {
             std::vector<Problem> work = problems;
             if (RunResident(dense_folder, work, num_images, max_num_downscale, g_gpus, &resident_views)) max_num_downscale = -1;     // done
             else { std::cout << "resident schedule not applicable to this scene; running the file-chained schedule" << std::endl; resident = 0; }

@@ -217,7 +217,16 @@ def test_cpp_driver_multi_gpu_shards_views_and_exchanges_depth_maps(tmp_path, le
         res[f"view{v}_final_depth_within_1pct"] = float((rel <= 0.01)[8:-8, 8:-8].mean())
         gt = scene.depths_gt[v]
         res[f"view{v}_within_1pct_of_gt"] = float((np.abs(b["depths_geom.dmb"] - gt) / gt <= 0.01)[8:-8, 8:-8].mean())
+    # the two-device run fed its fusion from the maps on the devices (peer copies to the first one); fusing its .dmb files
+    # again (--fusion-only) must give the same bytes
+    ply = two / "ACMMP" / "ACMM_model_cuda_5.ply"
+    resident_ply = ply.read_bytes()
+    r = subprocess.run([str(DRIVER), str(two), "--fusion-only", "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res["ply_of_resident_maps_equals_ply_of_files"] = bool(ply.read_bytes() == resident_ply)
+    res["fusion_points_two"] = out["two"]["fusion_points"]
     util.dump(f"cpp_driver_multi_gpu_{levels}_levels", res)
+    assert res["ply_of_resident_maps_equals_ply_of_files"] and res["fusion_points_two"] > 1000, res
     for v in range(5):
         if levels == 1:
             assert res[f"view{v}_prior_stage_depths_identical"], res
