@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--model", default="pinhole")
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--geom", action="store_true", help="also time a geometric-consistency stage (neighbour depth maps = ground truth)")
     ap.add_argument("--tap-prune", type=float, default=None, help="SPHERE: acmmp_set_sphere_tap_pruning threshold (0 = sample every tap)")
     a = ap.parse_args()
     from acmmp_b200 import Context, synth
@@ -45,6 +46,14 @@ def main():
         wall = time.time() - t0
         res[f"mine_run{rep}"] = dict(wall_ms=1e3 * wall, **ctx.timings())
     pa, ca = ctx.get_result()
+    if a.geom:
+        for rep in range(2):
+            ctx.reset_modes()
+            ctx.set_geom_consistency(False)
+            ctx.set_depth_maps([None] + [scene.depths_gt[i] for i in ids[1:]])
+            ctx.run_patch_match()
+            res[f"geom_run{rep}"] = dict(**ctx.timings())
+        res["geom_checksum"] = float(np.nansum(ctx.get_result()[0][..., 3], dtype=np.float64))
     gt = scene.depths_gt[0]
     res["mine_vs_gt_1pct"] = float((np.abs(pa[..., 3] - gt) / gt <= 0.01).mean())
     if not a.no_ref:
