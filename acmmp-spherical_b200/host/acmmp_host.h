@@ -182,8 +182,9 @@ FILE *OpenPlyForVertexRecords(const std::string &plyFilePath, size_t n_points); 
 
 // RunFusionCuda (ACMMP.cu:1817-2105): fuse the depth / normal maps of every view (depths_geom.dmb when geom_consistency,
 // else depths.dmb; normals.dmb) into ACMMP/ACMM_model_cuda_5.ply.  The per-pixel consistency kernel and the compaction
-// of its points run on the device (acmmp_fusion_*).  Colours: the grey level of the image the PatchMatch stages read
-// (the reference decodes the JPEG in colour).  Returns the number of points written.  kernel_ms: optional, sum of the
+// of its points run on the device (acmmp_fusion_*).  Colours: the view's colour image like the reference's
+// cv::imread(IMREAD_COLOR) (LoadColourImage: images/%08d.ppm or the .jpg through nvJPEG, rescaled to the map's size; a view
+// that only has a grey image gets (g, g, g)).  Returns the number of points written.  kernel_ms: optional, sum of the
 // CUDA-event kernel times.
 // `resident`: views whose final maps are still on `device` (the resident schedule leaves them there): their depth / normal
 // maps and grey image are taken from the device instead of the .dmb files and the image folder.
