@@ -77,7 +77,7 @@ _EXPORTS = [
     "acmmp_default_params", "acmmp_version", "acmmp_abi_sizeof_camera", "acmmp_abi_sizeof_params",
     "acmmp_create", "acmmp_destroy", "acmmp_last_error", "acmmp_set_views", "acmmp_set_views_device",
     "acmmp_set_geom_consistency", "acmmp_set_hierarchy", "acmmp_set_planar_prior", "acmmp_set_max_iterations",
-    "acmmp_get_params", "acmmp_reset_modes", "acmmp_park", "acmmp_reserve_device_memory", "acmmp_pool_alloc", "acmmp_pool_free", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
+    "acmmp_get_params", "acmmp_reset_modes", "acmmp_park", "acmmp_reserve_device_memory", "acmmp_reserve_pinned", "acmmp_pool_alloc", "acmmp_pool_free", "acmmp_last_jbu_ms", "acmmp_set_depth_maps", "acmmp_set_depth_maps_device", "acmmp_set_planes",
     "acmmp_set_hierarchy_inputs", "acmmp_next_level", "acmmp_next_level_device", "acmmp_result_host", "acmmp_set_planar_prior_inputs", "acmmp_support_points",
     "acmmp_planar_prior_from_triangles", "acmmp_download_prior", "acmmp_set_seed",
     "acmmp_set_plane_now_semantics", "acmmp_set_sphere_tap_pruning", "acmmp_run_patch_match", "acmmp_run_patch_match_resident", "acmmp_download_result", "acmmp_random_init", "acmmp_checkerboard_pass",

@@ -1368,6 +1368,24 @@ int acmmp_reserve_device_memory(int device, size_t bytes)
     return ACMMP_OK;
 }
 
+int acmmp_reserve_pinned(int device, size_t bytes)
+{
+    if (bytes == 0) return ACMMP_E_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ACMMP_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ACMMP_E_CUDA;
+    void *p = nullptr;
+    {
+        Trace tr("pool.cudaMallocHost");
+        if (cudaMallocHost(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return ACMMP_E_CUDA; }
+    }
+    DeviceShared &sh = device_shared(device);
+    std::lock_guard<std::mutex> lock(sh.m);
+    sh.pool.host_size[p] = bytes;
+    sh.pool.host_free.insert(std::make_pair(bytes, p));
+    return ACMMP_OK;
+}
+
 int acmmp_pool_alloc(int device, size_t bytes, void **out)
 {
     if (!out || bytes == 0) return ACMMP_E_ARG;

@@ -116,6 +116,9 @@ public:
     const Camera &GetReferenceCamera() const { return cameras_[0]; }      // not in the reference
     float4 GetPlaneHypothesis(const int index);
     float GetCost(const int index);
+    // the downloaded result as the library holds it (pinned): float4 (world normal, depth) per pixel, and the costs
+    const float *PlanesHost() const { return planes_host_; }
+    const float *CostsHost() const { return costs_host_; }
     void GetSupportPoints(std::vector<cv::Point> &support2DPoints);
     std::vector<Triangle> DelaunayTriangulation(const cv::Rect boundRC, const std::vector<cv::Point> &points);
     float4 GetPriorPlaneParams(const Triangle triangle, const cv::Mat_<float> &depths);

@@ -172,7 +172,7 @@ bool read_file(const std::string &path, std::vector<unsigned char> &bytes)
 }
 
 // binary PGM (P5), maxval <= 255
-bool parse_pgm(const std::vector<unsigned char> &b, int &w, int &h, size_t &offset)
+bool parse_pgm(const std::vector<unsigned char> &b, int &w, int &h, size_t &offset, bool header_only = false)
 {
     size_t p = 0;
     auto token = [&](std::string &out) {
@@ -193,7 +193,7 @@ bool parse_pgm(const std::vector<unsigned char> &b, int &w, int &h, size_t &offs
     h = std::atoi(t.c_str());
     if (!token(t) || std::atoi(t.c_str()) > 255) return false;
     offset = p + 1;                                 // exactly one whitespace byte after maxval
-    return w > 0 && h > 0 && offset + (size_t)w * h <= b.size();
+    return w > 0 && h > 0 && (header_only || offset + (size_t)w * h <= b.size());
 }
 
 // JPEG header scan for the frame size (SOF0..SOF15 except DHT/JPG/DAC)
@@ -391,12 +391,25 @@ void ResizeLinearBgr(const cv::Mat_<cv::Vec3b> &src, cv::Mat_<cv::Vec3b> &dst, i
     }
 }
 
+// the first `limit` bytes of a file (enough for a PGM header and, nearly always, a JPEG's frame header)
+static bool read_head(const std::string &path, size_t limit, std::vector<unsigned char> &bytes)
+{
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    bytes.resize(limit);
+    bytes.resize(std::fread(bytes.data(), 1, limit, f));
+    std::fclose(f);
+    return !bytes.empty();
+}
+
 bool ImageSize(const std::string &dense_folder, int id, int &cols, int &rows)
 {
     std::vector<unsigned char> bytes;
     size_t off;
-    if (read_file(view_file(dense_folder + "/images", id, ".pgm"), bytes) && parse_pgm(bytes, cols, rows, off)) return true;
-    if (read_file(view_file(dense_folder + "/images", id, ".jpg"), bytes) && jpeg_size(bytes, cols, rows)) return true;
+    const std::string pgm = view_file(dense_folder + "/images", id, ".pgm"), jpg = view_file(dense_folder + "/images", id, ".jpg");
+    if (read_head(pgm, 128, bytes) && parse_pgm(bytes, cols, rows, off, true)) return true;
+    if (read_head(jpg, 256 << 10, bytes) && jpeg_size(bytes, cols, rows)) return true;
+    if (read_file(jpg, bytes) && jpeg_size(bytes, cols, rows)) return true;          // a frame header behind a large EXIF block
     return false;
 }
 

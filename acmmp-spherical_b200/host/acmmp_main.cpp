@@ -38,7 +38,7 @@ int g_gpu_prior = 0;
 double g_gpu_ms = 0.0, g_prior_s = 0.0;
 // wall-clock attribution of the resident schedule (printed in the summary): image load + scaling, view upload / level
 // change (incl. context creation), stage runs (kernels + waits + downloads), depth-map export, result output
-double g_t_setup = 0.0, g_t_ctx = 0.0, g_t_upload = 0.0, g_t_support = 0.0, g_t_prior_dev = 0.0;
+double g_t_barrier = 0.0, g_t_setup = 0.0, g_t_ctx = 0.0, g_t_upload = 0.0, g_t_support = 0.0, g_t_prior_dev = 0.0;
 double g_t_load = 0.0, g_t_views = 0.0, g_t_run = 0.0, g_t_export = 0.0, g_t_output = 0.0, g_t_join = 0.0;
 double g_t_sweep1 = 0.0, g_t_geom = 0.0;   // totals: first sweep, geometric sweeps
 double g_t_exchange = 0.0;                 // --gpus N: peer copies of the depth maps
@@ -296,18 +296,33 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
     }
     ndev = (int)std::min<size_t>((size_t)ndev, std::max<size_t>(num_images, 1));
     const auto device_of = [&](size_t view) { return (int)(view % (size_t)ndev); };
-    std::vector<size_t> reserve_bytes;
+    // image sizes: once (headers only), not per device
+    std::vector<double> level_px(num_images, 0.0);
+    std::vector<size_t> full_px(num_images, 0);         // upper bound of a view's pixel count at any level
+    std::vector<size_t> finest_px(num_images, 0);       // exact pixel count of the finest level (LoadScaledView's arithmetic)
+    for (size_t i = 0; i < num_images; ++i) {
+        int cols = 0, rows = 0;
+        if (!ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) continue;
+        const double scale = std::min(1.0, (double)problems[i].max_image_size / std::max(cols, rows));
+        level_px[i] = (double)cols * rows * scale * scale;
+        full_px[i] = (size_t)cols * rows;
+        const int m = problems[i].max_image_size;
+        if (cols <= m && rows <= m) {
+            finest_px[i] = (size_t)cols * rows;
+        } else {
+            const float factor = std::min(static_cast<float>(m) / cols, static_cast<float>(m) / rows);
+            finest_px[i] = (size_t)std::round(cols * factor) * (size_t)std::round(rows * factor);
+        }
+    }
+    // What a device holds: per owned view the stage state of the current level (planes, costs, pre-costs: 24 bytes
+    // per pixel -- parked views keep nothing else); the level images of the views it needs (4 B/px); two depth-map tables
+    // of all views (8 B/px); and the scratch of the views in flight, which all views share through the device's pool
+    // (images twice -- layered + per-view textures --, padded reference, ping-pong planes and costs, view masks, two RNG
+    // states, prior planes + masks, pinned-result staging: 8 (n_src + 1) + 160 B/px, two sets in rotation plus the
+    // smaller sets of the coarser levels that stay in the pool).  Scenes that do not fit fall back to the file-chained
+    // schedule.
+    std::vector<size_t> reserve_bytes(ndev, 0);
     for (int d = 0; d < ndev; ++d) {
-        // What a device holds: per owned view the stage state of the current level (planes, costs, pre-costs: 24 bytes
-        // per pixel -- parked views keep nothing else); the level images of the views it needs (4 B/px); two depth-map tables
-        // of all views (8 B/px); and the scratch of the views in flight, which all views share through the device's pool
-        // (images twice -- layered + per-view textures --, padded reference, ping-pong planes and costs, view masks, two RNG
-        // states, prior planes + masks, pinned-result staging: 8 (n_src + 1) + 160 B/px, two sets in rotation plus the
-        // smaller sets of the coarser levels that stay in the pool).  Scenes that do not fit fall back to the file-chained
-        // schedule.
-        cudaSetDevice(g_device + d);
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
         double need = 0.0, scratch = 0.0;
         std::vector<char> uses(num_images, 0);
         for (size_t i = 0; i < num_images; ++i)
@@ -316,10 +331,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 for (int id : problems[i].src_image_ids) uses[index_of.at(id)] = 1;
             }
         for (size_t i = 0; i < num_images; ++i) {
-            int cols = 0, rows = 0;
-            if (!ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) continue;
-            const double scale = std::min(1.0, (double)problems[i].max_image_size / std::max(cols, rows));
-            const double px = (double)cols * rows * scale * scale;
+            const double px = level_px[i];
             if (device_of(i) == d) {
                 need += px * 24.0;
                 scratch = std::max(scratch, px * (8.0 * (problems[i].src_image_ids.size() + 1) + 160.0));
@@ -328,18 +340,41 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             need += px * 8.0;
         }
         need += 2.7 * scratch;
-        if (need > 0.85 * (double)free_b) {
-            std::cout << "resident schedule: device " << g_device + d << " needs about " << need / 1e9 << " GB of device memory, "
-                      << free_b / 1e9 << " GB are free" << std::endl;
-            return false;
-        }
-        reserve_bytes.push_back((size_t)(need * 1.1) + ((size_t)256 << 20));
+        reserve_bytes[d] = (size_t)(need * 1.1) + ((size_t)256 << 20);
     }
-    // one allocation per device that the library's pool carves the state blocks, scratch sets, level images and depth-map
-    // tables out of (the texture arrays and pinned buffers are separate allocations); what does not fit falls back to cudaMalloc
-    for (int d = 0; d < ndev; ++d)
-        if (acmmp_reserve_device_memory(g_device + d, reserve_bytes[d]) != ACMMP_OK)
-            std::cout << "resident schedule: no " << reserve_bytes[d] / 1e9 << " GB reservation on device " << g_device + d << " (allocating block by block)" << std::endl;
+    // The devices come up side by side (a CUDA context takes 1 - 2.5 s on these machines; one after the other that was 9.4 s
+    // of a 4-device run): context, memory check, and the one allocation per device that the library's pool carves the state
+    // blocks, scratch sets, level images and depth-map tables out of (texture arrays and pinned buffers are separate
+    // allocations; what does not fit falls back to cudaMalloc).
+    {
+        std::vector<int> fits(ndev, 1);
+        std::vector<std::thread> starters;
+        for (int d = 0; d < ndev; ++d)
+            starters.emplace_back([&, d]() {
+                size_t free_b = 0, total_b = 0;
+                if (cudaSetDevice(g_device + d) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { fits[d] = 0; return; }
+                if ((double)reserve_bytes[d] > 0.85 * (double)free_b) {
+                    std::cout << "resident schedule: device " << g_device + d << " needs about " << reserve_bytes[d] / 1e9 << " GB of device memory, "
+                              << free_b / 1e9 << " GB are free" << std::endl;
+                    fits[d] = 0;
+                    return;
+                }
+                if (acmmp_reserve_device_memory(g_device + d, reserve_bytes[d]) != ACMMP_OK)
+                    std::cout << "resident schedule: no " << reserve_bytes[d] / 1e9 << " GB reservation on device " << g_device + d << " (allocating block by block)" << std::endl;
+                // the page-locked result buffers of the final downloads (one pair per size: a writer thread hands them back
+                // after one copy pass, long before the device finishes its next view)
+                std::vector<size_t> sizes;
+                for (size_t i = 0; i < num_images; ++i)
+                    if (device_of(i) == d && finest_px[i] && std::find(sizes.begin(), sizes.end(), finest_px[i]) == sizes.end()) sizes.push_back(finest_px[i]);
+                for (size_t npx : sizes) {
+                    acmmp_reserve_pinned(g_device + d, 16 * npx);
+                    acmmp_reserve_pinned(g_device + d, 4 * npx);
+                }
+            });
+        for (auto &t : starters) t.join();
+        for (int d = 0; d < ndev; ++d)
+            if (!fits[d]) return false;
+    }
     if (ndev > 1) {
         for (int a = 0; a < ndev; ++a)
             for (int b = 0; b < ndev; ++b)
@@ -355,11 +390,6 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
     // tab[d][v]: the map of view v on device d ("d" = what depths.dmb would hold, "g" = depths_geom.dmb)
     std::vector<std::vector<DeviceMap>> dtab(ndev, std::vector<DeviceMap>(num_images)), gtab(ndev, std::vector<DeviceMap>(num_images));
     std::vector<cv::Mat_<float>> final_prior_depth(num_images);
-    std::vector<size_t> full_px(num_images, 0);         // upper bound of a view's pixel count at any level
-    for (size_t i = 0; i < num_images; ++i) {
-        int cols = 0, rows = 0;
-        if (ImageSize(dense_folder, problems[i].ref_image_id, cols, rows)) full_px[i] = (size_t)cols * rows;
-    }
     // which views does device d need the maps of (its own views' source views that another device owns)
     std::vector<std::vector<size_t>> remote(ndev);
     for (int d = 0; d < ndev; ++d) {
@@ -379,7 +409,13 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
 
     auto device_main = [&](const int d) {
         // per-thread wall-clock attribution, merged into the globals at the end
-        double t_ctx = 0, t_upload = 0, t_support = 0, t_prior_dev = 0;
+        double t_ctx = 0, t_upload = 0, t_support = 0, t_prior_dev = 0, t_barrier = 0;
+        auto timed_wait = [&]() {                           // time this thread waits for the other devices' threads
+            const double t0 = now_s();
+            const bool ok = barrier.wait();
+            t_barrier += now_s() - t0;
+            return ok;
+        };
         double t_load = 0, t_views = 0, t_run = 0, t_export = 0, t_output = 0, t_join = 0, t_sweep1 = 0, t_geom = 0, t_exchange = 0, gpu_ms = 0;
         cudaSetDevice(g_device + d);
         std::vector<size_t> mine;
@@ -423,7 +459,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                     }
                 }
             }
-            if (!barrier.wait()) return;
+            if (!timed_wait()) return;
             // every view of this level, read and scaled once (each thread its share, all of them shared afterwards)
             double tp = now_s();
             if (level == 0 || prefetch.valid()) {
@@ -441,7 +477,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                 level_h[i] = level_image[i].rows;
             }
             t_load += now_s() - tp;
-            if (!barrier.wait()) return;
+            if (!timed_wait()) return;
             // Every image this device's views use (their own and their source views'), on the device ONCE per level: a view's
             // image is a source image of ~10 other views, and uploading it with each of them was 0.3 s per 3200x2130 view
             tp = now_s();
@@ -593,9 +629,9 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
             }
             if (previous != (size_t)-1) finish_view(previous);
             t_sweep1 += now_s() - t_s1;
-            if (!barrier.wait()) return;                                             // every owner's map is in its table
+            if (!timed_wait()) return;                                             // every owner's map is in its table
             if (ndev > 1) pull(dtab);
-            if (!barrier.wait()) return;
+            if (!timed_wait()) return;
             const double t_g = now_s();
             for (int geom_iter = 0; geom_iter < 2; ++geom_iter) {                    // geometric sweeps
                 const bool multi_geometry = geom_iter > 0;
@@ -637,35 +673,42 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
                         const cv::Mat_<float> *prior_depth = &final_prior_depth[i];
                         writers.push_back(std::async(std::launch::async, [obj, ref_id, prior_depth, &dense_folder]() {
                             const int width = obj->GetReferenceImageWidth(), height = obj->GetReferenceImageHeight();
-                            cv::Mat_<float> depths = cv::Mat_<float>::zeros(height, width), costs = cv::Mat_<float>::zeros(height, width);
-                            cv::Mat_<cv::Vec3f> normals = cv::Mat_<cv::Vec3f>::zeros(height, width);
-                            for (int k = 0; k < width * height; ++k) {
-                                const float4 ph = obj->GetPlaneHypothesis(k);
-                                depths.ptr()[k] = ph.w;
-                                normals.ptr()[k] = cv::Vec3f(ph.x, ph.y, ph.z);
-                                costs.ptr()[k] = obj->GetCost(k);
+                            const size_t npx = (size_t)width * height;
+                            cv::Mat_<float> depths(height, width), costs(height, width);
+                            cv::Mat_<cv::Vec3f> normals(height, width);
+                            {
+                                // one pass over the pinned result, then the pinned buffers go back to the pool for the next
+                                // view's download (a page-locked allocation costs 20 - 100 ms): the files are written from the copies
+                                const float *ph = obj->PlanesHost();
+                                float *dd = depths.ptr();
+                                cv::Vec3f *nn = normals.ptr();
+                                for (size_t k = 0; k < npx; ++k) {
+                                    nn[k] = cv::Vec3f(ph[4 * k], ph[4 * k + 1], ph[4 * k + 2]);
+                                    dd[k] = ph[4 * k + 3];
+                                }
+                                std::memcpy(costs.ptr(), obj->CostsHost(), sizeof(float) * npx);
                             }
+                            obj->Park();
                             const std::string result_folder = result_folder_of(dense_folder, ref_id);
                             mkdir(result_folder.c_str(), 0777);
                             writeDepthDmb(result_folder + "/depths.dmb", *prior_depth);
                             writeDepthDmb(result_folder + "/depths_geom.dmb", depths);
                             writeNormalDmb(result_folder + "/normals.dmb", normals);
                             writeDepthDmb(result_folder + "/costs.dmb", costs);
-                            obj->Park();                       // the pinned result buffers serve the next view's download
                         }));
                         std::cout << "Processing image " << std::setw(8) << std::setfill('0') << problem.ref_image_id << " done!" << std::endl;
                     }
                     t_output += now_s() - tg;
                 }
                 if (!multi_geometry && ndev > 1) {
-                    if (!barrier.wait()) return;                                     // ExportDepthDevice waits for its copy
+                    if (!timed_wait()) return;                                     // ExportDepthDevice waits for its copy
                     pull(gtab);
-                    if (!barrier.wait()) return;
+                    if (!timed_wait()) return;
                 }
             }
             t_geom += now_s() - t_g;
             first_level = false;
-            if (!barrier.wait()) return;                                             // nobody overwrites a table somebody still reads
+            if (!timed_wait()) return;                                             // nobody overwrites a table somebody still reads
         }
         {
             const double tw = now_s();
@@ -676,6 +719,7 @@ bool RunResident(const std::string &dense_folder, std::vector<Problem> &problems
         g_gpu_ms += gpu_ms;
         g_t_ctx = std::max(g_t_ctx, t_ctx); g_t_upload = std::max(g_t_upload, t_upload); g_t_support = std::max(g_t_support, t_support);
         g_t_prior_dev = std::max(g_t_prior_dev, t_prior_dev);
+        g_t_barrier = std::max(g_t_barrier, t_barrier);
         g_t_load = std::max(g_t_load, t_load); g_t_views = std::max(g_t_views, t_views); g_t_run = std::max(g_t_run, t_run);
         g_t_export = std::max(g_t_export, t_export); g_t_output = std::max(g_t_output, t_output); g_t_join = std::max(g_t_join, t_join);
         g_t_sweep1 = std::max(g_t_sweep1, t_sweep1); g_t_geom = std::max(g_t_geom, t_geom); g_t_exchange = std::max(g_t_exchange, t_exchange);
@@ -837,7 +881,7 @@ int main(int argc, char **argv)
     }
     std::cout << "{\"mode\": \"" << (resident ? "resident" : "files") << "\", \"gpu_prior\": " << g_gpu_prior << ", \"views\": " << num_images << ", \"wall_s\": " << wall_patchmatch << ", \"kernel_ms\": " << g_gpu_ms
               << ", \"prior_cpu_s\": " << g_prior_s << ", \"load_s\": " << g_t_load << ", \"views_s\": " << g_t_views << ", \"run_s\": " << g_t_run
-              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"setup_s\": " << g_t_setup << ", \"ctx_s\": " << g_t_ctx << ", \"upload_s\": " << g_t_upload
+              << ", \"export_s\": " << g_t_export << ", \"output_s\": " << g_t_output << ", \"join_s\": " << g_t_join << ", \"barrier_s\": " << g_t_barrier << ", \"setup_s\": " << g_t_setup << ", \"ctx_s\": " << g_t_ctx << ", \"upload_s\": " << g_t_upload
               << ", \"support_s\": " << g_t_support << ", \"prior_dev_s\": " << g_t_prior_dev << ", \"sweep1_s\": " << g_t_sweep1 << ", \"geom_s\": " << g_t_geom
               << ", \"gpus\": " << (resident ? g_devices_used : 1) << ", \"exchange_s\": " << g_t_exchange
               << ", \"fusion_s\": " << fusion_s << ", \"fusion_kernel_ms\": " << fusion_kernel_ms << ", \"fusion_points\": " << fusion_points << "}" << std::endl;

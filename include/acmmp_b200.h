@@ -128,6 +128,10 @@ int acmmp_park(acmmp_ctx *ctx, int keep_prior, int keep_host_result);
  * device is destroyed.  acmmp_pool_alloc / acmmp_pool_free: device buffers of the host (image pool, depth-map tables) out
  * of the same pool; a block handed out keeps the pool alive like a context does.  Thread-safe. */
 int acmmp_reserve_device_memory(int device, size_t bytes);
+/* One page-locked host block of exactly `bytes` into the device's pool, ahead of time: the result buffers of
+ * acmmp_download_result / acmmp_run_patch_match are 16 and 4 bytes per pixel, and a page-locked allocation in the middle
+ * of a multi-threaded run costs 20 - 100 ms. */
+int acmmp_reserve_pinned(int device, size_t bytes);
 int acmmp_pool_alloc(int device, size_t bytes, void **out);
 int acmmp_pool_free(int device, void *p);
 
