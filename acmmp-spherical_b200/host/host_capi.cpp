@@ -128,6 +128,15 @@ int acmmp_host_load_grey(const char *dense_folder, int id, float *dst, int cap, 
     return 0;
 }
 
+// ImageSize: the size of a view's image from the file header (images/%08d.pgm or .jpg)
+int acmmp_host_image_size(const char *dense_folder, int id, int *w, int *h)
+{
+    int cols = 0, rows = 0;
+    if (!ImageSize(dense_folder, id, cols, rows)) return -1;
+    *w = cols; *h = rows;
+    return 0;
+}
+
 int acmmp_host_pair_count(const char *dense_folder)
 {
     std::vector<Problem> problems;

@@ -340,3 +340,24 @@ def test_colour_image_loader_reads_ppm_twins_in_opencv_channel_order(host, tmp_p
         w, h = C.c_int(), C.c_int()
         assert host.acmmp_host_load_colour(str(tmp_path).encode(), view, got.ctypes.data_as(u8), got.size, C.byref(w), C.byref(h)) == 0
         assert (w.value, h.value) == (31, 23) and np.array_equal(got, want)
+
+
+def test_image_size_comes_from_the_file_header(host, tmp_path):
+    """ImageSize (main.cpp:35-71 asks cv::imread for it) reads the PGM header or scans the JPEG for its frame header --
+    also behind a large application segment (EXIF with a thumbnail), which lies beyond the first read."""
+    import cv2
+    rng = np.random.default_rng(7)
+    (tmp_path / "images").mkdir()
+    cv2.imwrite(str(tmp_path / "images" / "00000000.pgm"), rng.integers(0, 256, (37, 91), dtype=np.uint8))
+    cv2.imwrite(str(tmp_path / "images" / "00000001.jpg"), rng.integers(0, 256, (53, 131, 3), dtype=np.uint8))
+    ok, enc = cv2.imencode(".jpg", rng.integers(0, 256, (45, 77), dtype=np.uint8))
+    raw = enc.tobytes()
+    # five APP1 segments of 65 533 payload bytes each between SOI and the rest: the frame header sits past 256 KB
+    app1 = b"\xff\xe1" + (65535).to_bytes(2, "big") + bytes(65533)
+    (tmp_path / "images" / "00000002.jpg").write_bytes(raw[:2] + app1 * 5 + raw[2:])
+    assert cv2.imread(str(tmp_path / "images" / "00000002.jpg"), cv2.IMREAD_GRAYSCALE).shape == (45, 77)
+    for view, (w, h) in enumerate([(91, 37), (131, 53), (77, 45)]):
+        cw, ch = C.c_int(), C.c_int()
+        assert host.acmmp_host_image_size(str(tmp_path).encode(), view, C.byref(cw), C.byref(ch)) == 0
+        assert (cw.value, ch.value) == (w, h)
+    assert host.acmmp_host_image_size(str(tmp_path).encode(), 9, C.byref(cw), C.byref(ch)) != 0
