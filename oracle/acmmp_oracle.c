@@ -1018,3 +1018,89 @@ void orc_checkerboard_pass(int n_images, const orc_image *imgs, const orc_image 
     pass_args a = {&pc, colour, iter, planes_in, costs_in, planes_out, costs_out, pre_costs, selected_views, rand6, prior_planes4, plane_masks};
     par_rows(H, pass_row, &a);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * fusion: SimpleFusionKernel, ACMMP.cu:1664-1814, one reference view on the CPU
+ * ---------------------------------------------------------------------------------------------- */
+/* tex2D<float4>(image, c, r) of a LINEAR-filtered texture with un-normalised coordinates at an integer coordinate
+ * (no half-texel offset): the sample point lies on the corner shared by the texels (c-1 .. c) x (r-1 .. r), both bilinear
+ * fractions are exactly 0.5, addressing clamps (ACMMP.cu:1966-1972) => the mean of the four texels.  Texels are
+ * value / 255 (convertTo(CV_32FC4, 1 / 255), :1955); the kernel multiplies back by 255 (:1704-1708). */
+static float fuse_texel_mean(const float *gray, const unsigned char *bgr, int channel, int w, int h, int c, int r)
+{
+    const int c0 = c - 1 < 0 ? 0 : (c - 1 > w - 1 ? w - 1 : c - 1), c1 = c < 0 ? 0 : (c > w - 1 ? w - 1 : c);
+    const int r0 = r - 1 < 0 ? 0 : (r - 1 > h - 1 ? h - 1 : r - 1), r1 = r < 0 ? 0 : (r > h - 1 ? h - 1 : r);
+    const int at[4] = {r0 * w + c0, r0 * w + c1, r1 * w + c0, r1 * w + c1};
+    float sum = 0.0f;
+    for (int k = 0; k < 4; ++k) {
+        const float level = bgr ? (float)bgr[3 * at[k] + channel] : gray[at[k]];
+        sum += (float)(level * (1.0 / 255.0));
+    }
+    return 0.25f * sum * 255.0f;
+}
+
+/* depths[i]: w_i * h_i, normals3[i]: w_i * h_i * 3 (world frame), gray[i]: grey levels 0..255, bgr (may be NULL) / bgr[i]
+ * (may be NULL): 3 bytes per pixel in OpenCV's B, G, R order; cams[i].width / height = the maps' size.
+ * points: w * h * 9 floats (PointList: coord, normal, color -- color in the kernel's order, which is B, G, R: its texels
+ * are RGBA after cvtColor(BGR2RGBA) and it sums .z first, :1704-1708), written where flags[idx] = 1. */
+void orc_fuse_view(int n_views, const orc_camera *cams, const float *const *depths, const float *const *normals3,
+                   const float *const *gray, const unsigned char *const *bgr, int ref, int n_src, const int *src_idx,
+                   float *points, int *flags)
+{
+    const orc_camera *rc = &cams[ref];
+    const int width = rc->width, height = rc->height;
+    (void)n_views;
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < height; ++r)
+        for (int c = 0; c < width; ++c) {
+            const int idx = r * width + c;
+            flags[idx] = 0;
+            const float ref_depth = depths[ref][idx];                       /* point-sampled at (c, r): texel (c, r) */
+            if (ref_depth <= 0.0f) continue;
+            float X[3];
+            orc_point_on_world((float)c, (float)r, ref_depth, rc, X);
+            const float *rn = normals3[ref] + 3 * idx;
+            float psum[3] = {X[0], X[1], X[2]}, nsum[3] = {rn[0], rn[1], rn[2]}, csum[3];
+            const unsigned char *rb = bgr ? bgr[ref] : 0;
+            for (int k = 0; k < 3; ++k) csum[k] = fuse_texel_mean(gray[ref], rb, k, width, height, c, r);
+            int num = 1;
+            for (int j = 0; j < n_src && j < 32; ++j) {
+                const int s = src_idx[j];
+                if (s < 0) continue;
+                const orc_camera *sc = &cams[s];
+                float pp[2], pd;
+                orc_project(X, sc, pp, &pd);
+                const int src_c = (int)(pp[0] + 0.5f), src_r = (int)(pp[1] + 0.5f);
+                if (src_c < 0 || src_c >= sc->width || src_r < 0 || src_r >= sc->height) continue;
+                const int sidx = src_r * sc->width + src_c;
+                const float src_depth = depths[s][sidx];
+                if (src_depth <= 0.0f) continue;
+                float Xs[3], rp[2], dummy;
+                orc_point_on_world((float)src_c, (float)src_r, src_depth, sc, Xs);
+                orc_project(Xs, rc, rp, &dummy);
+                const float reproj_error = hypotf((float)c - rp[0], (float)r - rp[1]);
+                const float relative_depth_diff = fabsf(pd - src_depth) / src_depth;
+                const float *sn = normals3[s] + 3 * sidx;
+                float dot = rn[0] * sn[0] + rn[1] * sn[1] + rn[2] * sn[2];
+                dot = fmaxf(-1.0f, fminf(1.0f, dot));
+                const float angle = acosf(dot);
+                if (reproj_error < 1.0 && relative_depth_diff < 0.01f && angle < 0.149f) {
+                    for (int k = 0; k < 3; ++k) { psum[k] += Xs[k]; nsum[k] += sn[k]; }
+                    const unsigned char *sb = bgr ? bgr[s] : 0;
+                    for (int k = 0; k < 3; ++k) csum[k] += fuse_texel_mean(gray[s], sb, k, sc->width, sc->height, src_c, src_r);
+                    num++;
+                }
+            }
+            if (num < 3) continue;
+            float *o = points + 9 * (size_t)idx;
+            float n[3] = {nsum[0] / num, nsum[1] / num, nsum[2] / num};
+            const float len = hypotf(hypotf(n[0], n[1]), n[2]);
+            if (len > 0.0f) { n[0] /= len; n[1] /= len; n[2] /= len; }
+            for (int k = 0; k < 3; ++k) {
+                o[k] = psum[k] / num;
+                o[3 + k] = n[k];
+                o[6 + k] = csum[k] / num;
+            }
+            flags[idx] = 1;
+        }
+}

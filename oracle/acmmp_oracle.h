@@ -70,6 +70,11 @@ void orc_checkerboard_pass(int n_images, const orc_image *imgs, const orc_image 
                            const uint32_t *plane_masks);
 
 /* planar-prior pass only: emulate the other extreme of the reference's data race (see acmmp_oracle.c) */
+/* SimpleFusionKernel, ACMMP.cu:1664-1814, one reference view; points = w*h*9 floats (coord, normal, color in the kernel's
+ * B, G, R order), flags = w*h ints; bgr (or bgr[i]) may be NULL: the grey level serves all three channels */
+void orc_fuse_view(int n_views, const orc_camera *cams, const float *const *depths, const float *const *normals3,
+                   const float *const *gray, const unsigned char *const *bgr, int ref, int n_src, const int *src_idx,
+                   float *points, int *flags);
 void orc_set_race_emulation(const float *late_planes, float *center_planes_out);
 
 #ifdef __cplusplus

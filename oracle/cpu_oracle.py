@@ -226,3 +226,27 @@ def prior_pass_race(images, cams, state, colour, it, prior_planes, plane_masks, 
     a, b = early["planes"], late["planes"]
     sensitive = ~np.all((np.abs(a - b) <= 1e-6 + 1e-6 * np.abs(b)) | (np.isnan(a) & np.isnan(b)), axis=-1)
     return early, late, sensitive
+
+
+def fuse_view(cams, depths, normals, grays, ref, src_indices, colours=None):
+    """SimpleFusionKernel (ACMMP.cu:1664-1814) for one reference view -> (points [h, w, 9], flags [h, w] bool).
+    cams: cameras with width / height = the maps' size; colours: optional uint8 [h, w, 3] images in B, G, R order."""
+    n = len(cams)
+    carr = _cams(cams)
+    for i in range(n):
+        carr[i].width, carr[i].height = depths[i].shape[1], depths[i].shape[0]
+    d = [_f32(x) for x in depths]
+    nm = [_f32(x) for x in normals]
+    g = [_f32(x) for x in grays]
+    FP, BP = C.POINTER(C.c_float), C.POINTER(C.c_ubyte)
+    bgr = None
+    if colours is not None:
+        keep = [np.ascontiguousarray(x, np.uint8) for x in colours]
+        bgr = (BP * n)(*[x.ctypes.data_as(BP) for x in keep])
+    h, w = d[ref].shape
+    pts = np.zeros((h, w, 9), np.float32)
+    flags = np.zeros((h, w), np.int32)
+    src = (C.c_int * len(src_indices))(*[int(s) for s in src_indices])
+    lib().orc_fuse_view(C.c_int(n), carr, (FP * n)(*[_fp(x) for x in d]), (FP * n)(*[_fp(x) for x in nm]), (FP * n)(*[_fp(x) for x in g]),
+                        bgr, C.c_int(ref), C.c_int(len(src_indices)), src, _fp(pts), flags.ctypes.data_as(C.POINTER(C.c_int)))
+    return pts, flags.astype(bool)

@@ -8,6 +8,7 @@ Tolerances: the reference is built with --use_fast_math and reads images through
 Integer work (XORWOW states, view bit masks) must match exactly.
 """
 import ctypes as C
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -161,3 +162,31 @@ def test_prior_pass_gap_is_the_references_data_race(model):
     assert res["early_on_insensitive"] >= floor - 0.03, res          # measured: 0.993 vs 0.991 (pinhole), 0.942 vs 0.965 (sphere)
     assert res["either"] >= res["early"] + 0.04, res                 # measured: 0.970 vs 0.921, 0.920 vs 0.845
     assert res["early_on_sensitive"] < res["early_on_insensitive"] - 0.1, res
+
+
+@pytest.mark.parametrize("model", ["pinhole", "sphere"])
+def test_fusion_restatement_against_reference_vectors(model):
+    """orc_fuse_view (SimpleFusionKernel, ACMMP.cu:1664-1814, restated in C) against what the compiled reference kernel
+    produced on a B200 for the same inputs (tests/golden/make_fusion_golden.py): the same pixels yield a point -- apart from
+    pixels that sit on one of the three consistency thresholds, where libm's acos / hypot and the device's differ in the
+    last bits --, coordinates, normals and colours agree to 1e-4, with grey and with three-channel colour images."""
+    sys.path.insert(0, str(GOLD))
+    from make_fusion_golden import inputs
+    from oracle import cpu_oracle
+    scene, depths, normals, colours = inputs(model)
+    gold = np.load(GOLD / f"golden_fusion_{model}.npz")
+    for tag, col in (("grey", None), ("colour", colours)):
+        for r in (0, 2):
+            pts, flags = cpu_oracle.fuse_view(scene.cams, depths, normals, scene.images, r, list(scene.pairs[r][1]), colours=col)
+            want_pts, want_flags = gold[f"{tag}_view{r}_points"], gold[f"{tag}_view{r}_flags"].astype(bool)
+            assert want_flags.sum() > 1000
+            assert (flags == want_flags).mean() >= 0.9995, (tag, r, (flags == want_flags).mean())
+            both = flags & want_flags
+            scale = np.abs(want_pts[both][:, :3]).max()
+            # (a pixel where ONE source view sits on a threshold keeps its point but averages over one view more or less:
+            # a handful per ten thousand)
+            assert (np.abs(pts[both][:, :3] - want_pts[both][:, :3]) <= 1e-4 * scale).all(axis=1).mean() >= 0.9995
+            assert (np.abs(pts[both][:, 3:6] - want_pts[both][:, 3:6]) <= 1e-4).all(axis=1).mean() >= 0.9995
+            assert (np.abs(pts[both][:, 6:] - want_pts[both][:, 6:]) <= 0.05).all(axis=1).mean() >= 0.9995
+            if col is not None:                                   # three different channels, in the kernel's B, G, R order
+                assert np.abs(want_pts[both][:, 6] - want_pts[both][:, 8]).mean() > 10
