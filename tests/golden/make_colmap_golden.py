@@ -19,6 +19,9 @@ ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT / "acmmp-spherical_b200"))
 REFERENCE = Path("/root/reference/colmap2mvsnet_acm.py")
 ARGS = ["--top_k", "4", "--min_shared", "5", "--theta0", "1.0", "--max_d", "192"]
+# a second set that takes the other branches: plane count from the one-pixel baseline (--max_d 0), pairs dropped by the
+# triangulation-angle test and by the shared-track floor, an interval scale
+ARGS_STRICT = ["--top_k", "3", "--min_shared", "60", "--theta0", "6.0", "--max_d", "0", "--interval_scale", "2"]
 
 
 def rotmat_to_qvec(R):
@@ -138,12 +141,12 @@ def main():
         for (iid, q, t, cid, fname, o), img in zip(images, scene.images):
             small = cv2.resize(img.astype(np.uint8), (32, 24))                 # the converter only copies / re-encodes them
             cv2.imwrite(str(dense / "images" / fname), small)
-        for ext in (".txt", ".bin"):
+        for ext, args, sub in ((".txt", ARGS, "expected"), (".bin", ARGS, "expected_bin"), (".txt", ARGS_STRICT, "expected_strict")):
             with tempfile.TemporaryDirectory() as tmp:
-                r = subprocess.run([sys.executable, str(REFERENCE), "--dense_folder", str(dense), "--save_folder", tmp, "--model_ext", ext] + ARGS,
+                r = subprocess.run([sys.executable, str(REFERENCE), "--dense_folder", str(dense), "--save_folder", tmp, "--model_ext", ext] + args,
                                    capture_output=True, text=True)
                 assert r.returncode == 0, r.stderr[-2000:]
-                exp = out / ("expected" + ("" if ext == ".txt" else "_bin"))
+                exp = out / sub
                 shutil.copytree(os.path.join(tmp, "cams"), exp / "cams")
                 shutil.copyfile(os.path.join(tmp, "pair.txt"), exp / "pair.txt")
                 (exp / "images.lst").write_text("\n".join(sorted(os.listdir(os.path.join(tmp, "images")))) + "\n")
