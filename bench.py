@@ -29,7 +29,7 @@ Workloads (BASELINE.json configs):
 
 C2 / C4: the CPU planar-prior stage (Delaunay etc., reference ACMMP.cpp:904-1011) is out of scope for both arms: it runs
 once per level during warm-up and its output is re-used in the timed steps; its time is reported separately
-(`prior_cpu_s`).  `e2e_driver` (C2, N = 1) is the prior-INCLUSIVE number: the C++ driver `lib/acmmp_b200 --resident 1
+(`prior_cpu_s`).  `e2e_driver` (C2 / C4, N = 1) is the prior-INCLUSIVE number: the C++ driver `lib/acmmp_b200 --resident 1
 --gpu-prior 1` on an 11-view dense folder of the same shape, seconds per view of its own wall clock (image files in, .dmb
 files out).  Data are synthetic (acmmp_b200/synth.py), neighbour depth maps that no rank computes are rendered stand-ins.
 """
@@ -298,7 +298,7 @@ def driver_leg(cfg, scene, ids, device):
     import tempfile
     from acmmp_b200 import synth
     driver = ROOT / "acmmp-spherical_b200" / "lib" / "acmmp_b200"
-    if not driver.exists() or cfg["model"] != "pinhole":
+    if not driver.exists():
         return None
     sub = synth.Scene(scene.model, [scene.images[i] for i in ids], [scene.cams[i] for i in ids], [scene.depths_gt[i] for i in ids],
                       [(k, [j for j in range(len(ids)) if j != k][: cfg["n_src"]]) for k in range(len(ids))],
@@ -644,7 +644,7 @@ def run_views(a, cfg, rank, local_rank, world, use_dist, json_fd):
                                 "samples per second over the 1.29 ps/sample special-function roofline"}
                 except Exception as e:
                     line["sphere_tap_pruning"] = {"error": str(e)[:200]}
-            if not a.no_driver_leg and n_gpus == 1 and a.config == "C2":
+            if not a.no_driver_leg and n_gpus == 1 and a.config in ("C2", "C4"):
                 try:
                     ctx.close()
                     line["e2e_driver"] = driver_leg(cfg, scene, ids, local_rank)

@@ -1,8 +1,7 @@
 #!/bin/bash
-python -m pytest tests/test_gpu_cpp_driver.py tests/test_gpu_edge_cases.py -m gpu -q -k "cpp_driver or reserved or parked" 2>&1 | tail -6 > gpurun_out/try3.log; tail -3 gpurun_out/try3.log | cut -c1-600
-python tools/driver_bench.py --views 11 --skip-files --out gpurun_out/r2ab_driver.json > gpurun_out/r2ab_driver.log 2>&1; echo "driver rc=$?"
+python bench.py --config C4 --steps 3 --warmup 3 > gpurun_out/r2ac_bench_c4.json 2> gpurun_out/r2ac_bench_c4.err; echo "c4 rc=$?"
 python - <<'PY'
 import json
-d=json.load(open("gpurun_out/r2ab_driver.json"))
-e=d["resident_gpu_prior"]; print(e["s_per_view"], {x:e.get(x) for x in ("wall_s","setup_s","views_s","run_s","output_s","sweep1_s","geom_s","fusion_s","process_wall_s")})
+d=json.loads(open("gpurun_out/r2ac_bench_c4.json").read().replace("NaN","null"))
+print({k:d.get(k) for k in ("value","ms_per_step")}, "e2e", d["e2e"]["value"], d["roofline"]["frac"], d.get("e2e_driver"))
 PY
